@@ -1,0 +1,24 @@
+# Top-level build: CUDA library (sm_100a only), synthetic workload generator, oracle.
+NVCC    ?= /usr/local/cuda/bin/nvcc
+CC      ?= gcc
+ARCH    := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC    := msamtools_b200/csrc
+LIB     := msamtools_b200/libmsamtools_b200.so
+SYNTH   := msamtools_b200/libmsamsynth.so
+
+all: $(LIB) $(SYNTH) oracle
+
+$(LIB): $(CSRC)/api.cu $(wildcard $(CSRC)/*.cuh) include/msamtools_b200.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/api.cu -ldl
+
+$(SYNTH): $(CSRC)/synth.c
+	$(CC) -O2 -g -std=gnu99 -Wall -Wextra -fPIC -shared -o $@ $< -lm
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -f $(LIB) $(SYNTH); $(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

@@ -1,0 +1,801 @@
+// api.cu -- context, chunk pipeline and the extern "C" surface of libmsamtools_b200.so
+// (include/msamtools_b200.h).  Host orchestration only; all record work is in the kernels.
+#include "../../include/msamtools_b200.h"
+#include "common.cuh"
+#include "scan.cuh"
+#include "decode.cuh"
+#include "besthit.cuh"
+#include "profile.cuh"
+#include "coverage.cuh"
+#include "gather.cuh"
+
+#include <nccl.h>        // types only; the library itself is dlopen'ed (no link-time dependency)
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace msg;
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct CsrChunk { uint32_t *off = nullptr; int32_t *fid = nullptr; uint32_t nlists = 0, nent = 0; };
+
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err) {
+        if (h) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        for (int i = 0; names[i] && !h; i++) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl is missing required symbols"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+} // namespace
+
+struct msg_ctx {
+    msg_config cfg;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    bool has_filter = false, need_stats = false, cov_fused = false;
+    uint32_t decode_mode = 0;
+
+    // static tables
+    int32_t *d_fmap = nullptr; uint32_t *d_tlen = nullptr; uint64_t *d_covbase = nullptr;
+    uint64_t cov_cells = 0;
+
+    // chunk staging (msg_push) and per-chunk columns
+    DevBuf raw, off, tid, fb, score, hash, nid, st_alen, st_qlen, st_qclip, st_edit;
+    DevBuf segcnt, segbase, out_idx, tile_sums, pcount, scanv, biglist;
+    DevBuf out_len, out_off, plan, out_rec;
+    const uint8_t *cur_raw = nullptr; const uint64_t *cur_off = nullptr;
+    uint64_t cur_n = 0, cur_nbytes = 0;
+    uint64_t n_kept = 0; bool have_stream = false;   // have_stream: out_idx valid (else identity)
+    uint64_t out_bytes = 0;
+
+    // device scalars: err[2], scan totals, accounting
+    uint32_t *d_err = nullptr;                 // [0] flags [1] first bad record
+    unsigned long long *d_acct = nullptr;      // [0] alg bytes [1] slow records
+    void *d_total = nullptr;                   // 16 bytes scratch for scan totals
+
+    // profile accumulators
+    uint32_t *d_ui = nullptr; double *d_d = nullptr; uint32_t *d_counters = nullptr;   // counters[8]
+    std::vector<CsrChunk> csr;
+    uint32_t *d_stamp = nullptr; uint32_t stamp_next = 0;
+    double *d_U = nullptr, *d_a = nullptr, *d_inc = nullptr, *d_partial = nullptr, *d_delta = nullptr;
+    uint32_t *d_purged = nullptr;
+
+    // coverage accumulators
+    int32_t *d_diff = nullptr, *d_depth = nullptr; uint8_t *d_covered = nullptr;
+    unsigned long long *d_touched = nullptr; long long *d_sum = nullptr;
+    bool cov_finished = false;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+
+    // timing
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_decode, ev_total;
+    std::vector<cudaEvent_t> ev_free;
+    cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double decode_ms = 0, total_ms = 0; uint64_t decode_launches = 0, kernel_launches = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
+};
+
+namespace {
+
+int fail(msg_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+    return fail(c, e__ == cudaErrorMemoryAllocation ? MSG_ENOMEM : MSG_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); } while (0)
+#define NC(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) \
+    return fail(c, MSG_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error"); } while (0)
+#define LAUNCHED(c) do { (c)->kernel_launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
+    return fail(c, MSG_ECUDA, "kernel launch failed (%s:%d): %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } while (0)
+
+inline uint32_t nblocks(uint64_t n, uint32_t per) { return (uint32_t)((n + per - 1) / per); }
+
+cudaEvent_t get_event(msg_ctx *c)
+{
+    if (!c->ev_free.empty()) { cudaEvent_t e = c->ev_free.back(); c->ev_free.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+void harvest_events(msg_ctx *c)
+{   // stream must be idle
+    for (auto &pr : c->ev_decode) { float ms = 0; cudaEventElapsedTime(&ms, pr.first, pr.second); c->decode_ms += ms; c->decode_launches++;
+                                    c->ev_free.push_back(pr.first); c->ev_free.push_back(pr.second); }
+    for (auto &pr : c->ev_total)  { float ms = 0; cudaEventElapsedTime(&ms, pr.first, pr.second); c->total_ms += ms;
+                                    c->ev_free.push_back(pr.first); c->ev_free.push_back(pr.second); }
+    c->ev_decode.clear(); c->ev_total.clear();
+}
+
+// exclusive scan driver: in -> out functor, total (T) left in c->d_total
+template <class T, class In, class Out>
+int run_scan(msg_ctx *c, In in, Out out, uint64_t n, T *h_total)
+{
+    uint32_t ntiles = nblocks(n, SCAN_TILE);
+    if (ntiles == 0) { if (h_total) *h_total = T(0); return MSG_OK; }
+    CU(c->tile_sums.reserve((size_t)ntiles * sizeof(T)));
+    T *ts = c->tile_sums.as<T>();
+    scan_reduce_kernel<T, In><<<ntiles, SCAN_BLOCK, 0, c->stream>>>(in, n, ts); LAUNCHED(c);
+    scan_tiles_kernel<T><<<1, SCAN_BLOCK, 0, c->stream>>>(ts, ntiles, reinterpret_cast<T *>(c->d_total)); LAUNCHED(c);
+    scan_apply_kernel<T, In, Out><<<ntiles, SCAN_BLOCK, 0, c->stream>>>(in, out, n, ts); LAUNCHED(c);
+    if (h_total) {
+        CU(cudaMemcpyAsync(h_total, c->d_total, sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += sizeof(T);
+    }
+    return MSG_OK;
+}
+
+int check_device_errors(msg_ctx *c)
+{
+    uint32_t h[2];
+    CU(cudaMemcpyAsync(h, c->d_err, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += sizeof h;
+    if (h[0] & DERR_FORMAT) return fail(c, MSG_EFORMAT, "malformed BAM record or reference id out of range (first near record %u)", h[1]);
+    if (h[0] & DERR_NOTAG)  return fail(c, MSG_ENOTAG, "Either NM or MD must be present in SAM/BAM input for 'filter' command. Type 'msamtools filter -h' for details.");
+    if (h[0] & DERR_NOAS)   return fail(c, MSG_ENOAS, "Required field AS not found in SAM/BAM input. Type 'msamtools -h' for details.");
+    return MSG_OK;
+}
+
+int profile_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
+{
+    const msg_config &g = c->cfg;
+    const uint64_t n = c->cur_n;
+    if (m == 0) return MSG_OK;
+    // QNAME run ids over ALL records of the chunk (inclusive count of run heads)
+    CU(c->nid.reserve(n * 4));
+    int rc = run_scan<uint32_t>(c, InFlagBit{c->fb.as<uint32_t>(), FB_EQPREV, 0u}, OutInclU32{c->nid.as<uint32_t>()}, n, (uint32_t *)nullptr);
+    if (rc) return rc;
+
+    const bool prop = g.share_type == MSG_MULTI_PROPORTIONAL;
+    if (prop) CU(c->pcount.reserve(m * 4));
+    const uint32_t big_cap = 65536;
+    CU(c->biglist.reserve((size_t)big_cap * 4));
+    ProfParams p;
+    p.raw = c->cur_raw; p.off = c->cur_off; p.stream = stream; p.m = m;
+    p.tid = c->tid.as<int32_t>(); p.nid = c->nid.as<uint32_t>(); p.hash = c->hash.as<uint32_t>();
+    p.fmap = c->d_fmap; p.n_targets = g.n_targets; p.n_features = g.n_features; p.share_type = g.share_type;
+    p.ui = c->d_ui; p.d = c->d_d; p.counters = c->d_counters;
+    p.pcount = prop ? c->pcount.as<uint32_t>() : nullptr;
+    p.big = c->biglist.as<uint32_t>(); p.big_cap = big_cap; p.big_threshold = 1024; p.err = c->d_err;
+    profile_count_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(p); LAUNCHED(c);
+
+    uint32_t nbig = 0;
+    if (prop) {
+        CU(c->scanv.reserve(m * 8));
+        unsigned long long tot = 0;
+        rc = run_scan<unsigned long long>(c, InPcountPacked{p.pcount}, OutExclU64{c->scanv.as<unsigned long long>()}, m, &tot);
+        if (rc) return rc;
+        CsrChunk ch; ch.nlists = (uint32_t)(tot >> 32); ch.nent = (uint32_t)tot;
+        if (ch.nlists) {
+            CU(cudaMalloc(&ch.off, ((size_t)ch.nlists + 1) * 4));
+            CU(cudaMalloc(&ch.fid, (size_t)ch.nent * 4));
+            c->csr.push_back(ch);
+            profile_fill_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(p, c->scanv.as<unsigned long long>(), ch.off, ch.fid); LAUNCHED(c);
+            CU(cudaMemcpyAsync(ch.off + ch.nlists, &c->csr.back().nent, 4, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    CU(cudaMemcpyAsync(&nbig, c->d_counters + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += 4;
+    if (nbig) {
+        if (nbig > big_cap) return fail(c, MSG_ERANGE, "more than %u oversized QNAME groups in one chunk", big_cap);
+        if (!c->d_stamp) { CU(cudaMalloc(&c->d_stamp, (size_t)(g.n_features > 0 ? g.n_features : 1) * 4));
+                           CU(cudaMemsetAsync(c->d_stamp, 0, (size_t)(g.n_features > 0 ? g.n_features : 1) * 4, c->stream)); }
+        uint32_t *d_tot = reinterpret_cast<uint32_t *>(c->d_total);
+        profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, nullptr, nullptr, d_tot, 0); LAUNCHED(c);
+        c->stamp_next += nbig + 1;
+        if (prop) {
+            uint32_t tot[2];
+            CU(cudaMemcpyAsync(tot, d_tot, 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (tot[0]) {
+                CsrChunk ch; ch.nlists = tot[0]; ch.nent = tot[1];
+                CU(cudaMalloc(&ch.off, ((size_t)ch.nlists + 1) * 4));
+                CU(cudaMalloc(&ch.fid, ((size_t)ch.nent + 1) * 4));
+                c->csr.push_back(ch);
+                profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, ch.off, ch.fid, d_tot, 1); LAUNCHED(c);
+                c->stamp_next += nbig + 1;
+            }
+        }
+        CU(cudaMemsetAsync(c->d_counters + 3, 0, 4, c->stream));
+    }
+    return MSG_OK;
+}
+
+int records_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
+{
+    c->out_bytes = 0;
+    if (m == 0) return MSG_OK;
+    CU(c->out_len.reserve(m * 4)); CU(c->out_off.reserve(m * 8)); CU(c->plan.reserve(m * sizeof(GatherPlan)));
+    const int rescore = c->cfg.do_filter && c->cfg.rescore;
+    gather_plan_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(c->cur_raw, c->cur_off, stream, m, rescore,
+                                                              c->out_len.as<uint32_t>(), c->plan.as<GatherPlan>()); LAUNCHED(c);
+    unsigned long long tot = 0;
+    int rc = run_scan<unsigned long long>(c, InLenU64{c->out_len.as<uint32_t>()}, OutExclU64{c->out_off.as<unsigned long long>()}, m, &tot);
+    if (rc) return rc;
+    CU(c->out_rec.reserve(tot + 16));
+    gather_copy_kernel<<<nblocks(m * 32, 256), 256, 0, c->stream>>>(c->cur_raw, c->cur_off, stream, m, c->out_off.as<unsigned long long>(),
+                                                                   c->out_len.as<uint32_t>(), c->plan.as<GatherPlan>(),
+                                                                   c->score.as<int32_t>(), c->out_rec.as<uint8_t>()); LAUNCHED(c);
+    c->out_bytes = tot;
+    return MSG_OK;
+}
+
+int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readable, const uint64_t *d_off, uint64_t n)
+{
+    const msg_config &g = c->cfg;
+    if (n >= 0xffffffffull) return fail(c, MSG_EINVAL, "a chunk may hold at most 2^32-2 records");
+    c->cur_raw = d_raw; c->cur_off = d_off; c->cur_n = n; c->cur_nbytes = nbytes;
+    c->n_kept = 0; c->have_stream = false; c->out_bytes = 0;
+    if (n == 0) return MSG_OK;
+
+    cudaEvent_t t0 = get_event(c), t1 = get_event(c), k0 = get_event(c), k1 = get_event(c);
+    CU(cudaEventRecord(t0, c->stream));
+
+    const bool hit = g.do_filter && g.hit_mode != MSG_HIT_NONE;
+    const bool need_score = hit || g.want_stats || (g.do_filter && g.rescore && g.want_records);
+    CU(c->tid.reserve(n * 4)); CU(c->fb.reserve(n * 4));
+    if (need_score) CU(c->score.reserve(n * 4));
+    if (g.want_profile) CU(c->hash.reserve(n * 4));
+    if (g.want_stats) { CU(c->st_alen.reserve(n * 4)); CU(c->st_qlen.reserve(n * 4)); CU(c->st_qclip.reserve(n * 4)); CU(c->st_edit.reserve(n * 4)); }
+
+    DecodeParams p;
+    memset(&p, 0, sizeof p);
+    p.raw = d_raw; p.off = d_off; p.n = n; p.nbytes_readable = readable;
+    p.tid = c->tid.as<int32_t>(); p.fb = c->fb.as<uint32_t>();
+    p.score = need_score ? c->score.as<int32_t>() : nullptr;
+    p.hash = g.want_profile ? c->hash.as<uint32_t>() : nullptr;
+    if (g.want_stats) { p.alen = c->st_alen.as<int32_t>(); p.qlen = c->st_qlen.as<int32_t>(); p.qclip = c->st_qclip.as<int32_t>(); p.edit = c->st_edit.as<int32_t>(); }
+    p.min_length = g.min_length; p.ppt = g.ppt; p.max_clip = g.max_clip;
+    uint32_t mode = c->decode_mode;
+    const bool need_stats = c->need_stats || g.want_stats;
+    if (need_stats) mode |= DM_NEED_STATS;
+    if (c->need_stats) mode |= DM_REQ_STATS;
+    if (need_stats || c->cov_fused) mode |= DM_NEED_CIGAR;
+    if (need_stats || (need_score && !(g.do_filter && g.rescore))) mode |= DM_NEED_AUX;
+    p.mode = mode;
+    p.diff = c->d_diff; p.covbase = c->d_covbase; p.tlen = c->d_tlen; p.covered = c->d_covered; p.n_targets = g.n_targets;
+    p.err = c->d_err; p.acct = c->d_acct;
+
+    CU(cudaEventRecord(k0, c->stream));
+    decode_kernel<<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); LAUNCHED(c);
+    CU(cudaEventRecord(k1, c->stream));
+    c->ev_decode.push_back({k0, k1});
+
+    // ---- filter stage -> stream of kept records in reference output order
+    const uint32_t *stream = nullptr; uint64_t m = n;
+    int rc = MSG_OK;
+    if (g.do_filter) {
+        CU(c->out_idx.reserve(n * 4));
+        uint32_t tot = 0;
+        if (!hit) {
+            rc = run_scan<uint32_t>(c, InFlagBit{p.fb, FB_INPOOL, FB_INPOOL}, OutCompact{c->out_idx.as<uint32_t>()}, n, &tot);
+            if (rc) return rc;
+        } else {
+            CU(c->segcnt.reserve(n * 4)); CU(c->segbase.reserve(n * 4));
+            BestHitParams bp{p.fb, p.score, c->segcnt.as<uint32_t>(), n, g.hit_mode == MSG_HIT_UNIQUE, c->d_err};
+            besthit_select_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(bp); LAUNCHED(c);
+            rc = run_scan<uint32_t>(c, InU32{c->segcnt.as<uint32_t>()}, OutExclU32{c->segbase.as<uint32_t>()}, n, &tot);
+            if (rc) return rc;
+            besthit_emit_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(p.fb, c->segcnt.as<uint32_t>(), c->segbase.as<uint32_t>(),
+                                                                         c->out_idx.as<uint32_t>(), n); LAUNCHED(c);
+        }
+        stream = c->out_idx.as<uint32_t>(); m = tot; c->have_stream = true;
+    }
+    c->n_kept = m;
+
+    if (g.want_profile) { rc = profile_stage(c, stream, m); if (rc) return rc; }
+    if (g.want_coverage && !c->cov_fused && m) {
+        coverage_stream_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(d_raw, d_off, stream, m, g.n_targets, c->d_diff, c->d_covbase,
+                                                                      c->d_tlen, c->d_covered, c->d_err); LAUNCHED(c);
+        c->cov_finished = false;
+    }
+    if (g.want_coverage) c->cov_finished = false;
+    if (g.want_records) { rc = records_stage(c, stream, m); if (rc) return rc; }
+
+    CU(cudaEventRecord(t1, c->stream));
+    c->ev_total.push_back({t0, t1});
+    return check_device_errors(c);
+}
+
+int allreduce(msg_ctx *c, void *buf, size_t count, ncclDataType_t dt, ncclRedOp_t op)
+{
+    if (c->cfg.n_ranks <= 1) return MSG_OK;
+    NC(g_nccl.AllReduce(buf, buf, count, dt, op, c->comm, c->stream));
+    return MSG_OK;
+}
+
+} // namespace
+
+// ================================================================================================
+extern "C" {
+
+int msg_abi_version(void) { return MSG_ABI_VERSION; }
+
+int msg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *msg_last_error(const msg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int msg_nccl_unique_id(void *id128)
+{
+    msg_ctx *c = nullptr;
+    std::string e;
+    if (!g_nccl.load(e)) return fail(c, MSG_ENCCL, "%s", e.c_str());
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return MSG_OK;
+}
+
+int msg_create(const msg_config *cfg, msg_ctx **out)
+{
+    msg_ctx *c = nullptr;
+    if (!cfg || !out) return fail(c, MSG_EINVAL, "null argument");
+    if (cfg->abi_version != MSG_ABI_VERSION) return fail(c, MSG_EINVAL, "ABI version mismatch (got %u, library %u)", cfg->abi_version, MSG_ABI_VERSION);
+    if (cfg->n_targets < 0 || cfg->n_features < 0) return fail(c, MSG_EINVAL, "negative n_targets/n_features");
+    if (cfg->want_profile && (cfg->share_type < 1 || cfg->share_type > 4)) return fail(c, MSG_EINVAL, "Do not understand share_type=%d", cfg->share_type);
+    if (cfg->want_coverage && !cfg->target_len) return fail(c, MSG_EINVAL, "want_coverage requires target_len");
+    if (cfg->do_filter && cfg->invert && cfg->hit_mode) return fail(c, MSG_EINVAL, "--invert cannot be combined with --besthit or --uniqhit");
+    if (cfg->hit_mode > MSG_HIT_UNIQUE) return fail(c, MSG_EINVAL, "bad hit_mode");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(c, MSG_ENODEV, "no CUDA device available (%s); libmsamtools_b200 has no CPU fallback", ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0"); }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(c, MSG_EINVAL, "device %d out of range (0..%d)", cfg->device, ndev - 1);
+    ce = cudaSetDevice(cfg->device);
+    if (ce != cudaSuccess) return fail(c, MSG_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(ce));
+
+    msg_ctx *ctx = new msg_ctx();
+    ctx->cfg = *cfg; ctx->cfg.fmap = nullptr; ctx->cfg.target_len = nullptr; ctx->cfg.nccl_unique_id = nullptr;
+    c = ctx;
+    const msg_config &g = ctx->cfg;
+#define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { int rc__ = fail(nullptr, e__ == cudaErrorMemoryAllocation ? MSG_ENOMEM : MSG_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); msg_destroy(ctx); return rc__; } } while (0)
+    CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->has_filter = g.do_filter && (g.min_length > 0 || g.ppt != 0 || g.max_clip < 100);        // msam_filter.c:79-81
+    ctx->need_stats = g.do_filter && (ctx->has_filter || g.rescore);                             // :104
+    ctx->cov_fused = g.want_coverage && !(g.do_filter && g.hit_mode != MSG_HIT_NONE);
+    uint32_t mode = 0;
+    if (g.do_filter) mode |= DM_DO_FILTER;
+    if (ctx->has_filter) mode |= DM_HAS_FILTER;
+    if (g.invert) mode |= DM_INVERT;
+    if (g.keep_unmapped) mode |= DM_KEEP_UNMAP;
+    if (g.do_filter && g.rescore) mode |= DM_RESCORE;
+    if (g.do_filter && g.hit_mode) mode |= DM_NEED_AS;
+    if (g.want_profile) mode |= DM_WANT_HASH;
+    if (ctx->cov_fused) mode |= DM_COV_FUSED;
+    if (g.debug_force_slow) mode |= DM_FORCE_SLOW;
+    ctx->decode_mode = mode;
+
+    CUC(cudaMalloc(&ctx->d_err, 8)); CUC(cudaMalloc(&ctx->d_acct, 16)); CUC(cudaMalloc(&ctx->d_total, 16));
+    const size_t T = (size_t)(g.n_targets > 0 ? g.n_targets : 1), F = (size_t)(g.n_features > 0 ? g.n_features : 1);
+    if (cfg->fmap) {
+        CUC(cudaMalloc(&ctx->d_fmap, T * 4));
+        CUC(cudaMemcpy(ctx->d_fmap, cfg->fmap, (size_t)g.n_targets * 4, cudaMemcpyHostToDevice));
+        for (int32_t i = 0; i < g.n_targets; i++)
+            if (cfg->fmap[i] < 0 || cfg->fmap[i] >= g.n_features) { int rc = fail(nullptr, MSG_EINVAL, "fmap[%d]=%d outside [0,%d)", i, cfg->fmap[i], g.n_features); msg_destroy(ctx); return rc; }
+    } else if (g.want_profile && g.n_features != g.n_targets) { int rc = fail(nullptr, MSG_EINVAL, "identity fmap needs n_features == n_targets"); msg_destroy(ctx); return rc; }
+    if (g.want_profile) {
+        CUC(cudaMalloc(&ctx->d_ui, F * 4)); CUC(cudaMalloc(&ctx->d_d, F * 8)); CUC(cudaMalloc(&ctx->d_counters, 32));
+        CUC(cudaMalloc(&ctx->d_U, F * 8)); CUC(cudaMalloc(&ctx->d_a, F * 8)); CUC(cudaMalloc(&ctx->d_inc, F * 8));
+        CUC(cudaMalloc(&ctx->d_partial, ((F + 255) / 256) * 8)); CUC(cudaMalloc(&ctx->d_delta, 8 * 20)); CUC(cudaMalloc(&ctx->d_purged, 4));
+    }
+    if (g.want_coverage) {
+        std::vector<uint64_t> base(T + 1, 0);
+        for (int32_t t = 0; t < g.n_targets; t++) base[t + 1] = base[t] + (uint64_t)cfg->target_len[t] + 1;
+        ctx->cov_cells = base[g.n_targets];
+        CUC(cudaMalloc(&ctx->d_tlen, T * 4)); CUC(cudaMalloc(&ctx->d_covbase, (T + 1) * 8));
+        CUC(cudaMemcpy(ctx->d_tlen, cfg->target_len, (size_t)g.n_targets * 4, cudaMemcpyHostToDevice));
+        CUC(cudaMemcpy(ctx->d_covbase, base.data(), (T + 1) * 8, cudaMemcpyHostToDevice));
+        const size_t cells = (size_t)(ctx->cov_cells ? ctx->cov_cells : 1);
+        CUC(cudaMalloc(&ctx->d_diff, cells * 4)); CUC(cudaMalloc(&ctx->d_depth, cells * 4));
+        CUC(cudaMalloc(&ctx->d_covered, T)); CUC(cudaMalloc(&ctx->d_touched, T * 8)); CUC(cudaMalloc(&ctx->d_sum, T * 8));
+    }
+    if (g.n_ranks > 1) {
+        std::string e;
+        if (!cfg->nccl_unique_id) { int rc = fail(nullptr, MSG_EINVAL, "n_ranks > 1 requires nccl_unique_id"); msg_destroy(ctx); return rc; }
+        if (!g_nccl.load(e)) { int rc = fail(nullptr, MSG_ENCCL, "%s", e.c_str()); msg_destroy(ctx); return rc; }
+        ncclUniqueId id; memcpy(&id, cfg->nccl_unique_id, 128);
+        ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, g.n_ranks, id, g.rank);
+        if (r != ncclSuccess) { int rc = fail(nullptr, MSG_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); msg_destroy(ctx); return rc; }
+    }
+#undef CUC
+    int rc = msg_reset(ctx);
+    if (rc) { g_create_error = ctx->err; msg_destroy(ctx); return rc; }
+    *out = ctx;
+    return MSG_OK;
+}
+
+void msg_destroy(msg_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    DevBuf *bufs[] = {&c->raw, &c->off, &c->tid, &c->fb, &c->score, &c->hash, &c->nid, &c->st_alen, &c->st_qlen, &c->st_qclip, &c->st_edit,
+                      &c->segcnt, &c->segbase, &c->out_idx, &c->tile_sums, &c->pcount, &c->scanv, &c->biglist, &c->out_len, &c->out_off, &c->plan, &c->out_rec};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &ch : c->csr) { cudaFree(ch.off); cudaFree(ch.fid); }
+    void *ptrs[] = {c->d_fmap, c->d_tlen, c->d_covbase, c->d_err, c->d_acct, c->d_total, c->d_ui, c->d_d, c->d_counters, c->d_stamp, c->d_U, c->d_a,
+                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &pr : c->ev_decode) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto &pr : c->ev_total) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : c->ev_free) cudaEventDestroy(e);
+    for (auto e : c->marks) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int msg_reset(msg_ctx *c)
+{
+    if (!c) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    const msg_config &g = c->cfg;
+    const size_t T = (size_t)(g.n_targets > 0 ? g.n_targets : 1), F = (size_t)(g.n_features > 0 ? g.n_features : 1);
+    CU(cudaMemsetAsync(c->d_err, 0, 4, c->stream));
+    CU(cudaMemsetAsync(c->d_err + 1, 0xff, 4, c->stream));
+    CU(cudaMemsetAsync(c->d_acct, 0, 16, c->stream));
+    if (g.want_profile) {
+        CU(cudaMemsetAsync(c->d_ui, 0, F * 4, c->stream)); CU(cudaMemsetAsync(c->d_d, 0, F * 8, c->stream));
+        CU(cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
+        for (auto &ch : c->csr) { cudaFree(ch.off); cudaFree(ch.fid); }
+        c->csr.clear();
+    }
+    if (g.want_coverage) {
+        CU(cudaMemsetAsync(c->d_diff, 0, (size_t)(c->cov_cells ? c->cov_cells : 1) * 4, c->stream));
+        CU(cudaMemsetAsync(c->d_covered, 0, T, c->stream));
+        c->cov_finished = false;
+    }
+    c->n_kept = 0; c->have_stream = false; c->out_bytes = 0; c->cur_n = 0;
+    CU(cudaStreamSynchronize(c->stream));
+    return MSG_OK;
+}
+
+// ------------------------------------------------------------------ host index helpers
+int msg_index_records(const uint8_t *raw, size_t nbytes, uint64_t *rec_off, size_t cap, size_t *nrec, size_t *consumed, int allow_partial)
+{
+    size_t o = 0, n = 0;
+    while (o + 4 <= nbytes) {
+        uint32_t bs = (uint32_t)raw[o] | (uint32_t)raw[o + 1] << 8 | (uint32_t)raw[o + 2] << 16 | (uint32_t)raw[o + 3] << 24;
+        if (bs < 32 || bs > 0x7fffffffu) return MSG_EFORMAT;
+        if (o + 4 + (size_t)bs > nbytes) break;
+        if (rec_off) { if (n + 1 >= cap) return MSG_ERANGE; rec_off[n] = o; }
+        n++; o += 4 + (size_t)bs;
+    }
+    if (rec_off) { if (n >= cap) return MSG_ERANGE; rec_off[n] = o; }
+    if (nrec) *nrec = n;
+    if (consumed) *consumed = o;
+    if (o != nbytes && !allow_partial) return MSG_EFORMAT;
+    return MSG_OK;
+}
+
+size_t msg_split_point(const uint8_t *raw, const uint64_t *rec_off, size_t nrec, size_t want)
+{
+    if (want > nrec) want = nrec;
+    if (want == nrec) return nrec;
+    for (size_t k = want; k > 0; k--) {
+        const uint8_t *a = raw + rec_off[k - 1], *b = raw + rec_off[k];
+        uint32_t flag = (uint32_t)a[18] | (uint32_t)a[19] << 8;
+        int32_t tid = (int32_t)((uint32_t)a[4] | (uint32_t)a[5] << 8 | (uint32_t)a[6] << 16 | (uint32_t)a[7] << 24);
+        if ((flag & 4u) || tid < 0) continue;
+        if (a[12] != b[12] || memcmp(a + 36, b + 36, a[12]) != 0) return k;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ data path
+int msg_device_alloc(msg_ctx *c, size_t nbytes, void **d_ptr)
+{
+    if (!c || !d_ptr) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMalloc(d_ptr, nbytes + 64));                 // 16-byte chunk loads may straddle the end
+    CU(cudaMemset((uint8_t *)*d_ptr + nbytes, 0, 64));
+    return MSG_OK;
+}
+int msg_device_free(msg_ctx *c, void *d_ptr) { if (!c) return MSG_EINVAL; CU(cudaSetDevice(c->cfg.device)); CU(cudaFree(d_ptr)); return MSG_OK; }
+int msg_device_upload(msg_ctx *c, void *d_dst, const void *h_src, size_t nbytes)
+{
+    if (!c) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemcpyAsync(d_dst, h_src, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MSG_OK;
+}
+int msg_sync(msg_ctx *c)
+{
+    if (!c) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    harvest_events(c);
+    return MSG_OK;
+}
+
+int msg_push(msg_ctx *c, const uint8_t *raw, size_t nbytes, const uint64_t *rec_off, size_t nrec)
+{
+    if (!c || (nrec && (!raw || !rec_off))) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    if (nrec == 0) { c->cur_n = 0; c->n_kept = 0; c->out_bytes = 0; return MSG_OK; }
+    CU(c->raw.reserve(nbytes + 64)); CU(c->off.reserve((nrec + 1) * 8));
+    CU(cudaMemcpyAsync(c->raw.p, raw, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync((uint8_t *)c->raw.p + nbytes, 0, 64, c->stream));
+    CU(cudaMemcpyAsync(c->off.p, rec_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += nbytes + (nrec + 1) * 8;
+    return run_chunk(c, c->raw.as<uint8_t>(), nbytes, nbytes + 64, c->off.as<uint64_t>(), nrec);
+}
+
+int msg_push_device(msg_ctx *c, const uint8_t *d_raw, size_t nbytes, const uint64_t *d_rec_off, size_t nrec)
+{
+    if (!c || (nrec && (!d_raw || !d_rec_off))) return MSG_EINVAL;
+    if ((uintptr_t)d_raw & 15u) return fail(c, MSG_EINVAL, "device chunk must be 16-byte aligned");
+    CU(cudaSetDevice(c->cfg.device));
+    return run_chunk(c, d_raw, nbytes, (nbytes + 15) & ~(size_t)15, d_rec_off, nrec);
+}
+
+int msg_kept_count(msg_ctx *c, size_t *n_kept) { if (!c || !n_kept) return MSG_EINVAL; *n_kept = c->n_kept; return MSG_OK; }
+
+int msg_pull_kept(msg_ctx *c, uint32_t *idx, size_t cap, size_t *n_kept)
+{
+    if (!c) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    if (n_kept) *n_kept = c->n_kept;
+    if (!idx) return MSG_OK;
+    if (cap < c->n_kept) return fail(c, MSG_ERANGE, "kept buffer too small (%zu < %llu)", cap, (unsigned long long)c->n_kept);
+    if (c->have_stream) {
+        CU(cudaMemcpyAsync(idx, c->out_idx.p, c->n_kept * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += c->n_kept * 4;
+    } else for (uint64_t i = 0; i < c->n_kept; i++) idx[i] = (uint32_t)i;
+    return MSG_OK;
+}
+
+int msg_pull_records(msg_ctx *c, uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec)
+{
+    if (!c) return MSG_EINVAL;
+    if (!c->cfg.want_records) return fail(c, MSG_ESTATE, "context was created without want_records");
+    CU(cudaSetDevice(c->cfg.device));
+    if (nbytes) *nbytes = c->out_bytes;
+    if (nrec) *nrec = c->n_kept;
+    if (!out) return MSG_OK;
+    if (cap < c->out_bytes) return fail(c, MSG_ERANGE, "record buffer too small");
+    if (c->out_bytes) {
+        CU(cudaMemcpyAsync(out, c->out_rec.p, c->out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += c->out_bytes;
+    }
+    return MSG_OK;
+}
+
+int msg_pull_stats(msg_ctx *c, size_t nrec, int32_t *alen, int32_t *qlen, int32_t *qclip, int32_t *edit, int32_t *score, uint8_t *flags)
+{
+    if (!c) return MSG_EINVAL;
+    if (!c->cfg.want_stats) return fail(c, MSG_ESTATE, "context was created without want_stats");
+    if (nrec != c->cur_n) return fail(c, MSG_EINVAL, "nrec does not match the last chunk");
+    CU(cudaSetDevice(c->cfg.device));
+    if (nrec == 0) return MSG_OK;
+    if (alen)  CU(cudaMemcpyAsync(alen, c->st_alen.p, nrec * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (qlen)  CU(cudaMemcpyAsync(qlen, c->st_qlen.p, nrec * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (qclip) CU(cudaMemcpyAsync(qclip, c->st_qclip.p, nrec * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (edit)  CU(cudaMemcpyAsync(edit, c->st_edit.p, nrec * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (score) CU(cudaMemcpyAsync(score, c->score.p, nrec * 4, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<uint32_t> fb;
+    if (flags) { fb.resize(nrec); CU(cudaMemcpyAsync(fb.data(), c->fb.p, nrec * 4, cudaMemcpyDeviceToHost, c->stream)); }
+    CU(cudaStreamSynchronize(c->stream));
+    if (flags) for (size_t i = 0; i < nrec; i++)
+        flags[i] = (uint8_t)(((fb[i] & FB_INPOOL) ? 1 : 0) | ((fb[i] & FB_HAS_AS) ? 2 : 0) | ((fb[i] & FB_EQPREV) ? 4 : 0) | ((fb[i] & FB_SLOW) ? 8 : 0));
+    return MSG_OK;
+}
+
+int msg_pull_counts(msg_ctx *c, uint32_t *ui, double *d)
+{
+    if (!c) return MSG_EINVAL;
+    if (!c->cfg.want_profile) return fail(c, MSG_ESTATE, "context was created without want_profile");
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t F = (size_t)c->cfg.n_features;
+    if (ui && F) CU(cudaMemcpyAsync(ui, c->d_ui, F * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (d && F)  CU(cudaMemcpyAsync(d, c->d_d, F * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MSG_OK;
+}
+
+int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
+{
+    if (!c) return MSG_EINVAL;
+    if (!c->cfg.want_profile) return fail(c, MSG_ESTATE, "context was created without want_profile");
+    CU(cudaSetDevice(c->cfg.device));
+    const msg_config &g = c->cfg;
+    const uint32_t F = (uint32_t)g.n_features;
+    msg_profile_stats s; memset(&s, 0, sizeof s);
+    int rc;
+    // work on copies so that finish can be called again after more chunks
+    uint32_t *ui = c->d_ui; double *dd = c->d_d; uint32_t *cnt = c->d_counters;
+    DevBuf t_ui, t_d, t_cnt;
+    if (g.n_ranks > 1) {
+        CU(t_ui.reserve((size_t)(F ? F : 1) * 4)); CU(t_d.reserve((size_t)(F ? F : 1) * 8)); CU(t_cnt.reserve(32));
+        CU(cudaMemcpyAsync(t_ui.p, c->d_ui, (size_t)F * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(t_d.p, c->d_d, (size_t)F * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(t_cnt.p, c->d_counters, 32, cudaMemcpyDeviceToDevice, c->stream));
+        ui = t_ui.as<uint32_t>(); dd = t_d.as<double>(); cnt = t_cnt.as<uint32_t>();
+        // the one allreduce of per-reference counts over NVLink (+ the scalar counters)
+        if ((rc = allreduce(c, ui, F, ncclUint32, ncclSum))) return rc;
+        if (g.share_type == MSG_MULTI_EQUAL && (rc = allreduce(c, dd, F, ncclFloat64, ncclSum))) return rc;
+        if ((rc = allreduce(c, cnt, 4, ncclUint32, ncclSum))) return rc;
+    }
+    uint32_t hc[4];
+    CU(cudaMemcpyAsync(hc, cnt, 16, cudaMemcpyDeviceToHost, c->stream));
+    if (F) { em_init_kernel<<<nblocks(F, 256), 256, 0, c->stream>>>(ui, dd, g.share_type == MSG_MULTI_EQUAL, c->d_U, c->d_a, F); LAUNCHED(c); }
+    uint64_t nl_local = 0, ne_local = 0;
+    for (auto &ch : c->csr) { nl_local += ch.nlists; ne_local += ch.nent; }
+    unsigned long long nl_global = nl_local;
+    if (g.share_type == MSG_MULTI_PROPORTIONAL) {
+        if (g.n_ranks > 1) {
+            unsigned long long *d_nl = reinterpret_cast<unsigned long long *>(c->d_total);
+            CU(cudaMemcpyAsync(d_nl, &nl_global, 8, cudaMemcpyHostToDevice, c->stream));
+            if ((rc = allreduce(c, d_nl, 1, ncclUint64, ncclSum))) return rc;
+            CU(cudaMemcpyAsync(&nl_global, d_nl, 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        const uint32_t nb = nblocks(F, 256);
+        for (int k = 1; k < 20; k++) {                                                            // msam_profile.c:331
+            CU(cudaMemsetAsync(c->d_inc, 0, (size_t)F * 8, c->stream));
+            for (auto &ch : c->csr) { em_gather_kernel<<<nblocks(ch.nlists, 256), 256, 0, c->stream>>>(ch.off, ch.fid, ch.nlists, c->d_a, c->d_inc); LAUNCHED(c); }
+            if ((rc = allreduce(c, c->d_inc, F, ncclFloat64, ncclSum))) return rc;
+            double delta = 0;
+            if (F) {
+                em_update_kernel<<<nb, 256, 0, c->stream>>>(c->d_U, c->d_inc, c->d_a, c->d_partial, F); LAUNCHED(c);
+                em_delta_kernel<<<1, 256, 0, c->stream>>>(c->d_partial, nb, F, c->d_delta + (k - 1)); LAUNCHED(c);
+                CU(cudaMemcpyAsync(&delta, c->d_delta + (k - 1), 8, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                c->d2h_bytes += 8;
+            } else delta = nan("");                                                           // reference divides by n_features == 0
+            s.em_delta[k - 1] = delta; s.em_iterations = k;
+            if (delta < 1e-10) { s.em_converged = 1; break; }                                     // :383
+        }
+        CU(cudaMemsetAsync(c->d_purged, 0, 4, c->stream));
+        for (auto &ch : c->csr) { em_purged_kernel<<<nblocks(ch.nlists, 256), 256, 0, c->stream>>>(ch.off, ch.fid, ch.nlists, c->d_a, c->d_purged); LAUNCHED(c); }
+        if ((rc = allreduce(c, c->d_purged, 1, ncclUint32, ncclSum))) return rc;
+        CU(cudaMemcpyAsync(&s.purged_insert_count, c->d_purged, 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (abundance && F) CU(cudaMemcpyAsync(abundance, c->d_a, (size_t)F * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += (size_t)F * 8 + 20;
+    s.mapped_inserts = hc[0]; s.uniq_mapper_count = hc[1]; s.multi_mapper_count = hc[2];
+    s.multi_lists = nl_global; s.multi_entries = ne_local;
+    if (st) *st = s;
+    t_ui.release(); t_d.release(); t_cnt.release();
+    return check_device_errors(c);
+}
+
+int msg_finish_coverage(msg_ctx *c, uint8_t *covered, int64_t *touched, int64_t *sum)
+{
+    if (!c) return MSG_EINVAL;
+    if (!c->cfg.want_coverage) return fail(c, MSG_ESTATE, "context was created without want_coverage");
+    CU(cudaSetDevice(c->cfg.device));
+    const msg_config &g = c->cfg;
+    const size_t T = (size_t)g.n_targets;
+    int rc;
+    if (T == 0) return MSG_OK;
+    CU(cudaMemcpyAsync(c->d_depth, c->d_diff, (size_t)c->cov_cells * 4, cudaMemcpyDeviceToDevice, c->stream));
+    DevBuf t_cov;
+    uint8_t *cov = c->d_covered;
+    if (g.n_ranks > 1) {
+        CU(t_cov.reserve(T));
+        CU(cudaMemcpyAsync(t_cov.p, c->d_covered, T, cudaMemcpyDeviceToDevice, c->stream));
+        cov = t_cov.as<uint8_t>();
+        if ((rc = allreduce(c, c->d_depth, c->cov_cells, ncclInt32, ncclSum))) return rc;
+        if ((rc = allreduce(c, cov, T, ncclUint8, ncclMax))) return rc;
+    }
+    rc = run_scan<int32_t>(c, InI32{c->d_depth}, OutInclI32{c->d_depth}, c->cov_cells, (int32_t *)nullptr);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_touched, 0, T * 8, c->stream)); CU(cudaMemsetAsync(c->d_sum, 0, T * 8, c->stream));
+    coverage_reduce_kernel<<<nblocks(nblocks(c->cov_cells, COV_SPAN), 256), 256, 0, c->stream>>>(c->d_depth, c->cov_cells, c->d_covbase, c->d_tlen,
+                                                                                                 g.n_targets, c->d_touched, c->d_sum); LAUNCHED(c);
+    if (covered) CU(cudaMemcpyAsync(covered, cov, T, cudaMemcpyDeviceToHost, c->stream));
+    if (touched) CU(cudaMemcpyAsync(touched, c->d_touched, T * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (sum)     CU(cudaMemcpyAsync(sum, c->d_sum, T * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += T * 17;
+    c->cov_finished = true;
+    t_cov.release();
+    return check_device_errors(c);
+}
+
+int msg_pull_coverage(msg_ctx *c, int32_t tid, int32_t *depth)
+{
+    if (!c || !depth) return MSG_EINVAL;
+    if (!c->cfg.want_coverage || !c->cov_finished) return fail(c, MSG_ESTATE, "call msg_finish_coverage first");
+    if (tid < 0 || tid >= c->cfg.n_targets) return fail(c, MSG_EINVAL, "tid out of range");
+    CU(cudaSetDevice(c->cfg.device));
+    uint64_t base[2]; uint32_t tl;
+    CU(cudaMemcpy(base, c->d_covbase + tid, 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&tl, c->d_tlen + tid, 4, cudaMemcpyDeviceToHost));
+    if (tl) CU(cudaMemcpy(depth, c->d_depth + base[0], (size_t)tl * 4, cudaMemcpyDeviceToHost));
+    return MSG_OK;
+}
+
+int msg_get_timing(msg_ctx *c, msg_timing *t, int reset)
+{
+    if (!c || !t) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    harvest_events(c);
+    unsigned long long acct[2];
+    CU(cudaMemcpy(acct, c->d_acct, 16, cudaMemcpyDeviceToHost));
+    t->decode_ms = c->decode_ms; t->decode_launches = c->decode_launches; t->total_ms = c->total_ms;
+    t->kernel_launches = c->kernel_launches; t->h2d_bytes = c->h2d_bytes; t->d2h_bytes = c->d2h_bytes;
+    t->alg_bytes = acct[0]; t->slow_records = acct[1];
+    if (reset) {
+        c->decode_ms = c->total_ms = 0; c->decode_launches = c->kernel_launches = 0; c->h2d_bytes = c->d2h_bytes = 0;
+        CU(cudaMemset(c->d_acct, 0, 16));
+    }
+    return MSG_OK;
+}
+
+int msg_mark(msg_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot >= 8) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    if (!c->marks[slot]) CU(cudaEventCreate(&c->marks[slot]));
+    CU(cudaEventRecord(c->marks[slot], c->stream));
+    return MSG_OK;
+}
+
+int msg_elapsed_ms(msg_ctx *c, int a, int b, double *ms)
+{
+    if (!c || !ms || a < 0 || a >= 8 || b < 0 || b >= 8 || !c->marks[a] || !c->marks[b]) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaEventSynchronize(c->marks[b]));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, c->marks[a], c->marks[b]));
+    *ms = f;
+    return MSG_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,66 @@
+// coverage.cuh -- K6: per-position depth as a difference array, then per-target summary.
+//
+// Replaces mUpdateCoverageForAlignment (msam_coverage.c:33-87; the reference's inner
+// loop is per *base*, ours is two atomics per M/=/X run) and the numeric part of
+// mWriteCoverageSummaryToStream (msam_coverage.c:189-219).
+//
+// Layout: one int32 array `diff` of sum(tlen[t] + 1) cells; target t owns
+// [covbase[t], covbase[t] + tlen[t]] -- the extra cell absorbs the "-1" of runs that
+// end exactly at tlen, so every target's cells sum to zero and ONE unsegmented
+// prefix sum over the whole array yields the depth of every target.
+#pragma once
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace msg {
+
+// stream-driven coverage (used when the kept list is only known after best-hit selection)
+__global__ void __launch_bounds__(256) coverage_stream_kernel(const uint8_t *raw, const uint64_t *off, const uint32_t *stream, uint64_t m,
+                                                              int32_t n_targets, int32_t *diff, const uint64_t *covbase,
+                                                              const uint32_t *tlen, uint8_t *covered, uint32_t *err)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t r = stream ? stream[j] : (uint32_t)j;
+    const uint64_t o = off[r];
+    GlAcc g{raw + o};
+    RecCore c = parse_core(g, off[r + 1] - o);
+    if (c.bad) { atomicOr(err, DERR_FORMAT); return; }
+    if (c.tid < 0) return;                                              // msam_coverage.c:42
+    if (c.tid >= n_targets) { atomicOr(err, DERR_FORMAT); return; }
+    cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, diff, covbase, tlen, covered);
+}
+
+// after the prefix sum: per-target (#cells != 0, sum of cells) over [covbase[t], covbase[t]+tlen[t])
+// Each thread owns SPAN consecutive cells; target lookup by binary search on covbase.
+constexpr int COV_SPAN = 16;
+
+__global__ void __launch_bounds__(256) coverage_reduce_kernel(const int32_t *depth, uint64_t total_cells, const uint64_t *covbase,
+                                                              const uint32_t *tlen, int32_t n_targets,
+                                                              unsigned long long *touched, long long *sum)
+{
+    const uint64_t start = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * COV_SPAN;
+    if (start >= total_cells) return;
+    const uint64_t stop = min(total_cells, start + COV_SPAN);
+    // largest t with covbase[t] <= start
+    int32_t lo = 0, hi = n_targets - 1;
+    while (lo < hi) { int32_t mid = (lo + hi + 1) >> 1; if (covbase[mid] <= start) lo = mid; else hi = mid - 1; }
+    int32_t t = lo;
+    uint64_t tend = covbase[t] + tlen[t];          // first cell that is NOT a position of t (the spill cell)
+    unsigned long long tc = 0; long long sm = 0;
+    for (uint64_t x = start; x < stop; x++) {
+        while (x > tend) {                         // moved past t's spill cell
+            if (tc | (unsigned long long)sm) { atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm); }
+            tc = 0; sm = 0; t++; tend = covbase[t] + tlen[t];
+        }
+        if (x == tend) continue;                   // spill cell
+        int32_t v = depth[x];
+        tc += (v != 0); sm += v;
+    }
+    if (tc | (unsigned long long)sm) { atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm); }
+}
+
+struct InI32 { const int32_t *v; __device__ __forceinline__ int32_t operator()(uint64_t i) const { return v[i]; } };
+struct OutInclI32 { int32_t *o; __device__ __forceinline__ void operator()(uint64_t i, int32_t ex, int32_t v) const { o[i] = ex + v; } };
+
+} // namespace msg

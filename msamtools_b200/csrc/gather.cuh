@@ -1,0 +1,98 @@
+// gather.cuh -- materialise the filter stage's output records (mSamWrite of every
+// kept record, msam_filter.c:243 / mBamVector.c:342-347) in reference output order.
+// With --rescore the first AS field is removed and "AS:i:<score>" appended, exactly
+// what bam_aux_del + bam_aux_append do at msam_filter.c:160-168.
+#pragma once
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace msg {
+
+struct GatherPlan {          // per stream record
+    uint32_t cut0, cut1;     // byte span [cut0,cut1) of the record to drop (AS field), cut0==cut1 -> none
+    uint32_t append;         // 1 -> append AS:i
+};
+
+// thread per stream record: output length + rescore plan
+__global__ void __launch_bounds__(256) gather_plan_kernel(const uint8_t *raw, const uint64_t *off, const uint32_t *stream, uint64_t m,
+                                                          int rescore, uint32_t *out_len, GatherPlan *plan)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t r = stream ? stream[j] : (uint32_t)j;
+    const uint64_t o = off[r];
+    const uint32_t len = (uint32_t)(off[r + 1] - o);
+    uint32_t nl = len;
+    GatherPlan pl = {0, 0, 0};
+    if (rescore) {
+        GlAcc g{raw + o};
+        RecCore c = parse_core(g, len);
+        if (!c.bad && !(c.flag & BAM_FUNMAP)) {              // unmapped records are never rescored (:132-138 precede :160)
+            // locate the first AS field (bam_aux_get), same walk as aux_scan
+            GlAcc ax{raw + o + c.aux_off};
+            uint32_t y = 0;
+            while (y + 3 <= c.aux_len) {
+                uint32_t t0 = ax.u8(y), t1 = ax.u8(y + 1), ty = ax.u8(y + 2);
+                uint32_t v0 = y + 3, vend = 0;
+                if (ty == 'A' || ty == 'c' || ty == 'C') vend = v0 + 1;
+                else if (ty == 's' || ty == 'S') vend = v0 + 2;
+                else if (ty == 'i' || ty == 'I' || ty == 'f') vend = v0 + 4;
+                else if (ty == 'd') vend = v0 + 8;
+                else if (ty == 'Z' || ty == 'H') {
+                    uint32_t z = v0; while (z < c.aux_len && ax.u8(z)) z++;
+                    if (z >= c.aux_len) break;
+                    vend = z + 1;
+                } else if (ty == 'B') {
+                    if (v0 + 5 > c.aux_len) break;
+                    uint32_t st = ax.u8(v0), cnt = ax.u32(v0 + 1), es;
+                    if (st == 'c' || st == 'C') es = 1; else if (st == 's' || st == 'S') es = 2;
+                    else if (st == 'i' || st == 'I' || st == 'f') es = 4; else break;
+                    unsigned long long tot = (unsigned long long)v0 + 5ull + (unsigned long long)cnt * es;
+                    if (tot > c.aux_len) break;
+                    vend = (uint32_t)tot;
+                } else break;
+                if (vend > c.aux_len) break;
+                if (t0 == 'A' && t1 == 'S') { pl.cut0 = c.aux_off + y; pl.cut1 = c.aux_off + vend; break; }
+                y = vend;
+            }
+            pl.append = 1;
+            nl = len - (pl.cut1 - pl.cut0) + 7;
+        }
+    }
+    out_len[j] = nl;
+    plan[j] = pl;
+}
+
+// warp per stream record: byte copy (source and destination are both unaligned)
+__global__ void __launch_bounds__(256) gather_copy_kernel(const uint8_t *raw, const uint64_t *off, const uint32_t *stream, uint64_t m,
+                                                          const unsigned long long *out_off, const uint32_t *out_len,
+                                                          const GatherPlan *plan, const int32_t *score, uint8_t *out)
+{
+    const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (j >= m) return;
+    const uint32_t r = stream ? stream[j] : (uint32_t)j;
+    const uint8_t *src = raw + off[r];
+    const uint32_t len = (uint32_t)(off[r + 1] - off[r]);
+    uint8_t *dst = out + out_off[j];
+    const GatherPlan pl = plan[j];
+    const uint32_t nl = out_len[j];
+    const uint32_t gap = pl.cut1 - pl.cut0;
+    const uint32_t body = len - gap;                 // bytes copied from the source
+    for (uint32_t k = lane; k < body; k += 32) {
+        uint32_t s = k < pl.cut0 || gap == 0 ? k : k + gap;
+        uint8_t b = src[s];
+        if (pl.append && k < 4) b = (uint8_t)((nl - 4) >> (8 * k));     // block_size of the rewritten record
+        dst[k] = b;
+    }
+    if (pl.append && lane == 0) {
+        int32_t sc = score[r];
+        uint8_t *t = dst + body;
+        t[0] = 'A'; t[1] = 'S'; t[2] = 'i';
+        t[3] = (uint8_t)sc; t[4] = (uint8_t)(sc >> 8); t[5] = (uint8_t)(sc >> 16); t[6] = (uint8_t)(sc >> 24);
+    }
+}
+
+struct InLenU64 { const uint32_t *v; __device__ __forceinline__ unsigned long long operator()(uint64_t i) const { return v[i]; } };
+
+} // namespace msg

@@ -1,0 +1,327 @@
+// profile.cuh -- K4/K5: insert counting over QNAME groups + multi-mapper sharing.
+//
+// Replaces mEstimateInsertCountOnFile (msam_profile.c:204-243), mEstimateInsertCountOnPool
+// (:65-200) and the numeric part of mInsertCountToAbundanceMatrix (:248-425).
+//
+// The profile stage consumes a *stream* of records: either the chunk itself
+// (plain `msamtools profile`) or the filter stage's kept list in reference output
+// order (`filter | profile`), addressed through `stream[j]` (NULL = identity).
+// A group is a maximal run of stream records with tid != -1 whose QNAME equals the
+// previous such record's (:223-232).  Name equality is decided exactly without
+// touching the record bytes again in the common case:
+//   same QNAME run id (nid)            -> equal     (adjacent byte compares chained)
+//   different run id, different hash   -> different
+//   different run id, same 32-bit hash -> byte compare in global memory (rare)
+// The group head walks its group, collects distinct features in first-appearance
+// order (:136-142) and applies the share rule.  Proportional mode writes the feature
+// lists into a CSR that the EM kernels iterate.
+#pragma once
+#include "common.cuh"
+
+namespace msg {
+
+struct ProfParams {
+    const uint8_t  *raw;
+    const uint64_t *off;
+    const uint32_t *stream;      // may be null (identity)
+    uint64_t m;                  // stream length
+    const int32_t  *tid;
+    const uint32_t *nid;
+    const uint32_t *hash;
+    const int32_t  *fmap;        // may be null (identity)
+    int32_t n_targets, n_features;
+    int share_type;
+    uint32_t *ui;                // [F]
+    double   *d;                 // [F]
+    uint32_t *counters;          // [0] inserts [1] uniq [2] multi [3] big groups
+    uint32_t *pcount;            // [m] list length at group heads (proportional), else 0
+    uint32_t *big;               // [big_cap] stream positions of oversized groups
+    uint32_t big_cap;
+    uint32_t big_threshold;
+    uint32_t *err;
+};
+
+__device__ __forceinline__ uint32_t stream_at(const ProfParams &p, uint64_t j) { return p.stream ? p.stream[j] : (uint32_t)j; }
+
+__device__ bool qname_equal_global(const uint8_t *raw, const uint64_t *off, uint32_t a, uint32_t b)
+{
+    const uint8_t *pa = raw + off[a], *pb = raw + off[b];
+    uint32_t la = pa[12], lb = pb[12];
+    if (la != lb) return false;
+    for (uint32_t k = 0; k < la; k++) if (pa[36 + k] != pb[36 + k]) return false;
+    return true;
+}
+
+__device__ __forceinline__ bool same_name(const ProfParams &p, uint32_t a, uint32_t b)
+{
+    if (p.nid[a] == p.nid[b]) return true;
+    if (p.hash[a] != p.hash[b]) return false;
+    return qname_equal_global(p.raw, p.off, a, b);
+}
+
+__device__ __forceinline__ int32_t feature_of(const ProfParams &p, int32_t t) { return p.fmap ? p.fmap[t] : t; }
+
+constexpr int PROF_CACHE = 8;
+
+// Walk the group headed at stream position j.  act(f, k) is called for the k-th
+// distinct feature in first-appearance order.  Returns #distinct; *size_out = group size;
+// *end_out = stream position after the group's last record.
+template <class Act>
+__device__ __forceinline__ uint32_t walk_group(const ProfParams &p, uint64_t j, uint32_t r0, uint32_t *size_out, Act act, uint32_t max_size)
+{
+    int32_t cache[PROF_CACHE];
+#pragma unroll
+    for (int k = 0; k < PROF_CACHE; k++) cache[k] = -1;
+    uint32_t nd = 0, size = 0;
+    for (uint64_t jj = j; jj < p.m; jj++) {
+        uint32_t rr = (jj == j) ? r0 : stream_at(p, jj);
+        int32_t tt = p.tid[rr];
+        if (tt == -1) continue;                                          // msam_profile.c:223-225
+        if (jj != j && !same_name(p, r0, rr)) break;                     // :226
+        if (tt < 0 || tt >= p.n_targets) { atomicOr(p.err, DERR_FORMAT); break; }
+        size++;
+        if (size > max_size) break;                                      // oversized: caller defers to the serial kernel
+        int32_t f = feature_of(p, tt);
+        bool seen = false;
+#pragma unroll
+        for (int k = 0; k < PROF_CACHE; k++) seen |= (cache[k] == f);
+        if (!seen && nd >= PROF_CACHE) {
+            // cache full: rescan the group's earlier records (exact, O(size) per probe)
+            for (uint64_t q = j; q < jj && !seen; q++) {
+                uint32_t rq = (q == j) ? r0 : stream_at(p, q);
+                int32_t tq = p.tid[rq];
+                if (tq == -1) continue;
+                seen = feature_of(p, tq) == f;
+            }
+        }
+        if (!seen) {
+#pragma unroll
+            for (int k = 0; k < PROF_CACHE; k++) if ((uint32_t)k == nd) cache[k] = f;
+            act(f, nd);
+            nd++;
+        }
+    }
+    *size_out = size;
+    return nd;
+}
+
+struct ActNone  { __device__ __forceinline__ void operator()(int32_t, uint32_t) const {} };
+struct ActFirst { int32_t *f0, *f1; __device__ __forceinline__ void operator()(int32_t f, uint32_t k) const { if (k == 0) *f0 = f; if (k == 1) *f1 = f; } };
+struct ActAddUi { uint32_t *ui; uint32_t v; __device__ __forceinline__ void operator()(int32_t f, uint32_t) const { atomicAdd(ui + f, v); } };
+struct ActAddD  { double *d; double v; __device__ __forceinline__ void operator()(int32_t f, uint32_t) const { atomicAdd(d + f, v); } };
+struct ActStore { int32_t *dst; __device__ __forceinline__ void operator()(int32_t f, uint32_t k) const { dst[k] = f; } };
+
+// is stream position j a group head?  (prev valid record has a different QNAME, or none)
+__device__ __forceinline__ bool group_head(const ProfParams &p, uint64_t j, uint32_t r)
+{
+    for (uint64_t k = j; k-- > 0;) {
+        uint32_t rk = stream_at(p, k);
+        if (p.tid[rk] == -1) continue;
+        return !same_name(p, rk, r);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) profile_count_kernel(const ProfParams p)
+{
+    __shared__ uint32_t s_cnt[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t ins = 0, uq = 0, mu = 0;
+    if (j < p.m) {
+        uint32_t pc = 0;
+        const uint32_t r = stream_at(p, j);
+        const int32_t t = p.tid[r];
+        if (t != -1 && group_head(p, j, r)) {
+            int32_t f0 = -1, f1 = -1; uint32_t size = 0;
+            uint32_t nd = walk_group(p, j, r, &size, ActFirst{&f0, &f1}, p.big_threshold);
+            if (size > p.big_threshold) {
+                uint32_t slot = atomicAdd(p.counters + 3, 1u);
+                if (slot < p.big_cap) p.big[slot] = (uint32_t)j;
+            } else if (size > 0) {
+                ins = 1;
+                if (nd == 1) { atomicAdd(p.ui + f0, 2u); uq = 1; }                               // :75-78,87-91,152-159
+                else {
+                    mu = 1;
+                    switch (p.share_type) {
+                    case 1: walk_group(p, j, r, &size, ActAddUi{p.ui, 2u}, p.big_threshold); break;               // :99-102,169-173
+                    case 2:
+                        if (size == 2) { atomicAdd(p.ui + f0, 1u); atomicAdd(p.ui + f1, 1u); }                    // :103-106
+                        else walk_group(p, j, r, &size, ActAddD{p.d, 1.0 / (int)nd}, p.big_threshold);            // :175-182
+                        break;
+                    case 3: pc = nd; break;                                                                        // :107-121,184-186
+                    default: break;                                                                                // ignore
+                    }
+                }
+            }
+        }
+        if (p.pcount) p.pcount[j] = pc;
+    }
+    ins = warp_sum_u32(ins); uq = warp_sum_u32(uq); mu = warp_sum_u32(mu);
+    if ((threadIdx.x & 31) == 0) {
+        if (ins) atomicAdd(&s_cnt[0], ins);
+        if (uq) atomicAdd(&s_cnt[1], uq);
+        if (mu) atomicAdd(&s_cnt[2], mu);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+// proportional: heads with pcount>0 write their list; scanv[j] = (lists before << 32) | entries before
+__global__ void __launch_bounds__(256) profile_fill_kernel(const ProfParams p, const unsigned long long *scanv,
+                                                           uint32_t *mm_off, int32_t *mm_fid)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.m) return;
+    if (p.pcount[j] == 0) return;
+    const unsigned long long sv = scanv[j];
+    const uint32_t li = (uint32_t)(sv >> 32), eo = (uint32_t)sv;
+    mm_off[li] = eo;
+    uint32_t size;
+    walk_group(p, j, stream_at(p, j), &size, ActStore{mm_fid + eo}, p.big_threshold);
+}
+
+// Oversized groups (> big_threshold records): one thread, the reference's own
+// ub_target_hit stamp algorithm (msam_profile.c:131-145) with a u32 stamp per feature.
+// Lists for proportional mode are appended to big_fid / big_off.
+__global__ void profile_big_kernel(const ProfParams p, uint32_t nbig, uint32_t *stamp, uint32_t stamp_base,
+                                   uint32_t *big_off, int32_t *big_fid, uint32_t *big_tot /*[0]=lists,[1]=entries*/, int fill)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t nl = 0, ne = 0;
+    for (uint32_t b = 0; b < nbig; b++) {
+        const uint64_t j = p.big[b];
+        const uint32_t r0 = stream_at(p, j);
+        const uint32_t st = stamp_base + b + 1;
+        uint32_t nd = 0, size = 0;
+        uint32_t e0 = ne;
+        for (uint64_t jj = j; jj < p.m; jj++) {
+            uint32_t rr = stream_at(p, jj);
+            int32_t tt = p.tid[rr];
+            if (tt == -1) continue;
+            if (jj != j && !same_name(p, r0, rr)) break;
+            if (tt < 0 || tt >= p.n_targets) { atomicOr(p.err, DERR_FORMAT); break; }
+            size++;
+            int32_t f = feature_of(p, tt);
+            if (stamp[f] != st) {
+                stamp[f] = st;
+                if (fill && p.share_type == 3) big_fid[ne] = f;
+                ne++; nd++;
+            }
+        }
+        if (!fill) {
+            // counting pass applies the non-proportional share rules and the counters once
+            atomicAdd(p.counters + 0, 1u);
+            if (nd == 1) { atomicAdd(p.ui + feature_of(p, p.tid[r0]), 2u); atomicAdd(p.counters + 1, 1u); ne = e0; }
+            else {
+                atomicAdd(p.counters + 2, 1u);
+                if (p.share_type == 1 || p.share_type == 2) {
+                    // second walk with a fresh stamp to apply the adds
+                    const uint32_t st2 = st | 0x80000000u;
+                    for (uint64_t jj = j; jj < p.m; jj++) {
+                        uint32_t rr = stream_at(p, jj);
+                        int32_t tt = p.tid[rr];
+                        if (tt == -1) continue;
+                        if (jj != j && !same_name(p, r0, rr)) break;
+                        if (tt < 0 || tt >= p.n_targets) break;
+                        int32_t f = feature_of(p, tt);
+                        if (stamp[f] != st2) {
+                            stamp[f] = st2;
+                            if (p.share_type == 1) atomicAdd(p.ui + f, 2u);
+                            else atomicAdd(p.d + f, 1.0 / (int)nd);
+                        }
+                    }
+                }
+                if (p.share_type != 3) ne = e0;
+            }
+            if (p.share_type == 3 && nd > 1) nl++;
+        } else {
+            if (nd == 1 || p.share_type != 3) ne = e0;
+            else { big_off[nl] = e0; nl++; }
+        }
+    }
+    if (!fill) { big_tot[0] = nl; big_tot[1] = ne; }
+    else if (p.share_type == 3) big_off[nl] = ne;
+}
+
+// ---------------------------------------------------------------- abundance / EM (msam_profile.c:284-404)
+__global__ void em_init_kernel(const uint32_t *ui, const double *d, int use_d, double *U, double *a, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double u = 1.0 * ui[i] / 2;                                         // :286
+    if (use_d) u += d[i];                                               // :305
+    U[i] = u; a[i] = u;
+}
+__global__ void em_init_from_U_kernel(const double *U, double *a, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = U[i];
+}
+
+// one thread per multi-mapper list: s = sum a[f] in list order; inc[f] += a[f]/s   (:341-365)
+__global__ void __launch_bounds__(256) em_gather_kernel(const uint32_t *mm_off, const int32_t *mm_fid, uint32_t nlists,
+                                                        const double *a, double *inc)
+{
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlists) return;
+    uint32_t b = mm_off[l], e = mm_off[l + 1];
+    double s = 0;
+    for (uint32_t k = b; k < e; k++) s += a[mm_fid[k]];
+    if (s > 0) for (uint32_t k = b; k < e; k++) { int32_t f = mm_fid[k]; atomicAdd(inc + f, a[f] / s); }
+}
+
+// a_new = U + inc; flush < 1e-20; per-block partial of sum (a_new - a_old)^2 in a fixed order  (:369-379)
+__global__ void __launch_bounds__(256) em_update_kernel(const double *U, const double *inc, double *a, double *partial, uint32_t n)
+{
+    __shared__ double s[256];
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    double dd = 0;
+    if (i < n) {
+        double an = U[i] + inc[i];
+        if (an < 1e-20) an = 0;
+        double diff = an - a[i];
+        dd = diff * diff;
+        a[i] = an;
+    }
+    s[threadIdx.x] = dd;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+__global__ void __launch_bounds__(256) em_delta_kernel(const double *partial, uint32_t nblocks, uint32_t n, double *delta_out)
+{
+    __shared__ double s[256];
+    double acc = 0;
+    for (uint32_t b = threadIdx.x; b < nblocks; b += 256) acc += partial[b];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) *delta_out = s[0] / n;                        // :380
+}
+// purged = #lists whose final abundances sum to exactly 0  (:394-404)
+__global__ void __launch_bounds__(256) em_purged_kernel(const uint32_t *mm_off, const int32_t *mm_fid, uint32_t nlists,
+                                                        const double *a, uint32_t *purged)
+{
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t z = 0;
+    if (l < nlists) {
+        double s = 0;
+        for (uint32_t k = mm_off[l]; k < mm_off[l + 1]; k++) s += a[mm_fid[k]];
+        z = (s == 0);
+    }
+    z = warp_sum_u32(z);
+    if ((threadIdx.x & 31) == 0 && z) atomicAdd(purged, z);
+}
+
+struct InPcountPacked {      // (is_list << 32) | entries, for one packed u64 scan
+    const uint32_t *pc;
+    __device__ __forceinline__ unsigned long long operator()(uint64_t i) const {
+        uint32_t v = pc[i];
+        return v ? ((1ull << 32) | v) : 0ull;
+    }
+};
+struct OutExclU64 { unsigned long long *o; __device__ __forceinline__ void operator()(uint64_t i, unsigned long long ex, unsigned long long) const { o[i] = ex; } };
+
+} // namespace msg

@@ -1,0 +1,359 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the committed golden
+vectors and against the CPU oracle on the same seeded inputs.  Integer/byte/index results must be
+bit-exact; float64 abundances within 1e-9 relative (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+import goldenutil as G
+
+pytestmark = pytest.mark.gpu
+
+SHARE = {"all": 1, "equal": 2, "proportional": 3, "ignore": 4}
+REL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def m():
+    import msamtools_b200 as mod
+    assert mod._lib.load().msg_device_count() > 0, "no CUDA device: the GPU tests must not silently pass"
+    return mod
+
+
+def close(a, b, rel=REL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= rel * np.maximum(np.abs(a), np.abs(b)))
+
+
+def gpu_filter(m, s, opts, force_slow=False, records=True):
+    with m.Context(stats=True, records=records, n_targets=len(s.ref_names), force_slow=force_slow, **opts) as ctx:
+        ctx.push(s.raw, s.off)
+        kept = ctx.pull_kept()
+        st = ctx.pull_stats()
+        rec = ctx.pull_records()[0] if records else None
+    return kept, st, rec
+
+
+@pytest.mark.parametrize("force_slow", [False, True], ids=["staged", "slowpath"])
+@pytest.mark.parametrize("c", G.cases("filter"), ids=G.case_id)
+def test_golden_filter(m, c, force_slow):
+    s = G.fixture(c["fixture"])
+    kept, st, rec = gpu_filter(m, s, c["opts"], force_slow)
+    assert s.name_flags(kept) == c["name_flags"]
+    assert kept.tolist() == c["kept"]
+    assert bytes(rec).hex() == c["records_hex"]
+    need_stats = any(k in c["opts"] for k in ("l", "p", "ppt", "z", "rescore"))
+    mapped = np.array([not (s.record_fields(i)[1] & 4) for i in range(s.n)])
+    if need_stats:
+        for k in ("alen", "qlen", "qclip", "edit"):
+            assert st[k][mapped].tolist() == np.array(c["stats"][k])[mapped].tolist(), k
+    if not c["opts"].get("rescore"):
+        has_as = np.array(c["stats"]["has_as"], dtype=bool)
+        assert st["score"][has_as].tolist() == np.array(c["stats"]["score"])[has_as].tolist()
+        assert ((st["flags"] & 2) != 0).tolist() == has_as.tolist()
+
+
+@pytest.mark.parametrize("force_slow", [False, True], ids=["staged", "slowpath"])
+@pytest.mark.parametrize("c", G.cases("profile"), ids=G.case_id)
+def test_golden_profile(m, c, force_slow):
+    s = G.fixture(c["fixture"])
+    pre = c["pre"] or {}
+    with m.Context(profile=True, multi=c["mode"], n_targets=len(s.ref_names), force_slow=force_slow, **pre) as ctx:
+        ctx.push(s.raw, s.off)
+        ui, d = ctx.pull_counts()
+        ab, st = ctx.finish_profile()
+    exp = c["stats"]
+    for k in ("mapped_inserts", "uniq", "multi", "purged", "iterations", "converged", "n_lists", "n_entries"):
+        assert st[k] == exp[k], k
+    assert ui.tolist() == G.dense(c, "ui", np.uint32).tolist()
+    assert close(ab, G.dense(c, "abundance", np.float64))
+    assert close(st["delta"], exp["delta"], 1e-6) or (np.array(exp["delta"]) < 1e-12).all()
+
+
+@pytest.mark.parametrize("c", G.cases("coverage"), ids=G.case_id)
+def test_golden_coverage(m, c):
+    s = G.fixture(c["fixture"])
+    pre = c["pre"] or {}
+    with m.Context(coverage=True, n_targets=len(s.ref_names), target_len=s.target_len, **pre) as ctx:
+        ctx.push(s.raw, s.off)
+        cov, touched, total = ctx.finish_coverage()
+        assert np.nonzero(cov)[0].tolist() == c["nz"]
+        assert touched.tolist() == G.dense(c, "touched", np.int64).tolist()
+        assert total.tolist() == G.dense(c, "sum", np.int64).tolist()
+        if c["depth"] is not None:
+            for t, dexp in enumerate(c["depth"]):
+                assert ctx.pull_coverage(t).tolist() == dexp
+
+
+# ---------------------------------------------------------------- seeded synthetic streams vs the oracle
+FILTER_OPTS = [
+    dict(l=80, p=95, z=80), dict(l=80, p=95, z=80, besthit=True), dict(l=80, p=95, z=80, uniqhit=True),
+    dict(besthit=True), dict(uniqhit=True), dict(p=99, invert=True), dict(p=99, invert=True, keep_unmapped=True),
+    dict(ppt=-990), dict(z=90), dict(l=140), dict(l=100, rescore=True, besthit=True), dict(rescore=True, uniqhit=True),
+]
+
+
+@pytest.fixture(scope="module")
+def mixed():
+    from msamtools_b200 import synth
+    p = synth.make_params("mixed", n_records=60_000, seed=24680)
+    raw, off, st = synth.generate(p)
+    return raw, off, synth.target_lengths(p), p
+
+
+@pytest.mark.parametrize("opts", FILTER_OPTS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
+def test_synth_filter(m, oracle, mixed, opts):
+    raw, off, tlen, p = mixed
+    cfg = oracle.filter_cfg(**opts)
+    exp = oracle.filter_stream(raw, off, cfg)
+    with m.Context(records=True, n_targets=len(tlen), **opts) as ctx:
+        ctx.push(raw, off)
+        kept = ctx.pull_kept()
+        rec, nrec = ctx.pull_records()
+    assert np.array_equal(kept, exp)
+    assert 0 < len(exp) < len(off) - 1
+    assert bytes(rec) == bytes(oracle.emit_records(raw, off, exp, cfg))
+
+
+def test_synth_stats(m, oracle, mixed):
+    raw, off, tlen, p = mixed
+    exp = oracle.record_stats(raw, off)
+    for slow in (False, True):
+        with m.Context(l=1, stats=True, n_targets=len(tlen), force_slow=slow) as ctx:
+            ctx.push(raw, off)
+            st = ctx.pull_stats()
+        tagged = exp["has_tag"] > 0
+        for k in ("alen", "qlen", "qclip", "edit"):
+            assert np.array_equal(st[k][tagged], exp[k][tagged]), k
+        assert np.array_equal((st["flags"] & 8) != 0, np.full(len(off) - 1, slow))
+
+
+@pytest.mark.parametrize("mode", ["all", "equal", "proportional", "ignore"])
+@pytest.mark.parametrize("pre", [None, dict(l=80, p=95, z=80, besthit=True), dict(p=97)], ids=["plain", "besthit", "p97"])
+def test_synth_profile(m, oracle, mixed, mode, pre):
+    raw, off, tlen, p = mixed
+    idx = None if pre is None else oracle.filter_stream(raw, off, oracle.filter_cfg(**pre))
+    eab, est, eui, ed = oracle.profile(raw, off, idx, len(tlen), SHARE[mode])
+    with m.Context(profile=True, multi=mode, n_targets=len(tlen), **(pre or {})) as ctx:
+        ctx.push(raw, off)
+        ui, d = ctx.pull_counts()
+        ab, st = ctx.finish_profile()
+    for k in ("mapped_inserts", "uniq", "multi", "purged", "iterations", "converged", "n_lists", "n_entries"):
+        assert st[k] == est[k], k
+    assert np.array_equal(ui, eui)
+    assert close(d, ed) and close(ab, eab)
+    assert est["multi"] > 0 and est["uniq"] > 0
+
+
+def test_synth_profile_genome_map(m, oracle, mixed):
+    # --genome style feature map: several sequences per feature (msam_profile.c:764-843)
+    raw, off, tlen, p = mixed
+    fmap = (np.arange(len(tlen)) % 7).astype(np.int32)
+    eab, est, eui, ed = oracle.profile(raw, off, None, len(tlen), 3, fmap=fmap, n_features=7)
+    with m.Context(profile=True, multi="prop", n_targets=len(tlen), n_features=7, fmap=fmap) as ctx:
+        ctx.push(raw, off)
+        ui, _ = ctx.pull_counts()
+        ab, st = ctx.finish_profile()
+    assert np.array_equal(ui, eui) and close(ab, eab)
+    assert (st["uniq"], st["multi"], st["purged"], st["iterations"]) == (est["uniq"], est["multi"], est["purged"], est["iterations"])
+
+
+@pytest.mark.parametrize("pre", [None, dict(l=80, p=95, z=80), dict(l=80, p=95, z=80, besthit=True)], ids=["plain", "fused", "besthit"])
+def test_synth_coverage(m, oracle, mixed, pre):
+    raw, off, tlen, p = mixed
+    idx = None if pre is None else oracle.filter_stream(raw, off, oracle.filter_cfg(**pre))
+    ecov, et, es, edepth = oracle.coverage(raw, off, idx, tlen, want_depth=True)
+    with m.Context(coverage=True, n_targets=len(tlen), target_len=tlen, **(pre or {})) as ctx:
+        ctx.push(raw, off)
+        cov, touched, total = ctx.finish_coverage()
+        assert np.array_equal(cov, ecov) and np.array_equal(touched, et) and np.array_equal(total, es)
+        for t in (0, len(tlen) // 2, len(tlen) - 1):
+            assert np.array_equal(ctx.pull_coverage(t), edepth[t])
+
+
+def test_chunked_push_equals_single(m, oracle, mixed):
+    # chunk boundaries from msg_split_point: no QNAME group straddles chunks
+    raw, off, tlen, p = mixed
+    n = len(off) - 1
+    opts = dict(l=80, p=95, z=80, besthit=True)
+    eidx = oracle.filter_stream(raw, off, oracle.filter_cfg(**opts))
+    eab, est, eui, _ = oracle.profile(raw, off, eidx, len(tlen), 3)
+    ecov = oracle.coverage(raw, off, eidx, tlen)
+    cuts = [0]
+    for want in (n // 3, 2 * n // 3):
+        k = m.split_point(raw, off, want)
+        assert 0 < k <= want
+        cuts.append(k)
+    cuts.append(n)
+    kept_all = []
+    with m.Context(profile=True, coverage=True, multi="proportional", n_targets=len(tlen), target_len=tlen, **opts) as ctx:
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            lo, hi = int(off[a]), int(off[b])
+            ctx.push(raw[lo:hi], off[a:b + 1] - off[a])
+            kept_all.append(ctx.pull_kept().astype(np.int64) + a)
+        ab, st = ctx.finish_profile()
+        ui, _ = ctx.pull_counts()
+        cov = ctx.finish_coverage()
+    assert np.array_equal(np.concatenate(kept_all), eidx)
+    assert np.array_equal(ui, eui) and close(ab, eab)
+    assert (st["mapped_inserts"], st["uniq"], st["multi"], st["purged"]) == (est["mapped_inserts"], est["uniq"], est["multi"], est["purged"])
+    for got, exp in zip(cov, ecov[:3]):
+        assert np.array_equal(got, exp)
+
+
+# ---------------------------------------------------------------- edge cases
+def _sam(text):
+    import samutil
+    return samutil.parse_sam_text(text)
+
+
+HDR = "@HD\tVN:1.6\tSO:queryname\n@SQ\tSN:A\tLN:1000\n@SQ\tSN:B\tLN:1000\n@SQ\tSN:C\tLN:500\n"
+
+
+def test_empty_and_unmapped(m):
+    s = _sam(HDR)
+    with m.Context(l=10, besthit=True, profile=True, coverage=True, n_targets=3, target_len=s.target_len) as ctx:
+        ctx.push(s.raw, s.off)
+        assert ctx.kept_count() == 0
+        ab, st = ctx.finish_profile()
+        assert not ab.any() and st["mapped_inserts"] == 0
+        cov, t, sm = ctx.finish_coverage()
+        assert not cov.any()
+    s = _sam(HDR + "u1\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\tIIII\nu2\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\tIIII\n")
+    with m.Context(profile=True, multi="equal", n_targets=3) as ctx:
+        ctx.push(s.raw, s.off)
+        ab, st = ctx.finish_profile()
+        assert not ab.any() and (st["mapped_inserts"], st["uniq"], st["multi"]) == (0, 0, 0)
+
+
+def test_missing_tags_errors(m, oracle):
+    s = _sam(HDR + "r1\t0\tA\t10\t60\t10M\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tAS:i:5\n")
+    with m.Context(l=5, n_targets=3) as ctx:                      # msam_filter.c:150-152
+        with pytest.raises(m.MsgError) as e:
+            ctx.push(s.raw, s.off)
+        assert e.value.code == m._lib.MSG_ENOTAG and "Either NM or MD must be present" in e.value.text
+    with pytest.raises(oracle.OracleError) as oe:
+        oracle.filter_stream(s.raw, s.off, oracle.filter_cfg(l=5))
+    assert oe.value.code == oracle.ORC_ENOTAG
+    with m.Context(besthit=True, n_targets=3) as ctx:             # plain --besthit never parses NM/MD (:104,145)
+        ctx.push(s.raw, s.off)
+        assert ctx.pull_kept().tolist() == [0]
+    s = _sam(HDR + "r1\t0\tA\t10\t60\t10M\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tNM:i:0\n")
+    with m.Context(besthit=True, n_targets=3) as ctx:             # msam_filter.c:219-221
+        with pytest.raises(m.MsgError) as e:
+            ctx.push(s.raw, s.off)
+        assert e.value.code == m._lib.MSG_ENOAS and "Required field AS not found" in e.value.text
+
+
+def test_aux_types_and_long_fields(m, oracle):
+    # every aux type before the tags we need, long Z/B fields (slow path), MD edge forms
+    seq, q = "A" * 50, "I" * 50
+    recs = [
+        f"a\t0\tA\t10\t60\t50M\t*\t0\t0\t{seq}\t{q}\tXA:A:x\tXc:i:-3\tXs:i:-300\tXi:i:-70000\tXI:i:3000000000\tXf:f:1.5\tXB:B:s,1,2,3\tNM:i:2\tMD:Z:10A20^CG0T18\tAS:i:44",
+        f"b\t0\tB\t10\t60\t10S40M\t*\t0\t0\t{seq}\t{q}\tXZ:Z:{'z' * 300}\tMD:Z:40\tNM:i:7\tAS:i:-5",
+        f"c\t16\tC\t10\t60\t20M5I25M\t*\t0\t0\t{seq}\t{q}\tAS:i:300\tMD:Z:A19^T0C24\tNM:i:1",
+        f"d\t0\tA\t10\t60\t25=1X24=\t*\t0\t0\t{seq}\t{q}\tNM:i:1\tAS:i:70000",
+        f"e\t0\tA\t10\t60\t5H45M5H\t*\t0\t0\t{'A' * 45}\t{'I' * 45}\tXH:H:1AE301\tNM:i:0\tAS:i:45",
+        f"{'n' * 200}\t0\tA\t10\t60\t50M\t*\t0\t0\t{seq}\t{q}\tNM:i:0\tAS:i:50",
+        f"{'n' * 200}\t256\tB\t10\t60\t30M20S\t*\t0\t0\t*\t*\tNM:i:1\tAS:i:50",
+    ]
+    s = _sam(HDR + "\n".join(recs) + "\n")
+    exp = oracle.record_stats(s.raw, s.off)
+    for slow in (False, True):
+        with m.Context(l=1, p=50, stats=True, besthit=True, n_targets=3, force_slow=slow) as ctx:
+            ctx.push(s.raw, s.off)
+            st = ctx.pull_stats()
+            kept = ctx.pull_kept()
+        for k in ("alen", "qlen", "qclip", "edit", "score"):
+            assert st[k].tolist() == exp[k].tolist(), (k, slow)
+        assert kept.tolist() == oracle.filter_stream(s.raw, s.off, oracle.filter_cfg(l=1, p=50, besthit=True)).tolist()
+
+
+def test_reopened_qname_and_unmapped_between(m, oracle):
+    # A, B, A is three pools for the filter (msam_filter.c:120-125); an unmapped record with a different
+    # name between two same-named mapped records splits the pool too, but the profile stage merges the
+    # two A groups when only tid != -1 records are compared (msam_profile.c:223-232).
+    a = "\t0\tA\t10\t60\t10M\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tNM:i:0\tAS:i:%d"
+    text = HDR + "x" + a % 10 + "\ny" + a % 5 + "\nx\t256\tB\t10\t60\t10M\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tNM:i:0\tAS:i:20\n"
+    text += "z" + a % 7 + "\nw\t4\t*\t0\t0\t*\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\nz\t256\tC\t10\t60\t10M\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tNM:i:0\tAS:i:9\n"
+    s = _sam(text)
+    for opts in (dict(besthit=True), dict(uniqhit=True), dict(l=5, besthit=True)):
+        exp = oracle.filter_stream(s.raw, s.off, oracle.filter_cfg(**opts))
+        with m.Context(n_targets=3, **opts) as ctx:
+            ctx.push(s.raw, s.off)
+            assert ctx.pull_kept().tolist() == exp.tolist()
+    for mode in ("all", "equal", "proportional", "ignore"):
+        eab, est, eui, ed = oracle.profile(s.raw, s.off, None, 3, SHARE[mode])
+        with m.Context(profile=True, multi=mode, n_targets=3) as ctx:
+            ctx.push(s.raw, s.off)
+            ui, d = ctx.pull_counts()
+            ab, st = ctx.finish_profile()
+        assert ui.tolist() == eui.tolist() and close(ab, eab) and close(d, ed)
+        assert (st["mapped_inserts"], st["uniq"], st["multi"]) == (est["mapped_inserts"], est["uniq"], est["multi"])
+
+
+def test_huge_group(m, oracle):
+    # one QNAME with 5000 alignments over 40 references: exercises the oversized-group serial kernel
+    rng = np.random.default_rng(7)
+    hdr = "@HD\tVN:1.6\tSO:queryname\n" + "".join(f"@SQ\tSN:r{i}\tLN:1000\n" for i in range(40))
+    lines = []
+    for k in range(5000):
+        lines.append(f"big\t{256 if k else 0}\tr{int(rng.integers(40))}\t{1 + int(rng.integers(900))}\t60\t10M\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tNM:i:0\tAS:i:{int(rng.integers(3))}")
+    lines.append("small\t0\tr3\t5\t60\t10M\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tNM:i:0\tAS:i:1")
+    s = _sam(hdr + "\n".join(lines) + "\n")
+    exp = oracle.filter_stream(s.raw, s.off, oracle.filter_cfg(besthit=True))
+    with m.Context(besthit=True, n_targets=40) as ctx:
+        ctx.push(s.raw, s.off)
+        assert ctx.pull_kept().tolist() == exp.tolist()
+    for mode in ("all", "equal", "proportional", "ignore"):
+        eab, est, eui, ed = oracle.profile(s.raw, s.off, None, 40, SHARE[mode])
+        with m.Context(profile=True, multi=mode, n_targets=40) as ctx:
+            ctx.push(s.raw, s.off)
+            ui, d = ctx.pull_counts()
+            ab, st = ctx.finish_profile()
+        assert ui.tolist() == eui.tolist() and close(d, ed) and close(ab, eab), mode
+        assert (st["mapped_inserts"], st["uniq"], st["multi"], st["purged"]) == (est["mapped_inserts"], est["uniq"], est["multi"], est["purged"])
+
+
+# ---------------------------------------------------------------- BASELINE sizes: size-independent properties
+def test_full_size_properties(m, oracle):
+    """configs[1] size (10 M PE150 alignments): idempotence of the filter, conservation laws of the
+    profile, and a bit-exact oracle comparison on a 1 M-record prefix."""
+    from msamtools_b200 import synth
+    p = synth.make_params("community", n_records=10_000_000, seed=13579)
+    raw, off, st = synth.generate(p)
+    tlen = synth.target_lengths(p)
+    n = len(off) - 1
+    opts = dict(l=80, p=95, z=80, besthit=True)
+    with m.Context(profile=True, multi="proportional", records=True, n_targets=len(tlen), **opts) as ctx:
+        ctx.push(raw, off)
+        kept = ctx.pull_kept()
+        rec, nrec = ctx.pull_records()
+        ab, pst = ctx.finish_profile()
+        ui, _ = ctx.pull_counts()
+    assert 0 < len(kept) < n and nrec == len(kept)
+    # kept indices are a permutation-free selection; within a QNAME group READ1 precedes READ2
+    assert len(np.unique(kept)) == len(kept)
+    # conservation: every insert is unique or multi; unique counts sum to 2*uniq (proportional mode)
+    assert pst["uniq"] + pst["multi"] == pst["mapped_inserts"]
+    assert int(ui.astype(np.int64).sum()) == 2 * pst["uniq"]
+    assert abs(ab.sum() - (pst["mapped_inserts"] - pst["purged"])) <= 1e-6 * pst["mapped_inserts"]
+    # idempotence: filtering the filtered stream again changes nothing (records are byte-identical)
+    off2 = m.index_records(rec)
+    with m.Context(records=True, n_targets=len(tlen), **opts) as ctx:
+        ctx.push(rec, off2)
+        assert ctx.kept_count() == nrec
+        rec2, _ = ctx.pull_records()
+    assert np.array_equal(rec, rec2)
+    # bit-exact against the oracle on a 1 M prefix cut at a QNAME boundary
+    k = m.split_point(raw, off, 1_000_000)
+    sub_raw, sub_off = raw[:int(off[k])], off[:k + 1]
+    exp = oracle.filter_stream(sub_raw, sub_off, oracle.filter_cfg(**opts))
+    assert np.array_equal(kept[kept < k], exp)
+    eab, est, eui, _ = oracle.profile(sub_raw, sub_off, exp, len(tlen), 3)
+    with m.Context(profile=True, multi="proportional", n_targets=len(tlen), **opts) as ctx:
+        ctx.push(sub_raw, sub_off)
+        ab1, st1 = ctx.finish_profile()
+        ui1, _ = ctx.pull_counts()
+    assert np.array_equal(ui1, eui) and close(ab1, eab)
+    assert (st1["iterations"], st1["purged"], st1["multi"]) == (est["iterations"], est["purged"], est["multi"])
