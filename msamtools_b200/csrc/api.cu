@@ -35,11 +35,22 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // grow but keep the first `keep` bytes (amortised doubling; used by the multi-mapper CSR)
+    cudaError_t reserve_keep(size_t bytes, size_t keep, cudaStream_t st) {
+        if (bytes <= cap && p) return cudaSuccess;
+        size_t want = bytes + bytes / 2 + 256;
+        void *np_ = nullptr;
+        cudaError_t e = cudaMalloc(&np_, want);
+        if (e != cudaSuccess) return e;
+        if (p && keep) { e = cudaMemcpyAsync(np_, p, keep, cudaMemcpyDeviceToDevice, st); if (e == cudaSuccess) e = cudaStreamSynchronize(st); }
+        if (p) cudaFree(p);
+        p = np_; cap = want;
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-struct CsrChunk { uint32_t *off = nullptr; int32_t *fid = nullptr; uint32_t nlists = 0, nent = 0; };
 
 struct NcclApi {
     void *h = nullptr;
@@ -93,7 +104,8 @@ struct msg_ctx {
 
     // profile accumulators
     uint32_t *d_ui = nullptr; double *d_d = nullptr; uint32_t *d_counters = nullptr;   // counters[8]
-    std::vector<CsrChunk> csr;
+    DevBuf csr_off, csr_fid; uint64_t csr_lists = 0, csr_ent = 0;     // multi-mapper lists (CSR), appended per chunk
+    DevBuf t_ui, t_d, t_cnt, t_cov;                                    // allreduce staging (n_ranks > 1)
     uint32_t *d_stamp = nullptr; uint32_t stamp_next = 0;
     double *d_U = nullptr, *d_a = nullptr, *d_inc = nullptr, *d_partial = nullptr, *d_delta = nullptr;
     uint32_t *d_purged = nullptr;
@@ -208,13 +220,16 @@ int profile_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
         unsigned long long tot = 0;
         rc = run_scan<unsigned long long>(c, InPcountPacked{p.pcount}, OutExclU64{c->scanv.as<unsigned long long>()}, m, &tot);
         if (rc) return rc;
-        CsrChunk ch; ch.nlists = (uint32_t)(tot >> 32); ch.nent = (uint32_t)tot;
-        if (ch.nlists) {
-            CU(cudaMalloc(&ch.off, ((size_t)ch.nlists + 1) * 4));
-            CU(cudaMalloc(&ch.fid, (size_t)ch.nent * 4));
-            c->csr.push_back(ch);
-            profile_fill_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(p, c->scanv.as<unsigned long long>(), ch.off, ch.fid); LAUNCHED(c);
-            CU(cudaMemcpyAsync(ch.off + ch.nlists, &c->csr.back().nent, 4, cudaMemcpyHostToDevice, c->stream));
+        const uint32_t nl = (uint32_t)(tot >> 32), ne = (uint32_t)tot;
+        if (nl) {
+            if (c->csr_lists + nl >= 0xffffffffull || c->csr_ent + ne >= 0xffffffffull) return fail(c, MSG_ERANGE, "multi-mapper CSR exceeds 2^32 entries on one GPU");
+            CU(c->csr_off.reserve_keep((c->csr_lists + nl + 1) * 4, (c->csr_lists + 1) * 4, c->stream));
+            CU(c->csr_fid.reserve_keep((c->csr_ent + ne + 1) * 4, c->csr_ent * 4, c->stream));
+            profile_fill_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(p, c->scanv.as<unsigned long long>(), c->csr_off.as<uint32_t>(),
+                                                                        c->csr_fid.as<int32_t>(), (uint32_t)c->csr_lists, (uint32_t)c->csr_ent); LAUNCHED(c);
+            c->csr_lists += nl; c->csr_ent += ne;
+            const uint32_t endv = (uint32_t)c->csr_ent;
+            CU(cudaMemcpyAsync(c->csr_off.as<uint32_t>() + c->csr_lists, &endv, 4, cudaMemcpyHostToDevice, c->stream));
         }
     }
     CU(cudaMemcpyAsync(&nbig, c->d_counters + 3, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -225,19 +240,20 @@ int profile_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
         if (!c->d_stamp) { CU(cudaMalloc(&c->d_stamp, (size_t)(g.n_features > 0 ? g.n_features : 1) * 4));
                            CU(cudaMemsetAsync(c->d_stamp, 0, (size_t)(g.n_features > 0 ? g.n_features : 1) * 4, c->stream)); }
         uint32_t *d_tot = reinterpret_cast<uint32_t *>(c->d_total);
-        profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, nullptr, nullptr, d_tot, 0); LAUNCHED(c);
+        profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, nullptr, nullptr, d_tot, 0, 0, 0); LAUNCHED(c);
         c->stamp_next += nbig + 1;
         if (prop) {
             uint32_t tot[2];
             CU(cudaMemcpyAsync(tot, d_tot, 8, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
             if (tot[0]) {
-                CsrChunk ch; ch.nlists = tot[0]; ch.nent = tot[1];
-                CU(cudaMalloc(&ch.off, ((size_t)ch.nlists + 1) * 4));
-                CU(cudaMalloc(&ch.fid, ((size_t)ch.nent + 1) * 4));
-                c->csr.push_back(ch);
-                profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, ch.off, ch.fid, d_tot, 1); LAUNCHED(c);
+                if (c->csr_lists + tot[0] >= 0xffffffffull || c->csr_ent + tot[1] >= 0xffffffffull) return fail(c, MSG_ERANGE, "multi-mapper CSR exceeds 2^32 entries on one GPU");
+                CU(c->csr_off.reserve_keep((c->csr_lists + tot[0] + 1) * 4, (c->csr_lists + 1) * 4, c->stream));
+                CU(c->csr_fid.reserve_keep((c->csr_ent + tot[1] + 2) * 4, c->csr_ent * 4, c->stream));
+                profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(),
+                                                           d_tot, 1, (uint32_t)c->csr_lists, (uint32_t)c->csr_ent); LAUNCHED(c);
                 c->stamp_next += nbig + 1;
+                c->csr_lists += tot[0]; c->csr_ent += tot[1];
             }
         }
         CU(cudaMemsetAsync(c->d_counters + 3, 0, 4, c->stream));
@@ -415,6 +431,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     ctx->decode_mode = mode;
 
     CUC(cudaMalloc(&ctx->d_err, 8)); CUC(cudaMalloc(&ctx->d_acct, 16)); CUC(cudaMalloc(&ctx->d_total, 16));
+    CUC(cudaMemset(ctx->d_acct, 0, 16));
     const size_t T = (size_t)(g.n_targets > 0 ? g.n_targets : 1), F = (size_t)(g.n_features > 0 ? g.n_features : 1);
     if (cfg->fmap) {
         CUC(cudaMalloc(&ctx->d_fmap, T * 4));
@@ -460,9 +477,9 @@ void msg_destroy(msg_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     DevBuf *bufs[] = {&c->raw, &c->off, &c->tid, &c->fb, &c->score, &c->hash, &c->nid, &c->st_alen, &c->st_qlen, &c->st_qclip, &c->st_edit,
-                      &c->segcnt, &c->segbase, &c->out_idx, &c->tile_sums, &c->pcount, &c->scanv, &c->biglist, &c->out_len, &c->out_off, &c->plan, &c->out_rec};
+                      &c->segcnt, &c->segbase, &c->out_idx, &c->tile_sums, &c->pcount, &c->scanv, &c->biglist, &c->out_len, &c->out_off, &c->plan, &c->out_rec,
+                      &c->csr_off, &c->csr_fid, &c->t_ui, &c->t_d, &c->t_cnt, &c->t_cov};
     for (DevBuf *b : bufs) b->release();
-    for (auto &ch : c->csr) { cudaFree(ch.off); cudaFree(ch.fid); }
     void *ptrs[] = {c->d_fmap, c->d_tlen, c->d_covbase, c->d_err, c->d_acct, c->d_total, c->d_ui, c->d_d, c->d_counters, c->d_stamp, c->d_U, c->d_a,
                     c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -482,12 +499,10 @@ int msg_reset(msg_ctx *c)
     const size_t T = (size_t)(g.n_targets > 0 ? g.n_targets : 1), F = (size_t)(g.n_features > 0 ? g.n_features : 1);
     CU(cudaMemsetAsync(c->d_err, 0, 4, c->stream));
     CU(cudaMemsetAsync(c->d_err + 1, 0xff, 4, c->stream));
-    CU(cudaMemsetAsync(c->d_acct, 0, 16, c->stream));
     if (g.want_profile) {
         CU(cudaMemsetAsync(c->d_ui, 0, F * 4, c->stream)); CU(cudaMemsetAsync(c->d_d, 0, F * 8, c->stream));
         CU(cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
-        for (auto &ch : c->csr) { cudaFree(ch.off); cudaFree(ch.fid); }
-        c->csr.clear();
+        c->csr_lists = c->csr_ent = 0;
     }
     if (g.want_coverage) {
         CU(cudaMemsetAsync(c->d_diff, 0, (size_t)(c->cov_cells ? c->cov_cells : 1) * 4, c->stream));
@@ -656,7 +671,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
     int rc;
     // work on copies so that finish can be called again after more chunks
     uint32_t *ui = c->d_ui; double *dd = c->d_d; uint32_t *cnt = c->d_counters;
-    DevBuf t_ui, t_d, t_cnt;
+    DevBuf &t_ui = c->t_ui, &t_d = c->t_d, &t_cnt = c->t_cnt;
     if (g.n_ranks > 1) {
         CU(t_ui.reserve((size_t)(F ? F : 1) * 4)); CU(t_d.reserve((size_t)(F ? F : 1) * 8)); CU(t_cnt.reserve(32));
         CU(cudaMemcpyAsync(t_ui.p, c->d_ui, (size_t)F * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -672,7 +687,9 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
     CU(cudaMemcpyAsync(hc, cnt, 16, cudaMemcpyDeviceToHost, c->stream));
     if (F) { em_init_kernel<<<nblocks(F, 256), 256, 0, c->stream>>>(ui, dd, g.share_type == MSG_MULTI_EQUAL, c->d_U, c->d_a, F); LAUNCHED(c); }
     uint64_t nl_local = 0, ne_local = 0;
-    for (auto &ch : c->csr) { nl_local += ch.nlists; ne_local += ch.nent; }
+    nl_local = c->csr_lists; ne_local = c->csr_ent;
+    const uint32_t nl32 = (uint32_t)c->csr_lists;
+    const uint32_t em_grid = nl32 ? (nblocks(nl32, 256) < 148u * 8u ? nblocks(nl32, 256) : 148u * 8u) : 0;
     unsigned long long nl_global = nl_local;
     if (g.share_type == MSG_MULTI_PROPORTIONAL) {
         if (g.n_ranks > 1) {
@@ -685,7 +702,14 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
         const uint32_t nb = nblocks(F, 256);
         for (int k = 1; k < 20; k++) {                                                            // msam_profile.c:331
             CU(cudaMemsetAsync(c->d_inc, 0, (size_t)F * 8, c->stream));
-            for (auto &ch : c->csr) { em_gather_kernel<<<nblocks(ch.nlists, 256), 256, 0, c->stream>>>(ch.off, ch.fid, ch.nlists, c->d_a, c->d_inc); LAUNCHED(c); }
+            if (nl32) {
+                if (F <= EM_SMEM_F) {
+                    em_gather_smem_kernel<<<em_grid, 256, (size_t)F * 16, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_inc, F);
+                } else {
+                    em_gather_kernel<<<em_grid, 256, 0, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_inc);
+                }
+                LAUNCHED(c);
+            }
             if ((rc = allreduce(c, c->d_inc, F, ncclFloat64, ncclSum))) return rc;
             double delta = 0;
             if (F) {
@@ -699,7 +723,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
             if (delta < 1e-10) { s.em_converged = 1; break; }                                     // :383
         }
         CU(cudaMemsetAsync(c->d_purged, 0, 4, c->stream));
-        for (auto &ch : c->csr) { em_purged_kernel<<<nblocks(ch.nlists, 256), 256, 0, c->stream>>>(ch.off, ch.fid, ch.nlists, c->d_a, c->d_purged); LAUNCHED(c); }
+        if (nl32) { em_purged_kernel<<<em_grid, 256, 0, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_purged); LAUNCHED(c); }
         if ((rc = allreduce(c, c->d_purged, 1, ncclUint32, ncclSum))) return rc;
         CU(cudaMemcpyAsync(&s.purged_insert_count, c->d_purged, 4, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -709,7 +733,6 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
     s.mapped_inserts = hc[0]; s.uniq_mapper_count = hc[1]; s.multi_mapper_count = hc[2];
     s.multi_lists = nl_global; s.multi_entries = ne_local;
     if (st) *st = s;
-    t_ui.release(); t_d.release(); t_cnt.release();
     return check_device_errors(c);
 }
 
@@ -723,7 +746,7 @@ int msg_finish_coverage(msg_ctx *c, uint8_t *covered, int64_t *touched, int64_t 
     int rc;
     if (T == 0) return MSG_OK;
     CU(cudaMemcpyAsync(c->d_depth, c->d_diff, (size_t)c->cov_cells * 4, cudaMemcpyDeviceToDevice, c->stream));
-    DevBuf t_cov;
+    DevBuf &t_cov = c->t_cov;
     uint8_t *cov = c->d_covered;
     if (g.n_ranks > 1) {
         CU(t_cov.reserve(T));
@@ -743,7 +766,6 @@ int msg_finish_coverage(msg_ctx *c, uint8_t *covered, int64_t *touched, int64_t 
     CU(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += T * 17;
     c->cov_finished = true;
-    t_cov.release();
     return check_device_errors(c);
 }
 

@@ -170,13 +170,13 @@ __global__ void __launch_bounds__(256) profile_count_kernel(const ProfParams p)
 
 // proportional: heads with pcount>0 write their list; scanv[j] = (lists before << 32) | entries before
 __global__ void __launch_bounds__(256) profile_fill_kernel(const ProfParams p, const unsigned long long *scanv,
-                                                           uint32_t *mm_off, int32_t *mm_fid)
+                                                           uint32_t *mm_off, int32_t *mm_fid, uint32_t list_base, uint32_t ent_base)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= p.m) return;
     if (p.pcount[j] == 0) return;
     const unsigned long long sv = scanv[j];
-    const uint32_t li = (uint32_t)(sv >> 32), eo = (uint32_t)sv;
+    const uint32_t li = list_base + (uint32_t)(sv >> 32), eo = ent_base + (uint32_t)sv;
     mm_off[li] = eo;
     uint32_t size;
     walk_group(p, j, stream_at(p, j), &size, ActStore{mm_fid + eo}, p.big_threshold);
@@ -186,10 +186,11 @@ __global__ void __launch_bounds__(256) profile_fill_kernel(const ProfParams p, c
 // ub_target_hit stamp algorithm (msam_profile.c:131-145) with a u32 stamp per feature.
 // Lists for proportional mode are appended to big_fid / big_off.
 __global__ void profile_big_kernel(const ProfParams p, uint32_t nbig, uint32_t *stamp, uint32_t stamp_base,
-                                   uint32_t *big_off, int32_t *big_fid, uint32_t *big_tot /*[0]=lists,[1]=entries*/, int fill)
+                                   uint32_t *big_off, int32_t *big_fid, uint32_t *big_tot /*[0]=lists,[1]=entries*/, int fill,
+                                   uint32_t list_base, uint32_t ent_base)
 {
     if (blockIdx.x || threadIdx.x) return;
-    uint32_t nl = 0, ne = 0;
+    uint32_t nl = fill ? list_base : 0, ne = fill ? ent_base : 0;
     for (uint32_t b = 0; b < nbig; b++) {
         const uint64_t j = p.big[b];
         const uint32_t r0 = stream_at(p, j);
@@ -261,15 +262,36 @@ __global__ void em_init_from_U_kernel(const double *U, double *a, uint32_t n)
 }
 
 // one thread per multi-mapper list: s = sum a[f] in list order; inc[f] += a[f]/s   (:341-365)
+// Large catalogs (F up to 1e6): the F-sized vectors live in L2, contention per address is low,
+// so the adds go straight to global memory.
 __global__ void __launch_bounds__(256) em_gather_kernel(const uint32_t *mm_off, const int32_t *mm_fid, uint32_t nlists,
                                                         const double *a, double *inc)
 {
-    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlists) return;
-    uint32_t b = mm_off[l], e = mm_off[l + 1];
-    double s = 0;
-    for (uint32_t k = b; k < e; k++) s += a[mm_fid[k]];
-    if (s > 0) for (uint32_t k = b; k < e; k++) { int32_t f = mm_fid[k]; atomicAdd(inc + f, a[f] / s); }
+    for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < nlists; l += gridDim.x * blockDim.x) {
+        uint32_t b = mm_off[l], e = mm_off[l + 1];
+        double s = 0;
+        for (uint32_t k = b; k < e; k++) s += a[mm_fid[k]];
+        if (s > 0) for (uint32_t k = b; k < e; k++) { int32_t f = mm_fid[k]; atomicAdd(inc + f, a[f] / s); }
+    }
+}
+// Small feature sets (genomes, F <= EM_SMEM_F): millions of lists hit a few hundred addresses.
+// Each CTA keeps a private copy of a[] and inc[] in shared memory and flushes inc once.
+constexpr uint32_t EM_SMEM_F = 2048;
+__global__ void __launch_bounds__(256) em_gather_smem_kernel(const uint32_t *mm_off, const int32_t *mm_fid, uint32_t nlists,
+                                                             const double *a, double *inc, uint32_t F)
+{
+    extern __shared__ double s_em[];
+    double *sa = s_em, *si = s_em + F;
+    for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { sa[i] = a[i]; si[i] = 0.0; }
+    __syncthreads();
+    for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < nlists; l += gridDim.x * blockDim.x) {
+        uint32_t b = mm_off[l], e = mm_off[l + 1];
+        double s = 0;
+        for (uint32_t k = b; k < e; k++) s += sa[mm_fid[k]];
+        if (s > 0) for (uint32_t k = b; k < e; k++) { int32_t f = mm_fid[k]; atomicAdd(si + f, sa[f] / s); }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { double v = si[i]; if (v != 0.0) atomicAdd(inc + i, v); }
 }
 
 // a_new = U + inc; flush < 1e-20; per-block partial of sum (a_new - a_old)^2 in a fixed order  (:369-379)
@@ -304,12 +326,11 @@ __global__ void __launch_bounds__(256) em_delta_kernel(const double *partial, ui
 __global__ void __launch_bounds__(256) em_purged_kernel(const uint32_t *mm_off, const int32_t *mm_fid, uint32_t nlists,
                                                         const double *a, uint32_t *purged)
 {
-    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t z = 0;
-    if (l < nlists) {
+    for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < nlists; l += gridDim.x * blockDim.x) {
         double s = 0;
         for (uint32_t k = mm_off[l]; k < mm_off[l + 1]; k++) s += a[mm_fid[k]];
-        z = (s == 0);
+        z += (s == 0);
     }
     z = warp_sum_u32(z);
     if ((threadIdx.x & 31) == 0 && z) atomicAdd(purged, z);
