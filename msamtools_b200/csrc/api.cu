@@ -14,7 +14,9 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -82,6 +84,7 @@ struct msg_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     bool has_filter = false, need_stats = false, cov_fused = false;
+    uint32_t lay_lpr = 0, lay_hc = 0, lay_tc = 0;     // decode window layout (probe_layout)
     uint32_t decode_mode = 0;
 
     // static tables
@@ -90,7 +93,8 @@ struct msg_ctx {
 
     // chunk staging (msg_push) and per-chunk columns
     DevBuf raw, off, tid, fb, score, hash, nid, st_alen, st_qlen, st_qclip, st_edit;
-    DevBuf segcnt, segbase, out_idx, tile_sums, pcount, scanv, biglist;
+    DevBuf kbase, worklist, gmeta, out_idx, tile_sums, pcount, scanv, biglist;
+    uint32_t *d_wl = nullptr;                  // [0] best-hit worklist length [1] profile worklist length
     DevBuf out_len, out_off, plan, out_rec;
     const uint8_t *cur_raw = nullptr; const uint64_t *cur_off = nullptr;
     uint64_t cur_n = 0, cur_nbytes = 0;
@@ -212,7 +216,17 @@ int profile_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
     p.ui = c->d_ui; p.d = c->d_d; p.counters = c->d_counters;
     p.pcount = prop ? c->pcount.as<uint32_t>() : nullptr;
     p.big = c->biglist.as<uint32_t>(); p.big_cap = big_cap; p.big_threshold = 1024; p.err = c->d_err;
-    profile_count_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(p); LAUNCHED(c);
+    CU(c->worklist.reserve((std::max<uint64_t>(n, m) / 32 + 2) * 4));
+    if (prop) CU(c->gmeta.reserve(m));
+    CU(cudaMemsetAsync(c->d_wl + 1, 0, 4, c->stream));
+    uint8_t *gmeta = prop ? c->gmeta.as<uint8_t>() : nullptr;
+    const uint32_t pgrid = std::min<uint32_t>(nblocks(m / 32 + 1, 256), 148u * 4u);
+    if ((uint32_t)g.n_features <= 4096u)
+        profile_warp_count_kernel<true><<<nblocks(m, 256), 256, (size_t)g.n_features * 4, c->stream>>>(p, gmeta, c->worklist.as<uint32_t>(), c->d_wl + 1);
+    else
+        profile_warp_count_kernel<false><<<nblocks(m, 256), 256, 0, c->stream>>>(p, gmeta, c->worklist.as<uint32_t>(), c->d_wl + 1);
+    LAUNCHED(c);
+    profile_walk_count_kernel<<<pgrid, 256, 0, c->stream>>>(p, c->worklist.as<uint32_t>(), c->d_wl + 1); LAUNCHED(c);
 
     uint32_t nbig = 0;
     if (prop) {
@@ -225,8 +239,10 @@ int profile_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
             if (c->csr_lists + nl >= 0xffffffffull || c->csr_ent + ne >= 0xffffffffull) return fail(c, MSG_ERANGE, "multi-mapper CSR exceeds 2^32 entries on one GPU");
             CU(c->csr_off.reserve_keep((c->csr_lists + nl + 1) * 4, (c->csr_lists + 1) * 4, c->stream));
             CU(c->csr_fid.reserve_keep((c->csr_ent + ne + 1) * 4, c->csr_ent * 4, c->stream));
-            profile_fill_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(p, c->scanv.as<unsigned long long>(), c->csr_off.as<uint32_t>(),
-                                                                        c->csr_fid.as<int32_t>(), (uint32_t)c->csr_lists, (uint32_t)c->csr_ent); LAUNCHED(c);
+            profile_warp_fill_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(p, gmeta, c->scanv.as<unsigned long long>(), c->csr_off.as<uint32_t>(),
+                                                                             c->csr_fid.as<int32_t>(), (uint32_t)c->csr_lists, (uint32_t)c->csr_ent); LAUNCHED(c);
+            profile_walk_fill_kernel<<<pgrid, 256, 0, c->stream>>>(p, c->scanv.as<unsigned long long>(), c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(),
+                                                                   (uint32_t)c->csr_lists, (uint32_t)c->csr_ent, c->worklist.as<uint32_t>(), c->d_wl + 1); LAUNCHED(c);
             c->csr_lists += nl; c->csr_ent += ne;
             const uint32_t endv = (uint32_t)c->csr_ent;
             CU(cudaMemcpyAsync(c->csr_off.as<uint32_t>() + c->csr_lists, &endv, 4, cudaMemcpyHostToDevice, c->stream));
@@ -280,7 +296,56 @@ int records_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
     return MSG_OK;
 }
 
-int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readable, const uint64_t *d_off, uint64_t n)
+// Pick the decode kernel's window split from the sizes of the chunk's first records: head window
+// covers 36 + qname (+ cigar) for ~98 % of them, tail window their aux block.  h_raw/h_off may be
+// null (device-resident chunk): the sample is then copied back once per context.
+int probe_layout(msg_ctx *c, const uint8_t *h_raw, const uint64_t *h_off, const uint8_t *d_raw, const uint64_t *d_off,
+                 uint64_t nbytes, uint64_t n, bool need_cigar, bool need_aux)
+{
+    const uint64_t S = n < 4096 ? n : 4096;
+    std::vector<uint64_t> offv; std::vector<uint8_t> rawv;
+    if (!h_raw) {
+        if (c->lay_lpr) return MSG_OK;                       // keep the first decision for resident chunks
+        offv.resize(S + 1);
+        CU(cudaMemcpyAsync(offv.data(), d_off, (S + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        uint64_t span = offv[S] <= nbytes ? offv[S] : nbytes;
+        rawv.resize(span + 1);
+        CU(cudaMemcpyAsync(rawv.data(), d_raw, span, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += span + (S + 1) * 8;
+        h_raw = rawv.data(); h_off = offv.data();
+    }
+    std::vector<uint32_t> heads, auxs;
+    heads.reserve(S); auxs.reserve(S);
+    for (uint64_t k = 0; k < S; k++) {
+        const uint64_t o = h_off[k], len = h_off[k + 1] - o;
+        if (len < 36 || o + len > nbytes) continue;
+        const uint8_t *r = h_raw + o;
+        uint32_t lq = r[12], nc = (uint32_t)r[16] | (uint32_t)r[17] << 8;
+        int32_t ls = (int32_t)((uint32_t)r[20] | (uint32_t)r[21] << 8 | (uint32_t)r[22] << 16 | (uint32_t)r[23] << 24);
+        if (ls < 0) continue;
+        uint64_t ao = 36ull + lq + 4ull * nc + (((uint64_t)ls + 1) >> 1) + (uint64_t)ls;
+        if (ao > len) continue;
+        heads.push_back(36 + lq + (need_cigar ? 4 * nc : 0));
+        auxs.push_back((uint32_t)(len - ao));
+    }
+    uint32_t hc = 4, tc = need_aux ? 2 : 0;
+    if (!heads.empty()) {
+        std::sort(heads.begin(), heads.end()); std::sort(auxs.begin(), auxs.end());
+        const size_t q = (heads.size() * 98) / 100 < heads.size() ? (heads.size() * 98) / 100 : heads.size() - 1;
+        hc = (15 + heads[q] + 15) / 16;
+        tc = need_aux ? (auxs[q] + 15 + 15) / 16 : 0;
+    }
+    if (hc < 4) hc = 4;
+    uint32_t lpr = hc + tc <= 8 ? 8 : 16;
+    if (hc + tc > 16) { if (hc > 12) hc = 12; tc = 16 - hc; }
+    c->lay_lpr = lpr; c->lay_hc = hc; c->lay_tc = tc;
+    return MSG_OK;
+}
+
+int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readable, const uint64_t *d_off, uint64_t n,
+              const uint8_t *h_raw = nullptr, const uint64_t *h_off = nullptr)
 {
     const msg_config &g = c->cfg;
     if (n >= 0xffffffffull) return fail(c, MSG_EINVAL, "a chunk may hold at most 2^32-2 records");
@@ -316,8 +381,12 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
     p.diff = c->d_diff; p.covbase = c->d_covbase; p.tlen = c->d_tlen; p.covered = c->d_covered; p.n_targets = g.n_targets;
     p.err = c->d_err; p.acct = c->d_acct;
 
+    { int prc = probe_layout(c, h_raw, h_off, d_raw, d_off, nbytes, n, (mode & DM_NEED_CIGAR) != 0, (mode & DM_NEED_AUX) != 0); if (prc) return prc; }
+    p.head_chunks = c->lay_hc; p.tail_chunks = c->lay_tc;
     CU(cudaEventRecord(k0, c->stream));
-    decode_kernel<<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); LAUNCHED(c);
+    if (c->lay_lpr == 8) decode_kernel<8><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p);
+    else                 decode_kernel<16><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p);
+    LAUNCHED(c);
     CU(cudaEventRecord(k1, c->stream));
     c->ev_decode.push_back({k0, k1});
 
@@ -331,13 +400,17 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
             rc = run_scan<uint32_t>(c, InFlagBit{p.fb, FB_INPOOL, FB_INPOOL}, OutCompact{c->out_idx.as<uint32_t>()}, n, &tot);
             if (rc) return rc;
         } else {
-            CU(c->segcnt.reserve(n * 4)); CU(c->segbase.reserve(n * 4));
-            BestHitParams bp{p.fb, p.score, c->segcnt.as<uint32_t>(), n, g.hit_mode == MSG_HIT_UNIQUE, c->d_err};
-            besthit_select_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(bp); LAUNCHED(c);
-            rc = run_scan<uint32_t>(c, InU32{c->segcnt.as<uint32_t>()}, OutExclU32{c->segbase.as<uint32_t>()}, n, &tot);
+            CU(c->kbase.reserve(n * 4)); CU(c->worklist.reserve((n / 32 + 2) * 4));
+            CU(cudaMemsetAsync(c->d_wl, 0, 4, c->stream));
+            BestHitParams bp{p.fb, p.score, n, g.hit_mode == MSG_HIT_UNIQUE, c->d_err, c->worklist.as<uint32_t>(), c->d_wl};
+            const uint32_t wgrid = std::min<uint32_t>(nblocks(n / 32 + 1, 256), 148u * 4u);
+            besthit_warp_select_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(bp); LAUNCHED(c);
+            besthit_walk_select_kernel<<<wgrid, 256, 0, c->stream>>>(bp); LAUNCHED(c);
+            rc = run_scan<uint32_t>(c, InFlagBit{p.fb, FB_KEEP, FB_KEEP}, OutExclU32{c->kbase.as<uint32_t>()}, n, &tot);
             if (rc) return rc;
-            besthit_emit_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(p.fb, c->segcnt.as<uint32_t>(), c->segbase.as<uint32_t>(),
-                                                                         c->out_idx.as<uint32_t>(), n); LAUNCHED(c);
+            besthit_warp_emit_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(p.fb, c->kbase.as<uint32_t>(), c->out_idx.as<uint32_t>(), n); LAUNCHED(c);
+            besthit_walk_emit_kernel<<<wgrid, 256, 0, c->stream>>>(p.fb, c->kbase.as<uint32_t>(), c->out_idx.as<uint32_t>(), n,
+                                                                   c->worklist.as<uint32_t>(), c->d_wl); LAUNCHED(c);
         }
         stream = c->out_idx.as<uint32_t>(); m = tot; c->have_stream = true;
     }
@@ -408,6 +481,12 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     if (cfg->device < 0 || cfg->device >= ndev) return fail(c, MSG_EINVAL, "device %d out of range (0..%d)", cfg->device, ndev - 1);
     ce = cudaSetDevice(cfg->device);
     if (ce != cudaSuccess) return fail(c, MSG_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(ce));
+    {   // The decode kernel touches short, scattered spans: ask the L2 to fetch single 32-byte sectors
+        // from HBM instead of 64/128-byte granules (a hint; MSG_L2_FETCH=64|128 overrides for A/B runs).
+        size_t gran = 32;
+        if (const char *e = getenv("MSG_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
+    }
 
     msg_ctx *ctx = new msg_ctx();
     ctx->cfg = *cfg; ctx->cfg.fmap = nullptr; ctx->cfg.target_len = nullptr; ctx->cfg.nccl_unique_id = nullptr;
@@ -432,6 +511,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
 
     CUC(cudaMalloc(&ctx->d_err, 8)); CUC(cudaMalloc(&ctx->d_acct, 16)); CUC(cudaMalloc(&ctx->d_total, 16));
     CUC(cudaMemset(ctx->d_acct, 0, 16));
+    CUC(cudaMalloc(&ctx->d_wl, 8));
     const size_t T = (size_t)(g.n_targets > 0 ? g.n_targets : 1), F = (size_t)(g.n_features > 0 ? g.n_features : 1);
     if (cfg->fmap) {
         CUC(cudaMalloc(&ctx->d_fmap, T * 4));
@@ -477,11 +557,11 @@ void msg_destroy(msg_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     DevBuf *bufs[] = {&c->raw, &c->off, &c->tid, &c->fb, &c->score, &c->hash, &c->nid, &c->st_alen, &c->st_qlen, &c->st_qclip, &c->st_edit,
-                      &c->segcnt, &c->segbase, &c->out_idx, &c->tile_sums, &c->pcount, &c->scanv, &c->biglist, &c->out_len, &c->out_off, &c->plan, &c->out_rec,
+                      &c->kbase, &c->worklist, &c->gmeta, &c->out_idx, &c->tile_sums, &c->pcount, &c->scanv, &c->biglist, &c->out_len, &c->out_off, &c->plan, &c->out_rec,
                       &c->csr_off, &c->csr_fid, &c->t_ui, &c->t_d, &c->t_cnt, &c->t_cov};
     for (DevBuf *b : bufs) b->release();
     void *ptrs[] = {c->d_fmap, c->d_tlen, c->d_covbase, c->d_err, c->d_acct, c->d_total, c->d_ui, c->d_d, c->d_counters, c->d_stamp, c->d_U, c->d_a,
-                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
+                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_wl, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &pr : c->ev_decode) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto &pr : c->ev_total) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -583,7 +663,7 @@ int msg_push(msg_ctx *c, const uint8_t *raw, size_t nbytes, const uint64_t *rec_
     CU(cudaMemsetAsync((uint8_t *)c->raw.p + nbytes, 0, 64, c->stream));
     CU(cudaMemcpyAsync(c->off.p, rec_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += nbytes + (nrec + 1) * 8;
-    return run_chunk(c, c->raw.as<uint8_t>(), nbytes, nbytes + 64, c->off.as<uint64_t>(), nrec);
+    return run_chunk(c, c->raw.as<uint8_t>(), nbytes, nbytes + 64, c->off.as<uint64_t>(), nrec, raw, rec_off);
 }
 
 int msg_push_device(msg_ctx *c, const uint8_t *d_raw, size_t nbytes, const uint64_t *d_rec_off, size_t nrec)

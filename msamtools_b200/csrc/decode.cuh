@@ -7,30 +7,26 @@
 // of mFilterFile (msam_filter.c:132-138,181-183).
 //
 // HBM plan.  A BAM record is [core 36 B | qname | cigar | SEQ | QUAL | aux]; the
-// result depends on everything except SEQ/QUAL (~70 % of a PE150 record).  One CTA
-// takes 128 consecutive records.  Phase A stages the first 64 B of every record with
-// coalesced 16-byte streaming loads (4 lanes per record); each thread then reads its
-// record's lengths from shared memory and publishes the exact extra spans it needs
-// (rest of qname/cigar, and the aux tail located by the NEXT record's offset); phase B
-// fetches those with 8 lanes per record.  SEQ/QUAL sectors are never requested.
-// Parsing runs out of shared memory with an odd word stride per record slot so that
-// thread-per-record accesses are bank-conflict-free.  Records whose qname/cigar or aux
-// exceed the slot fall back to a byte-wise global-memory parser (same code, other
-// accessor), which is also what `debug_force_slow` exercises in the tests.
+// result depends on everything except SEQ/QUAL (~75 % of a PE150 record).  One CTA
+// takes 128 consecutive records and stages, per record, two speculative windows with
+// coalesced 16-byte streaming loads (LPR = 8 or 16 lanes per record, one load each):
+//   head window: `hc` chunks from the record start rounded down to 16 B
+//   tail window: `tc` chunks ending at the NEXT record's offset rounded up to 16 B
+//                (the aux fields sit at the very end of a record, so the offset index
+//                 locates them without reading the record first)
+// hc/tc come from a host-side probe of the chunk's typical qname/cigar/aux sizes.  There is
+// one dependent load phase (offsets -> windows); SEQ/QUAL sectors are never requested.
+// Parsing runs out of shared memory, thread per record, with an odd word stride per slot
+// (bank-conflict-free); the MD string is classified four bytes at a time (SWAR) into
+// letter/caret bit masks and the reference's tokenizer rule becomes one add + popc.
+// Records that do not fit their windows fall back to a byte-wise global-memory parser
+// (same template code, other accessor), which `debug_force_slow` exercises in the tests.
 #pragma once
 #include "common.cuh"
 
 namespace msg {
 
-constexpr int DEC_R      = 128;                         // records == threads per CTA
-constexpr int HEAD_FIX   = 4;                           // 16-B chunks always staged
-constexpr int HEAD_X     = 3;                           // optional extra head chunks
-constexpr int AUX_C      = 5;                           // aux chunks
-constexpr int HEAD_WORDS = (HEAD_FIX + HEAD_X) * 4;     // 28
-constexpr int AUX_WORDS  = AUX_C * 4;                   // 20
-constexpr int SLOT_WORDS = HEAD_WORDS + AUX_WORDS + 1;  // 49: odd -> conflict-free thread-per-slot
-static_assert(HEAD_X + AUX_C == 8, "phase B uses 8 lanes per record");
-static_assert((SLOT_WORDS & 1) == 1, "slot stride must be odd");
+constexpr int DEC_R = 128;                              // records == threads per CTA
 
 struct DecodeParams {
     const uint8_t  *raw;
@@ -52,6 +48,7 @@ struct DecodeParams {
     const uint32_t *tlen;
     uint8_t  *covered;
     int32_t  n_targets;
+    uint32_t head_chunks, tail_chunks;   // window split, head_chunks + tail_chunks <= LPR
     // accounting
     uint32_t *err;                  // [0] flags, [1] first offending record (atomicMin)
     unsigned long long *acct;       // [0] algorithmic bytes, [1] slow records
@@ -59,10 +56,11 @@ struct DecodeParams {
 
 // ---------------------------------------------------------------- accessors
 struct SmAcc {                       // bytes staged in a shared-memory slot region
+    static constexpr bool kSwar = true;
     const uint32_t *w; uint32_t rel;
     __device__ __forceinline__ uint32_t u32(uint32_t x) const {
         uint32_t b = rel + x, i = b >> 2;
-        return __funnelshift_r(w[i], w[i + 1], (b & 3u) * 8u);
+        return __funnelshift_r(w[i], w[i + 1], b << 3);          // SHF uses the shift amount mod 32
     }
     __device__ __forceinline__ uint32_t u8(uint32_t x) const {
         uint32_t b = rel + x;
@@ -70,6 +68,7 @@ struct SmAcc {                       // bytes staged in a shared-memory slot reg
     }
 };
 struct GlAcc {                       // byte-wise global memory (slow path)
+    static constexpr bool kSwar = false;
     const uint8_t *p;
     __device__ __forceinline__ uint32_t u8(uint32_t x) const { return p[x]; }
     __device__ __forceinline__ uint32_t u32(uint32_t x) const {
@@ -103,6 +102,29 @@ __device__ __forceinline__ RecCore parse_core(const A &hd, uint64_t rec_len64)
     return c;
 }
 
+// same fields from a staged slot: 6 aligned LDS + 5 funnel shifts instead of 5 unaligned reads
+__device__ __forceinline__ RecCore parse_core(const SmAcc &hd, uint64_t rec_len64)
+{
+    RecCore c;
+    const uint32_t *w = hd.w + (hd.rel >> 2);
+    const uint32_t sh = hd.rel << 3;
+    const uint32_t w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5], w6 = w[6];
+    c.bad = rec_len64 < 36 || rec_len64 > 0x7fffffffull;
+    c.rec_len = (uint32_t)rec_len64;
+    c.tid = (int32_t)__funnelshift_r(w1, w2, sh);
+    c.pos = (int32_t)__funnelshift_r(w2, w3, sh);
+    c.lq  = __funnelshift_r(w3, w4, sh) & 0xffu;
+    const uint32_t f4 = __funnelshift_r(w4, w5, sh);
+    c.nc = f4 & 0xffffu; c.flag = f4 >> 16;
+    c.lseq = (int32_t)__funnelshift_r(w5, w6, sh);
+    if (c.lseq < 0) { c.bad = true; c.lseq = 0; }
+    uint64_t ao = 36ull + c.lq + 4ull * c.nc + (((uint64_t)c.lseq + 1) >> 1) + (uint64_t)c.lseq;
+    if (ao > rec_len64) { c.bad = true; ao = rec_len64; }
+    if (c.bad) { c.aux_off = 0; c.aux_len = 0; c.lq = 0; c.nc = 0; }
+    else { c.aux_off = (uint32_t)ao; c.aux_len = c.rec_len - c.aux_off; }
+    return c;
+}
+
 struct CigSum { int32_t wM, wI, wD, wClip, wOther; };
 
 template <class A>
@@ -110,18 +132,35 @@ __device__ __forceinline__ CigSum cigar_sum(const A &hd, uint32_t x0, uint32_t n
 {
     CigSum s = {0, 0, 0, 0, 0};
     for (uint32_t k = 0; k < nc; k++) {
-        uint32_t c = hd.u32(x0 + 4 * k);
-        uint32_t op = c & 0xfu; int32_t w = (int32_t)(c >> 4);
-        if (op == 0 || op == 7 || op == 8) s.wM += w;           // M = X
-        else if (op == 1) s.wI += w;                            // I
-        else if (op == 2) s.wD += w;                            // D
-        else if (op == 4 || op == 5) s.wClip += w;              // S H
-        else if (op != 3 && op != 6) s.wOther += w;             // B and undefined ops: NM path only (mBamVector.c:32-33)
+        const uint32_t c = hd.u32(x0 + 4 * k);
+        const uint32_t bit = 1u << (c & 0xfu); const int32_t w = (int32_t)(c >> 4);
+        s.wM     += (bit & 0x0181u) ? w : 0;            // M = X
+        s.wI     += (bit & 0x0002u) ? w : 0;            // I
+        s.wD     += (bit & 0x0004u) ? w : 0;            // D
+        s.wClip  += (bit & 0x0030u) ? w : 0;            // S H
+        s.wOther += (bit & 0xfe00u) ? w : 0;            // B and undefined ops: NM path only (mBamVector.c:32-33)
     }
     return s;
 }
 
 struct AuxOut { bool hasMD, hasNM, hasAS; int32_t md_letters, nm, as; };
+
+// size of a fixed-width aux value by type byte, 0 for Z/H/B/invalid.  Nibble table over
+// 'A'..'P' and 'a'..'p' plus 's'/'S' handled apart keeps this at a handful of instructions.
+__device__ __forceinline__ uint32_t aux_fixed_size(uint32_t ty)
+{
+    // index = ty - 'A' for 'A'..'P' (upper) / ty - 'a' (lower); nibble = size
+    //            P O N M L K J I H G F E D C B A
+    const unsigned long long UP = 0x0000000400000101ull;   // A=1 C=1 I=4
+    //            p o n m l k j i h g f e d c b a
+    const unsigned long long LO = 0x0000000400408100ull;   // c=1 d=8 f=4 i=4
+    uint32_t r = 0;
+    const uint32_t u = ty - 'A', l = ty - 'a';
+    if (u < 16) r = (uint32_t)(UP >> (4 * u)) & 0xfu;
+    if (l < 16) r = (uint32_t)(LO >> (4 * l)) & 0xfu;
+    if ((ty | 0x20u) == 's') r = 2;
+    return r;
+}
 
 __device__ __forceinline__ int32_t aux_int(uint32_t ty, uint32_t v)
 {   // htslib bam_aux2i then the reference's (int32_t) truncation
@@ -132,6 +171,86 @@ __device__ __forceinline__ int32_t aux_int(uint32_t ty, uint32_t v)
     case 'S': return (int32_t)(v & 0xffff);
     case 'i': case 'I': return (int32_t)v;
     default:  return 0;
+    }
+}
+
+// NUL-terminated field starting at y: *zend = index of the NUL.  false if no NUL before `limit`.
+template <class A>
+__device__ __forceinline__ bool z_skip(const A &ax, uint32_t y, uint32_t limit, uint32_t *zend)
+{
+    if constexpr (A::kSwar) {
+        for (uint32_t z = y; z < limit; z += 4) {
+            uint32_t w = ax.u32(z);
+            uint32_t nul = ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w | 0x7f7f7f7fu);      // exact zero-byte flags (bit 7 of each byte)
+            if (nul) { uint32_t k = (uint32_t)(__ffs((int)nul) - 8) >> 3; if (z + k >= limit) return false; *zend = z + k; return true; }
+        }
+        return false;
+    } else {
+        for (uint32_t z = y; z < limit; z++) if (ax.u8(z) == 0) { *zend = z; return true; }
+        return false;
+    }
+}
+
+// MD tokenizer (mBamVector.c:112-118): a maximal run of bytes outside "^0123456789" adds its
+// length to `edit` iff it does not start the string and the byte before it is not '^'.
+template <class A>
+__device__ __forceinline__ bool md_scan_bytes(const A &ax, uint32_t y, uint32_t limit, int32_t *letters_out, uint32_t *zend)
+{
+    int32_t letters = 0; bool in_run = false, counted = false; uint32_t prev = 0;
+    for (uint32_t z = y; z < limit; z++) {
+        uint32_t c = ax.u8(z);
+        if (c == 0) { *letters_out = letters; *zend = z; return true; }
+        bool delim = (c == '^') || (c >= '0' && c <= '9');
+        if (delim) in_run = false;
+        else {
+            if (!in_run) { in_run = true; counted = (z > y) && (prev != '^'); }
+            letters += counted ? 1 : 0;
+        }
+        prev = c;
+    }
+    return false;
+}
+
+__device__ __forceinline__ uint32_t byteflags_to_bits(uint32_t m)
+{   // flags at bits 7,15,23,31 -> bits 0..3
+    return (((m >> 7) * 0x00204081u) >> 21) & 0xfu;
+}
+
+template <class A>
+__device__ __forceinline__ bool md_scan(const A &ax, uint32_t y, uint32_t limit, int32_t *letters_out, uint32_t *zend)
+{
+    if constexpr (!A::kSwar) return md_scan_bytes(ax, y, limit, letters_out, zend);
+    else {
+        // one bit per character (strings up to 32 chars; longer or non-ASCII -> byte loop)
+        uint32_t L = 0, C = 0;
+        for (uint32_t pos = 0; pos < 32; pos += 4) {
+            if (y + pos >= limit) return false;
+            const uint32_t w = ax.u32(y + pos);
+            if (w & 0x80808080u) return md_scan_bytes(ax, y, limit, letters_out, zend);
+            uint32_t nul = ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w | 0x7f7f7f7fu);
+            const uint32_t x = w ^ 0x5e5e5e5eu;                                           // '^'
+            uint32_t car = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+            const uint32_t dig = (w + 0x50505050u) & ~(w + 0x46464646u) & 0x80808080u;    // '0'..'9' (bytes < 0x80)
+            uint32_t let = ~(nul | car | dig) & 0x80808080u;
+            uint32_t k = 4;
+            if (nul) {
+                k = (uint32_t)(__ffs((int)nul) - 8) >> 3;                                 // first NUL byte in this word
+                const uint32_t keep = (1u << (8 * k)) - 1u;
+                let &= keep; car &= keep;
+            }
+            L |= byteflags_to_bits(let) << pos;
+            C |= byteflags_to_bits(car) << pos;
+            if (nul) {
+                if (y + pos + k >= limit) return false;
+                // runs that start the string or follow a caret are not counted: adding their lowest bit
+                // to L ripples through the run and clears it
+                const uint32_t S = ((C << 1) | 1u) & L;
+                *letters_out = __popc(L & (L + S));
+                *zend = y + pos + k;
+                return true;
+            }
+        }
+        return md_scan_bytes(ax, y, limit, letters_out, zend);
     }
 }
 
@@ -148,37 +267,20 @@ __device__ __forceinline__ AuxOut aux_scan(const A &ax, uint32_t aux_len, bool n
         bool isMD = need_mdnm && tag == TAG_MD && !o.hasMD;
         bool isNM = need_mdnm && tag == TAG_NM && !o.hasNM;
         bool isAS = need_as && tag == TAG_AS && !o.hasAS;
-        uint32_t vsz = 0;
-        if (ty == 'A' || ty == 'c' || ty == 'C') vsz = 1;
-        else if (ty == 's' || ty == 'S') vsz = 2;
-        else if (ty == 'i' || ty == 'I' || ty == 'f') vsz = 4;
-        else if (ty == 'd') vsz = 8;
+        const uint32_t vsz = aux_fixed_size(ty);
         if (vsz) {
             if (y + vsz > aux_len) break;
             if (isNM | isAS) {
-                int32_t v = aux_int(ty, ax.u32(y));
+                int32_t v = aux_int(ty, vsz == 1 ? (w >> 24) : ax.u32(y));   // 1-byte values ride in the header word
                 if (isNM) { o.hasNM = true; o.nm = v; }
                 if (isAS) { o.hasAS = true; o.as = v; }
             }
             if (isMD) { o.hasMD = true; o.md_letters = 0; }
             y += vsz;
         } else if (ty == 'Z' || ty == 'H') {
-            // MD tokenizer (mBamVector.c:112-118): a maximal run of bytes outside
-            // "^0123456789" adds its length iff it does not start the string and
-            // the byte before it is not '^'.
-            int32_t letters = 0; bool in_run = false, counted = false; uint32_t prev = 0;
-            uint32_t z = y; bool term = false;
-            while (z < aux_len) {
-                uint32_t c = ax.u8(z);
-                if (c == 0) { term = true; break; }
-                bool delim = (c == '^') || (c >= '0' && c <= '9');
-                if (delim) in_run = false;
-                else {
-                    if (!in_run) { in_run = true; counted = (z > y) && (prev != '^'); }
-                    letters += counted ? 1 : 0;
-                }
-                prev = c; z++;
-            }
+            int32_t letters = 0; uint32_t z = y; bool term;
+            if (isMD) term = md_scan(ax, y, aux_len, &letters, &z);
+            else      term = z_skip(ax, y, aux_len, &z);
             if (!term) break;
             if (isMD) { o.hasMD = true; o.md_letters = letters; }
             if (isNM) { o.hasNM = true; o.nm = 0; }
@@ -201,32 +303,25 @@ __device__ __forceinline__ AuxOut aux_scan(const A &ax, uint32_t aux_len, bool n
     return o;
 }
 
-template <class A>
-__device__ __forceinline__ uint32_t name_hash(const A &hd, uint32_t lq)
-{
-    uint32_t h = 0x811c9dc5u ^ lq;
-    for (uint32_t k = 0; k < lq; k += 4) {
-        uint32_t w = hd.u32(36 + k);
-        uint32_t rem = lq - k;
-        if (rem < 4) w &= (1u << (rem * 8)) - 1u;
-        h = (h ^ w) * 0x9E3779B1u;
-        h ^= h >> 15;
-    }
-    h *= 0x85ebca6bu; h ^= h >> 13;
-    return h;
-}
+__device__ __forceinline__ uint32_t hash_step(uint32_t h, uint32_t w) { h = (h ^ w) * 0x9E3779B1u; return h ^ (h >> 15); }
+__device__ __forceinline__ uint32_t hash_fin(uint32_t h) { h *= 0x85ebca6bu; return h ^ (h >> 13); }
 
+// QNAME hash (any equal byte strings hash equal) and byte-exact equality with another record's QNAME
+// in one pass over the name words.  `other` is only read when do_eq (lengths already equal).
 template <class A, class B>
-__device__ __forceinline__ bool name_equal(const A &a, uint32_t lqa, const B &b, uint32_t lqb)
+__device__ __forceinline__ uint32_t name_hash_eq(const A &a, uint32_t lq, const B &other, bool do_eq, bool *eq)
 {
-    if (lqa != lqb) return false;
-    for (uint32_t k = 0; k < lqa; k += 4) {
-        uint32_t x = a.u32(36 + k) ^ b.u32(36 + k);
-        uint32_t rem = lqa - k;
-        if (rem < 4) x &= (1u << (rem * 8)) - 1u;
-        if (x) return false;
+    uint32_t h = 0x811c9dc5u ^ lq, diff = 0;
+    for (uint32_t k = 0; k < lq; k += 4) {
+        uint32_t w = a.u32(36 + k);
+        const uint32_t rem = lq - k;
+        const uint32_t mask = rem < 4 ? (1u << (rem * 8)) - 1u : 0xffffffffu;
+        w &= mask;
+        h = hash_step(h, w);
+        if (do_eq) diff |= (w ^ other.u32(36 + k)) & mask;
     }
-    return true;
+    *eq = do_eq && diff == 0;
+    return hash_fin(h);
 }
 
 // coverage of one alignment: diff-array +1/-1 per M/=/X run (msam_coverage.c:60-86)
@@ -296,13 +391,15 @@ __device__ __forceinline__ RecResult finish_record(const DecodeParams &p, const 
     return r;
 }
 
+template <int LPR>
 __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ DecodeParams p)
 {
+    constexpr int SLOT_WORDS = LPR * 4 + 1;            // odd stride: thread-per-slot reads are conflict-free
     __shared__ uint32_t s_slot[DEC_R * SLOT_WORDS + 2];
     __shared__ uint64_t s_off[DEC_R + 1];
-    __shared__ uint64_t s_auxa[DEC_R];
     __shared__ uint64_t s_offprev;
-    __shared__ uint8_t  s_xh[DEC_R], s_auxn[DEC_R], s_slow[DEC_R], s_lq[DEC_R];
+    __shared__ uint32_t s_hb[DEC_R], s_tb[DEC_R];
+    __shared__ uint8_t  s_slow[DEC_R], s_lq[DEC_R];
 
     const uint32_t t = threadIdx.x;
     const uint64_t t0 = (uint64_t)blockIdx.x * DEC_R;
@@ -311,25 +408,41 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
     const bool active = t < nrec;
     const uint32_t mode = p.mode;
     const bool force_slow = mode & DM_FORCE_SLOW;
+    const uint32_t hc = p.head_chunks, tc = p.tail_chunks;
 
-    if (active) s_off[t] = p.off[i];
-    if (t == 0) { s_off[nrec] = p.off[t0 + nrec]; s_offprev = t0 ? p.off[t0 - 1] : 0; }
+    // offsets: one coalesced load; each thread also fetches its successor's offset so that the
+    // 16-byte chunk indices of both windows are known without a second barrier round
+    if (active) {
+        const uint64_t o = p.off[i], o1 = p.off[i + 1];
+        s_off[t] = o;
+        if (t == nrec - 1) s_off[nrec] = o1;
+        s_hb[t] = (uint32_t)(o >> 4);                                       // head window: first chunk
+        s_tb[t] = (uint32_t)((o1 + 15ull) >> 4) - (hc + tc);                // tail window: chunk index of lane `sub` is s_tb + sub
+    }
+    if (t == 0) s_offprev = t0 ? p.off[t0 - 1] : 0;
     __syncthreads();
 
-    // ---- phase A: first HEAD_FIX chunks of every record, 4 lanes per record
+    // ---- stage both windows of every record: LPR lanes per record, one 16-byte load each
     if (!force_slow) {
-        for (uint32_t g = t; g < nrec * HEAD_FIX; g += DEC_R) {
-            uint32_t r = g / HEAD_FIX, cidx = g % HEAD_FIX;
-            uint64_t a = (s_off[r] & ~15ull) + 16ull * cidx;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (a + 16 <= p.nbytes_readable) v = ldg_stream128(reinterpret_cast<const uint4 *>(p.raw + a));
-            uint32_t *d = s_slot + r * SLOT_WORDS + cidx * 4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        const uint32_t nchunks = (uint32_t)(p.nbytes_readable >> 4);
+        const uint32_t sub = t % LPR, r0 = t / LPR;
+        const bool head = sub < hc, go = sub < hc + tc;
+#pragma unroll
+        for (uint32_t it = 0; it < LPR; it++) {
+            const uint32_t r = it * (DEC_R / LPR) + r0;
+            if (go && r < nrec) {
+                const uint32_t cidx = (head ? s_hb[r] : s_tb[r]) + sub;     // a tail window that starts before the buffer wraps to a huge index
+                if (cidx < nchunks) {
+                    const uint4 v = ldg_stream128(reinterpret_cast<const uint4 *>(p.raw) + cidx);
+                    uint32_t *d = s_slot + r * SLOT_WORDS + sub * 4;
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                }
+            }
         }
     }
     __syncthreads();
 
-    // ---- core fields, extents of the extra spans
+    // ---- core fields; does the record fit its windows?
     RecCore c; c.bad = false; c.lq = 0; c.nc = 0; c.aux_len = 0; c.aux_off = 0; c.flag = 0; c.tid = -1; c.pos = 0; c.lseq = 0; c.rec_len = 0;
     bool slow = force_slow;
     uint32_t rel = 0, arel = 0;
@@ -339,53 +452,20 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
         rel = (uint32_t)(o & 15u);
         if (force_slow) c = parse_core(GlAcc{p.raw + o}, len);
         else            c = parse_core(SmAcc{slot, rel}, len);
-        uint32_t need_head = 36 + c.lq + ((mode & DM_NEED_CIGAR) ? 4 * c.nc : 0);
-        uint32_t hchunks = (rel + need_head + 15) >> 4;
-        uint32_t achunks = 0; uint64_t a0 = 0;
+        const uint32_t need_head = 36 + c.lq + ((mode & DM_NEED_CIGAR) ? 4 * c.nc : 0);
+        if (rel + need_head > 16 * hc) slow = true;
         if ((mode & DM_NEED_AUX) && c.aux_len) {
-            a0 = (o + c.aux_off) & ~15ull;
-            achunks = (uint32_t)((((o + c.rec_len + 15) & ~15ull) - a0) >> 4);
-            arel = (uint32_t)((o + c.aux_off) & 15u);
+            const uint64_t wend = (o + c.rec_len + 15ull) & ~15ull;           // end of the tail window
+            const uint64_t astart = o + c.aux_off;
+            if (wend < 16ull * tc || astart < wend - 16ull * tc) slow = true;
+            else arel = (uint32_t)(astart - (wend - 16ull * tc));
         }
-        if (hchunks > HEAD_FIX + HEAD_X || achunks > AUX_C) slow = true;
-        s_xh[t]   = slow ? 0 : (uint8_t)(hchunks > HEAD_FIX ? hchunks - HEAD_FIX : 0);
-        s_auxn[t] = slow ? 0 : (uint8_t)achunks;
-        s_auxa[t] = a0;
         s_slow[t] = slow;
         s_lq[t]   = (uint8_t)c.lq;
     }
     __syncthreads();
 
-    // ---- phase B: exact extra spans, 8 lanes per record (3 head + 5 aux)
-    if (!force_slow) {
-        const uint32_t lane = t & 31u, wbase = t & ~31u;
-#pragma unroll
-        for (uint32_t it = 0; it < 8; it++) {
-            uint32_t r = wbase + it * 4 + (lane >> 3), sub = lane & 7u;
-            if (r < nrec) {
-                uint64_t a; uint32_t *d; bool go;
-                if (sub < HEAD_X) {
-                    go = sub < s_xh[r];
-                    a = (s_off[r] & ~15ull) + 16ull * (HEAD_FIX + sub);
-                    d = s_slot + r * SLOT_WORDS + (HEAD_FIX + sub) * 4;
-                } else {
-                    uint32_t cidx = sub - HEAD_X;
-                    go = cidx < s_auxn[r];
-                    a = s_auxa[r] + 16ull * cidx;
-                    d = s_slot + r * SLOT_WORDS + HEAD_WORDS + cidx * 4;
-                }
-                if (go) {
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (a + 16 <= p.nbytes_readable) v = ldg_stream128(reinterpret_cast<const uint4 *>(p.raw + a));
-                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    unsigned long long alg = 0;
-    uint32_t nslow = 0;
+    uint32_t alg = 0, nslow = 0;
     if (active) {
         const uint64_t o = s_off[t];
         RecResult r;
@@ -397,11 +477,10 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
             GlAcc g{p.raw + o};
             GlAcc gx{p.raw + o + c.aux_off};
             r = finish_record(p, c, g, gx);
-            if (mode & DM_WANT_HASH) h = name_hash(g, c.lq);
-            if (i > 0) {
-                uint64_t op = t ? s_off[t - 1] : s_offprev;
+            {
+                const uint64_t op = t ? s_off[t - 1] : s_offprev;
                 GlAcc gp{p.raw + op};
-                eq = name_equal(g, c.lq, gp, gp.u8(12));
+                h = name_hash_eq(g, c.lq, gp, i > 0 && gp.u8(12) == c.lq, &eq);
             }
             if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
                 if (c.tid < p.n_targets) cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
@@ -410,18 +489,15 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
             r.fbits |= FB_SLOW; nslow = 1;
         } else {
             SmAcc hd{slot, rel};
-            SmAcc ax{slot + HEAD_WORDS, arel};
+            SmAcc ax{slot + hc * 4, arel};
             r = finish_record(p, c, hd, ax);
-            if (mode & DM_WANT_HASH) h = name_hash(hd, c.lq);
-            if (i > 0) {
-                if (t > 0 && !s_slow[t - 1]) {
-                    SmAcc pv{slot - SLOT_WORDS, (uint32_t)(s_off[t - 1] & 15u)};
-                    eq = name_equal(hd, c.lq, pv, s_lq[t - 1]);
-                } else {
-                    uint64_t op = t ? s_off[t - 1] : s_offprev;
-                    GlAcc gp{p.raw + op};
-                    eq = name_equal(hd, c.lq, gp, gp.u8(12));
-                }
+            if (t > 0 && !s_slow[t - 1]) {
+                SmAcc pv{slot - SLOT_WORDS, (uint32_t)(s_off[t - 1] & 15u)};
+                h = name_hash_eq(hd, c.lq, pv, s_lq[t - 1] == c.lq, &eq);
+            } else {
+                const uint64_t op = t ? s_off[t - 1] : s_offprev;
+                GlAcc gp{p.raw + op};
+                h = name_hash_eq(hd, c.lq, gp, i > 0 && gp.u8(12) == c.lq, &eq);
             }
             if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
                 if (c.tid < p.n_targets) cover_record(hd, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
@@ -436,12 +512,13 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
         if (p.hash)  p.hash[i] = h;
         if (p.alen)  { p.alen[i] = r.alen; p.qlen[i] = r.qlen; p.qclip[i] = r.qclip; p.edit[i] = r.edit; }
         // algorithmic bytes A(rec) = 8 (index) + 36 + qname [+ cigar] [+ aux]   
-        alg = 8ull + 36ull + c.lq + ((mode & DM_NEED_CIGAR) ? 4ull * c.nc : 0ull) + ((mode & DM_NEED_AUX) ? c.aux_len : 0u);
+        alg = 8u + 36u + c.lq + ((mode & DM_NEED_CIGAR) ? 4u * c.nc : 0u) + ((mode & DM_NEED_AUX) ? c.aux_len : 0u);
+        if (alg > (1u << 26)) alg = 1u << 26;                       // keeps the 32-lane sum inside 32 bits
     }
-    alg = warp_sum_u64(alg);
-    nslow = warp_sum_u32(nslow);
+    alg = __reduce_add_sync(0xffffffffu, alg);                      // REDUX: one instruction per warp
+    nslow = __reduce_add_sync(0xffffffffu, nslow);
     if ((t & 31u) == 0) {
-        if (alg) atomicAdd(p.acct, alg);
+        if (alg) atomicAdd(p.acct, (unsigned long long)alg);
         if (nslow) atomicAdd(p.acct + 1, (unsigned long long)nslow);
     }
 }

@@ -122,64 +122,218 @@ __device__ __forceinline__ bool group_head(const ProfParams &p, uint64_t j, uint
     return true;
 }
 
-__global__ void __launch_bounds__(256) profile_count_kernel(const ProfParams p)
+// ---- head-walks-its-group path (worklist fallback; exact for any group size) ----------------
+// Applies the share rule of the group headed at stream position j; returns list length for
+// proportional mode (0 otherwise).  ins/uq/mu are incremented for the caller's counters.
+__device__ __forceinline__ uint32_t count_group_walk(const ProfParams &p, uint64_t j, uint32_t r, uint32_t &ins, uint32_t &uq, uint32_t &mu)
 {
-    __shared__ uint32_t s_cnt[3];
-    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t ins = 0, uq = 0, mu = 0;
-    if (j < p.m) {
-        uint32_t pc = 0;
-        const uint32_t r = stream_at(p, j);
-        const int32_t t = p.tid[r];
-        if (t != -1 && group_head(p, j, r)) {
-            int32_t f0 = -1, f1 = -1; uint32_t size = 0;
-            uint32_t nd = walk_group(p, j, r, &size, ActFirst{&f0, &f1}, p.big_threshold);
-            if (size > p.big_threshold) {
-                uint32_t slot = atomicAdd(p.counters + 3, 1u);
-                if (slot < p.big_cap) p.big[slot] = (uint32_t)j;
-            } else if (size > 0) {
-                ins = 1;
-                if (nd == 1) { atomicAdd(p.ui + f0, 2u); uq = 1; }                               // :75-78,87-91,152-159
-                else {
-                    mu = 1;
-                    switch (p.share_type) {
-                    case 1: walk_group(p, j, r, &size, ActAddUi{p.ui, 2u}, p.big_threshold); break;               // :99-102,169-173
-                    case 2:
-                        if (size == 2) { atomicAdd(p.ui + f0, 1u); atomicAdd(p.ui + f1, 1u); }                    // :103-106
-                        else walk_group(p, j, r, &size, ActAddD{p.d, 1.0 / (int)nd}, p.big_threshold);            // :175-182
-                        break;
-                    case 3: pc = nd; break;                                                                        // :107-121,184-186
-                    default: break;                                                                                // ignore
-                    }
-                }
+    int32_t f0 = -1, f1 = -1; uint32_t size = 0, pc = 0;
+    const uint32_t nd = walk_group(p, j, r, &size, ActFirst{&f0, &f1}, p.big_threshold);
+    if (size > p.big_threshold) {
+        const uint32_t slot = atomicAdd(p.counters + 3, 1u);
+        if (slot < p.big_cap) p.big[slot] = (uint32_t)j;
+    } else if (size > 0) {
+        ins++;
+        if (nd == 1) { atomicAdd(p.ui + f0, 2u); uq++; }                                       // :75-78,87-91,152-159
+        else {
+            mu++;
+            switch (p.share_type) {
+            case 1: walk_group(p, j, r, &size, ActAddUi{p.ui, 2u}, p.big_threshold); break;               // :99-102,169-173
+            case 2:
+                if (size == 2) { atomicAdd(p.ui + f0, 1u); atomicAdd(p.ui + f1, 1u); }                    // :103-106
+                else walk_group(p, j, r, &size, ActAddD{p.d, 1.0 / (int)nd}, p.big_threshold);            // :175-182
+                break;
+            case 3: pc = nd; break;                                                                        // :107-121,184-186
+            default: break;                                                                                // ignore
             }
         }
+    }
+    return pc;
+}
+
+__global__ void __launch_bounds__(256) profile_walk_count_kernel(const ProfParams p, const uint32_t *worklist, const uint32_t *wl_count)
+{
+    const uint32_t nw = *wl_count;
+    uint32_t ins = 0, uq = 0, mu = 0;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nw; q += gridDim.x * blockDim.x) {
+        const uint64_t j = worklist[q];
+        const uint32_t pc = count_group_walk(p, j, stream_at(p, j), ins, uq, mu);
         if (p.pcount) p.pcount[j] = pc;
     }
-    ins = warp_sum_u32(ins); uq = warp_sum_u32(uq); mu = warp_sum_u32(mu);
-    if ((threadIdx.x & 31) == 0) {
-        if (ins) atomicAdd(&s_cnt[0], ins);
-        if (uq) atomicAdd(&s_cnt[1], uq);
-        if (mu) atomicAdd(&s_cnt[2], mu);
+    if (ins) atomicAdd(p.counters + 0, ins);
+    if (uq)  atomicAdd(p.counters + 1, uq);
+    if (mu)  atomicAdd(p.counters + 2, mu);
+}
+
+// proportional: worklist heads with pcount>0 write their list; scanv[j] = (lists before << 32) | entries before
+__global__ void __launch_bounds__(256) profile_walk_fill_kernel(const ProfParams p, const unsigned long long *scanv, uint32_t *mm_off, int32_t *mm_fid,
+                                                                uint32_t list_base, uint32_t ent_base, const uint32_t *worklist, const uint32_t *wl_count)
+{
+    const uint32_t nw = *wl_count;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nw; q += gridDim.x * blockDim.x) {
+        const uint64_t j = worklist[q];
+        if (p.pcount[j] == 0) continue;
+        const unsigned long long sv = scanv[j];
+        const uint32_t li = list_base + (uint32_t)(sv >> 32), eo = ent_base + (uint32_t)sv;
+        mm_off[li] = eo;
+        uint32_t size;
+        walk_group(p, j, stream_at(p, j), &size, ActStore{mm_fid + eo}, p.big_threshold);
+    }
+}
+
+// ---- main path: one stream record per lane ---------------------------------------------------
+// Group heads come from comparing every valid record (tid != -1) with the previous valid one
+// (shuffle for neighbours in the window, a short look-back for the window's first); lanes of
+// the same (group, feature) find each other with MATCH.ANY, the lowest lane of each match set is
+// the feature's first appearance (msam_profile.c:136-142), and popc of those gives the number
+// of distinct features.  Groups that leave the 32-record window go to the worklist.
+constexpr uint8_t GM_MEMBER = 1, GM_HEAD = 2, GM_FIRST = 4;
+
+struct GroupView {
+    uint32_t gmask, gs;      // valid lanes of my group in this window, lane of its head
+    bool member;             // valid record of a group that lies entirely inside the window
+    bool head;               // ... and I am its head
+    bool open_head;          // head of a group that leaves the window on the right
+    int32_t feat;            // my feature id (members only)
+    uint32_t r;
+};
+
+__device__ __forceinline__ GroupView group_view(const ProfParams &p, uint64_t j, uint64_t w0)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t NONE = 0xffffffffu;
+    GroupView v;
+    const bool inb = j < p.m;
+    v.r = inb ? stream_at(p, j) : 0u;
+    int32_t t = inb ? p.tid[v.r] : -1;
+    bool valid = inb && t != -1;                                                     // msam_profile.c:223-225
+    if (valid && (t < 0 || t >= p.n_targets)) { atomicOr(p.err, DERR_FORMAT); valid = false; }
+    const uint32_t mynid = valid ? p.nid[v.r] : 0u, myhash = valid ? p.hash[v.r] : 0u;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+
+    // previous / next valid record outside the window (lane 0 looks back, lane 31 looks ahead)
+    uint32_t out_r = NONE, out_nid = 0, out_hash = 0;
+    if (lane == 0) {
+        for (uint64_t k = w0; k-- > 0;) { const uint32_t rk = stream_at(p, k); if (p.tid[rk] != -1) { out_r = rk; break; } }
+    } else if (lane == 31) {
+        for (uint64_t k = w0 + 32; k < p.m; k++) { const uint32_t rk = stream_at(p, k); if (p.tid[rk] != -1) { out_r = rk; break; } }
+    }
+    if ((lane == 0 || lane == 31) && out_r != NONE) { out_nid = p.nid[out_r]; out_hash = p.hash[out_r]; }
+    const uint32_t prev_r = __shfl_sync(0xffffffffu, out_r, 0), prev_nid = __shfl_sync(0xffffffffu, out_nid, 0), prev_hash = __shfl_sync(0xffffffffu, out_hash, 0);
+    const uint32_t next_r = __shfl_sync(0xffffffffu, out_r, 31), next_nid = __shfl_sync(0xffffffffu, out_nid, 31), next_hash = __shfl_sync(0xffffffffu, out_hash, 31);
+
+    // compare with the previous valid record (:226)
+    const uint32_t lowv = vmask & ((1u << lane) - 1u);
+    const int pl = lowv ? 31 - __clz((int)lowv) : 0;
+    uint32_t pn = __shfl_sync(0xffffffffu, mynid, pl), ph = __shfl_sync(0xffffffffu, myhash, pl), pr = __shfl_sync(0xffffffffu, v.r, pl);
+    bool have_prev = lowv != 0;
+    if (!have_prev) { pn = prev_nid; ph = prev_hash; pr = prev_r; have_prev = prev_r != NONE; }
+    bool same = false;
+    if (valid && have_prev) same = (mynid == pn) || (myhash == ph && qname_equal_global(p.raw, p.off, v.r, pr));
+    const bool ghead = valid && !same;
+    const uint32_t hmask = __ballot_sync(0xffffffffu, ghead);
+
+    const uint32_t le = hmask & (0xffffffffu >> (31u - lane));
+    const uint32_t gt = lane == 31 ? 0u : (hmask & (0xffffffffu << (lane + 1)));
+    const bool open_left = le == 0;
+    v.gs = open_left ? 0u : 31u - (uint32_t)__clz((int)le);
+    const uint32_t e = gt ? (uint32_t)__ffs((int)gt) - 1u : 32u;
+    v.gmask = vmask & (e == 32 ? 0xffffffffu : ((1u << e) - 1u)) & (0xffffffffu << v.gs);
+    // does the window's last group continue?  compare the next valid record with the last valid lane
+    const int ll = vmask ? 31 - __clz((int)vmask) : 0;
+    const uint32_t ln = __shfl_sync(0xffffffffu, mynid, ll), lh = __shfl_sync(0xffffffffu, myhash, ll), lr = __shfl_sync(0xffffffffu, v.r, ll);
+    bool tail_same = false;                                                          // warp-uniform
+    if (next_r != NONE && vmask) tail_same = (ln == next_nid) || (lh == next_hash && qname_equal_global(p.raw, p.off, lr, next_r));
+    const bool open_right = gt == 0 && tail_same;
+    v.member = valid && !open_left && !open_right;
+    v.head = v.member && lane == v.gs;
+    v.open_head = valid && !open_left && open_right && lane == v.gs;
+    v.feat = valid ? feature_of(p, t) : -1;
+    return v;
+}
+
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(256) profile_warp_count_kernel(const ProfParams p, uint8_t *gmeta, uint32_t *worklist, uint32_t *wl_count)
+{
+    extern __shared__ uint32_t s_hist[];                 // SMEM_HIST: CTA-private ui histogram (small feature sets)
+    __shared__ uint32_t s_cnt[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    if (SMEM_HIST) for (uint32_t k = threadIdx.x; k < (uint32_t)p.n_features; k += blockDim.x) s_hist[k] = 0;
+    __syncthreads();
+    uint32_t *ui = SMEM_HIST ? s_hist : p.ui;
+
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t w0 = j & ~31ull;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (w0 < p.m) {
+        const GroupView v = group_view(p, j, w0);
+        if (v.open_head) { const uint32_t slot = atomicAdd(wl_count, 1u); worklist[slot] = (uint32_t)j; }
+        __syncwarp();
+        const unsigned long long key = v.member ? (((unsigned long long)v.gs << 32) | (uint32_t)v.feat) : ((1ull << 40) | lane);
+        const uint32_t mm = __match_any_sync(0xffffffffu, key);
+        const bool first = v.member && lane == (uint32_t)__ffs((int)mm) - 1u;                       // first appearance of this feature
+        const uint32_t fm = __ballot_sync(0xffffffffu, first) & v.gmask;
+        const uint32_t nd = __popc(fm), size = __popc(v.gmask);
+        const bool multi = nd > 1;
+        uint32_t pc = 0;
+        if (v.member) {
+            if (!multi) { if (v.head) atomicAdd(ui + v.feat, 2u); }                                 // :75-78,87-91,152-159
+            else if (first) {
+                if (p.share_type == 1) atomicAdd(ui + v.feat, 2u);                                   // :99-102,169-173
+                else if (p.share_type == 2) {
+                    if (size == 2) atomicAdd(ui + v.feat, 1u);                                       // :103-106
+                    else atomicAdd(p.d + v.feat, 1.0 / (int)nd);                                     // :175-182
+                }
+            }
+            if (v.head && multi && p.share_type == 3) pc = nd;                                       // :107-121,184-186
+        }
+        if (j < p.m) {
+            if (p.pcount) p.pcount[j] = pc;
+            if (gmeta) gmeta[j] = (uint8_t)((v.member ? GM_MEMBER : 0) | (v.head ? GM_HEAD : 0) | (first ? GM_FIRST : 0));
+        }
+        const uint32_t heads = __ballot_sync(0xffffffffu, v.head);
+        const uint32_t mheads = __ballot_sync(0xffffffffu, v.head && multi);
+        if (lane == 0 && heads) {
+            atomicAdd(&s_cnt[0], (uint32_t)__popc(heads));
+            atomicAdd(&s_cnt[1], (uint32_t)__popc(heads & ~mheads));
+            atomicAdd(&s_cnt[2], (uint32_t)__popc(mheads));
+        }
     }
     __syncthreads();
     if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
+    if (SMEM_HIST) for (uint32_t k = threadIdx.x; k < (uint32_t)p.n_features; k += blockDim.x) { const uint32_t c = s_hist[k]; if (c) atomicAdd(p.ui + k, c); }
 }
 
-// proportional: heads with pcount>0 write their list; scanv[j] = (lists before << 32) | entries before
-__global__ void __launch_bounds__(256) profile_fill_kernel(const ProfParams p, const unsigned long long *scanv,
-                                                           uint32_t *mm_off, int32_t *mm_fid, uint32_t list_base, uint32_t ent_base)
+// proportional: first-appearance lanes of in-window multi groups write their feature at
+// (list offset of the head) + (rank among the group's first appearances)
+__global__ void __launch_bounds__(256) profile_warp_fill_kernel(const ProfParams p, const uint8_t *gmeta, const unsigned long long *scanv,
+                                                                uint32_t *mm_off, int32_t *mm_fid, uint32_t list_base, uint32_t ent_base)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p.m) return;
-    if (p.pcount[j] == 0) return;
-    const unsigned long long sv = scanv[j];
-    const uint32_t li = list_base + (uint32_t)(sv >> 32), eo = ent_base + (uint32_t)sv;
-    mm_off[li] = eo;
-    uint32_t size;
-    walk_group(p, j, stream_at(p, j), &size, ActStore{mm_fid + eo}, p.big_threshold);
+    const uint64_t w0 = j & ~31ull;
+    if (w0 >= p.m) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint8_t g = j < p.m ? gmeta[j] : 0;
+    const uint32_t pc = j < p.m ? p.pcount[j] : 0u;
+    const bool head = (g & GM_HEAD) != 0, first = (g & GM_FIRST) != 0, member = (g & GM_MEMBER) != 0;
+    const uint32_t hmask = __ballot_sync(0xffffffffu, head);
+    const uint32_t fmask = __ballot_sync(0xffffffffu, first);
+    const uint32_t le = hmask & (0xffffffffu >> (31u - lane));
+    const uint32_t gs = le ? 31u - (uint32_t)__clz((int)le) : 0u;
+    const uint32_t gt = lane == 31 ? 0u : (hmask & (0xffffffffu << (lane + 1)));
+    const uint32_t e = gt ? (uint32_t)__ffs((int)gt) - 1u : 32u;
+    const uint32_t span = (e == 32 ? 0xffffffffu : ((1u << e) - 1u)) & (0xffffffffu << gs);
+    unsigned long long sv = (head && pc) ? scanv[j] : 0ull;
+    const uint32_t hpc = __shfl_sync(0xffffffffu, pc, (int)gs);
+    sv = __shfl_sync(0xffffffffu, sv, (int)gs);
+    if (member && le && hpc) {
+        const uint32_t li = list_base + (uint32_t)(sv >> 32), eo = ent_base + (uint32_t)sv;
+        if (head) mm_off[li] = eo;
+        if (first) {
+            const uint32_t rank = __popc(fmask & span & ((1u << lane) - 1u));
+            mm_fid[eo + rank] = feature_of(p, p.tid[stream_at(p, j)]);
+        }
+    }
 }
 
 // Oversized groups (> big_threshold records): one thread, the reference's own
