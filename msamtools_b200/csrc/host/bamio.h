@@ -1,0 +1,59 @@
+/*
+ * bamio.h -- from-scratch SAM / BAM / BGZF reader and writer over zlib (C99).
+ *
+ * htslib is not available in this build (the reference downloads it at build time,
+ * deps/htslib/defs.txt:2), so the host side carries its own I/O.  Records always travel
+ * as raw BAM records (int32 block_size + body, SAM spec 4.2): that is what the GPU path
+ * takes (include/msamtools_b200.h) and what BAM output needs; SAM text is parsed into /
+ * printed from that form following htslib's conventions (smallest integer aux type,
+ * reg2bin, "*" sequences).
+ */
+#ifndef MSG_BAMIO_H
+#define MSG_BAMIO_H
+#include <stddef.h>
+#include <stdint.h>
+
+typedef struct bio_hdr {
+    char     *text;          /* SAM header text, NUL terminated */
+    size_t    l_text;
+    int32_t   n_targets;
+    char    **target_name;
+    uint32_t *target_len;
+} bio_hdr;
+
+typedef struct bio_file bio_file;
+
+/* ---- reading: "-" is stdin; BGZF/gzip and BAM/SAM are auto-detected (as htslib does) */
+bio_file *bio_open_read(const char *path);
+bio_hdr  *bio_read_header(bio_file *f);                       /* NULL on error */
+/* next record as a raw BAM record appended at (*buf)+(*len); grows *buf. 1 = record, 0 = EOF, <0 = error */
+int       bio_read_record(bio_file *f, const bio_hdr *h, uint8_t **buf, size_t *cap, size_t *len);
+const char *bio_error(const bio_file *f);
+
+/* ---- writing: mode "w" SAM, "wh" SAM+header, "wb" BAM, "wbu" BAM in level-0 BGZF (msam_filter.c:464-470) */
+bio_file *bio_open_write(const char *path, const char *mode);
+int       bio_write_header(bio_file *f, const bio_hdr *h);
+int       bio_write_record(bio_file *f, const bio_hdr *h, const uint8_t *rec, size_t len);
+int       bio_close(bio_file *f);
+int       bio_is_bam(const bio_file *f);
+
+/* ---- header helpers */
+bio_hdr *bio_hdr_parse_text(const char *text, size_t l_text); /* builds targets from @SQ lines */
+bio_hdr *bio_hdr_dup(const bio_hdr *h);
+void     bio_hdr_free(bio_hdr *h);
+/* value of TAG on the @HD line (malloc'ed) or NULL */
+char    *bio_hdr_find_hd_tag(const bio_hdr *h, const char *tag);
+/* append "@PG ID:<unique id> PN:.. [PP:<last in chain>] VN:.. CL:.. DS:.." (htslib sam_hdr_add_pg semantics) */
+int      bio_hdr_add_pg(bio_hdr *h, const char *name, const char *pn, const char *vn, const char *cl, const char *ds);
+int      bio_hdr_tid(const bio_hdr *h, const char *name);
+
+/* ---- record <-> SAM text */
+/* parse one SAM line (no trailing newline needed) into a raw BAM record appended at (*buf)+(*len) */
+int      bio_sam_parse(const char *line, size_t l, const bio_hdr *h, uint8_t **buf, size_t *cap, size_t *len, char *err, size_t lerr);
+/* format a raw BAM record as a SAM line (with trailing '\n') appended to a growable string */
+int      bio_sam_format(const uint8_t *rec, size_t len, const bio_hdr *h, char **out, size_t *cap, size_t *olen);
+
+/* join argv with spaces, quoting nothing -- htslib's stringify_argv (tabs become spaces) */
+char    *bio_stringify_argv(int argc, char *argv[]);
+
+#endif

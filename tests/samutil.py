@@ -173,3 +173,37 @@ def split_records(raw):
         out.append(raw[p:p + 4 + bs])
         p += 4 + bs
     return out
+
+
+def write_bam(path, header_text, ref_names, target_len, raw, level=1):
+    """Write a BGZF-compressed BAM file (concatenated gzip members with the BC extra field)."""
+    import zlib
+    text = header_text.encode()
+    parts = [b"BAM\1", struct.pack("<i", len(text)), text, struct.pack("<i", len(ref_names))]
+    for n, l in zip(ref_names, target_len):
+        nb = n.encode() + b"\0"
+        parts += [struct.pack("<i", len(nb)), nb, struct.pack("<i", int(l))]
+    data = b"".join(parts) + bytes(raw)
+    with open(path, "wb") as fh:
+        for o in range(0, len(data), 0xff00):
+            blk = data[o:o + 0xff00]
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            comp = co.compress(blk) + co.flush()
+            fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25))
+            fh.write(comp + struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))
+        fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def synth_header(ref_names, target_len, so="queryname"):
+    lines = ["@HD\tVN:1.6\tSO:%s" % so] if so else []
+    lines += ["@SQ\tSN:%s\tLN:%d" % (n, int(l)) for n, l in zip(ref_names, target_len)]
+    return "\n".join(lines) + "\n"
+
+
+def read_profile_gz(path):
+    """msamtools profile output -> (header comment lines, {feature: value string})"""
+    with gzip.open(path, "rt") as fh:
+        lines = fh.read().splitlines()
+    comments = [l for l in lines if l.startswith("#")]
+    body = [l.split("\t") for l in lines if not l.startswith("#")]
+    return comments, body
