@@ -7,7 +7,10 @@ CSRC    := msamtools_b200/csrc
 LIB     := msamtools_b200/libmsamtools_b200.so
 SYNTH   := msamtools_b200/libmsamsynth.so
 
-all: $(LIB) $(SYNTH) oracle
+CLI     := msamtools_b200/bin/msamtools
+HOSTSRC := $(CSRC)/host/bamio.c $(CSRC)/host/margs.c $(CSRC)/host/keyorder.c
+
+all: $(LIB) $(SYNTH) $(CLI) oracle
 
 $(LIB): $(CSRC)/api.cu $(wildcard $(CSRC)/*.cuh) include/msamtools_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/api.cu -ldl
@@ -15,10 +18,15 @@ $(LIB): $(CSRC)/api.cu $(wildcard $(CSRC)/*.cuh) include/msamtools_b200.h
 $(SYNTH): $(CSRC)/synth.c
 	$(CC) -O2 -g -std=gnu99 -Wall -Wextra -fPIC -shared -o $@ $< -lm
 
+# drop-in CLI: plain C host (own BAM/SAM/BGZF I/O over zlib) linked against the CUDA library
+$(CLI): $(CSRC)/cli/msamtools_main.c $(HOSTSRC) $(wildcard $(CSRC)/host/*.h) include/msamtools_b200.h $(LIB)
+	mkdir -p msamtools_b200/bin
+	$(CC) -O2 -g -std=gnu99 -Wall -Wextra -o $@ $(CSRC)/cli/msamtools_main.c $(HOSTSRC) -Lmsamtools_b200 -lmsamtools_b200 -Wl,-rpath,'$$ORIGIN/..' -lz -lm
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(LIB) $(SYNTH); $(MAKE) -C oracle clean
+	rm -f $(LIB) $(SYNTH) $(CLI); $(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

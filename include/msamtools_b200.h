@@ -157,6 +157,10 @@ int  msg_push_device(msg_ctx *ctx, const uint8_t *d_raw, size_t nbytes,
 int  msg_device_alloc(msg_ctx *ctx, size_t nbytes, void **d_ptr);
 int  msg_device_free(msg_ctx *ctx, void *d_ptr);
 int  msg_device_upload(msg_ctx *ctx, void *d_dst, const void *h_src, size_t nbytes);
+/* Pinned (page-locked) host staging for msg_push callers: H2D copies from it run at full PCIe rate
+ * and asynchronously.  Usable before any context exists (device = CUDA ordinal).               */
+int  msg_host_alloc(int device, size_t nbytes, void **h_ptr);
+int  msg_host_free(void *h_ptr);
 int  msg_sync(msg_ctx *ctx);
 /* Forget accumulated profile/coverage/kept state (keeps allocations).        */
 int  msg_reset(msg_ctx *ctx);

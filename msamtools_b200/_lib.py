@@ -55,7 +55,7 @@ EXPORTS = [
     "msg_push", "msg_push_device", "msg_device_alloc", "msg_device_free", "msg_device_upload", "msg_sync", "msg_reset",
     "msg_kept_count", "msg_pull_kept", "msg_pull_records", "msg_pull_stats", "msg_pull_counts",
     "msg_finish_profile", "msg_finish_coverage", "msg_pull_coverage", "msg_get_timing", "msg_nccl_unique_id",
-    "msg_mark", "msg_elapsed_ms",
+    "msg_mark", "msg_elapsed_ms", "msg_host_alloc", "msg_host_free",
 ]
 
 _lib = None
@@ -97,6 +97,8 @@ def load():
     lib.msg_get_timing.argtypes = [vp, C.POINTER(MsgTiming), C.c_int]
     lib.msg_nccl_unique_id.argtypes = [vp]
     lib.msg_mark.argtypes = [vp, C.c_int]
+    lib.msg_host_alloc.argtypes = [C.c_int, sz, C.POINTER(vp)]
+    lib.msg_host_free.argtypes = [vp]
     lib.msg_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     for name in EXPORTS:
         fn = getattr(lib, name)

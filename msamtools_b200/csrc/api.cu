@@ -644,6 +644,21 @@ int msg_device_upload(msg_ctx *c, void *d_dst, const void *h_src, size_t nbytes)
     CU(cudaStreamSynchronize(c->stream));
     return MSG_OK;
 }
+int msg_host_alloc(int device, size_t nbytes, void **h_ptr)
+{
+    msg_ctx *c = nullptr;
+    if (!h_ptr) return MSG_EINVAL;
+    CU(cudaSetDevice(device));
+    CU(cudaHostAlloc(h_ptr, nbytes ? nbytes : 1, cudaHostAllocPortable));
+    return MSG_OK;
+}
+int msg_host_free(void *h_ptr)
+{
+    msg_ctx *c = nullptr;
+    if (h_ptr) CU(cudaFreeHost(h_ptr));
+    return MSG_OK;
+}
+
 int msg_sync(msg_ctx *c)
 {
     if (!c) return MSG_EINVAL;

@@ -1,0 +1,683 @@
+/*
+ * msamtools_main.c -- drop-in `msamtools {filter,profile,coverage}` whose hot path runs on the GPU
+ * through libmsamtools_b200 (include/msamtools_b200.h).
+ *
+ * What is mirrored from the reference, by file:line --
+ *   command dispatch and usage                  msamtools.c:8-49
+ *   filter options, validation order, messages  msam_filter.c:304-458 (messages go to stdout, then "\n" on stderr, exit 1)
+ *   output modes "w"/"wh"/"wb"/"wbu"            msam_filter.c:464-470, msam_helper.c:238-241
+ *   QNAME grouping pre-flight + status strings  msam_helper.c:88-137,295-484
+ *   @PG / '#' provenance                        msam_helper.c:139-184
+ *   profile options, prefix matching, --genome, --mincount, Unknown, units, header statistics, "%.8g" table
+ *                                               msam_profile.c:434-499,503-1015; mMatrix.c:168-179,359-376
+ *   coverage options and both writers           msam_coverage.c:143-219,223-390
+ *   error convention "Fatal Error: ...", exit 1 mCommon.c:3-31
+ * The help glossaries are written for this build; option names and semantics are the reference's.
+ * `summary` is outside the accelerated path and is not provided.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include "../../../include/msamtools_b200.h"
+#include "../host/bamio.h"
+#include "../host/keyorder.h"
+#include "../host/margs.h"
+
+#define PROGRAM "msamtools"
+#define PACKAGE_VERSION "1.1.3-b200"
+#define MSAM_GIT_COMMIT "b200-native"
+
+#define QNAME_GROUP_CHECK_RECORDS 10000
+#define COORD_ORDER_CHECK_RECORDS 100000
+#define COORD_ORDER_MIN_RECORDS   10000
+
+static void mQuit(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
+    fprintf(stderr, "\n");
+    exit(EXIT_FAILURE);
+}
+static void mDie(const char *fmt, ...)
+{
+    va_list ap;
+    fflush(stdout);
+    fprintf(stderr, "Fatal Error: ");
+    va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
+    fprintf(stderr, "\n");
+    exit(EXIT_FAILURE);
+}
+
+static void print_help(const char *sub, void **argtable)
+{   /* mPrintHelp, msam_helper.c:49-57 */
+    fprintf(stdout, "Usage:\n------\n\n%s %s", PROGRAM, sub);
+    arg_print_syntax(stdout, argtable, "\n");
+    fprintf(stdout, "\nGeneral options:\n----------------\n\nThese options specify the input/output formats of BAM/SAM files \n(same meaning as in 'samtools view'):\n");
+    arg_print_glossary(stdout, argtable, "  %-25s %s\n");
+}
+
+static void multiple_file_error(const char *sub, void **argtable)
+{
+    fprintf(stderr, "Multiple input files not supported in %s.\n", sub);
+    fprintf(stderr, "Use 'samtools merge' to combine BAM/SAM files.\n");
+    print_help(sub, argtable);
+    mQuit("");
+}
+
+static char *command_line(int argc, char *argv[])
+{   /* mBuildCommandLine: PROGRAM + the sub-command's argv */
+    char **full = malloc(sizeof(char *) * (size_t)(argc + 1));
+    full[0] = (char *)PROGRAM;
+    for (int i = 0; i < argc; i++) full[i + 1] = argv[i];
+    char *s = bio_stringify_argv(argc + 1, full);
+    free(full);
+    if (!s) mDie("Cannot construct command line for provenance");
+    return s;
+}
+
+/* ============================================================ record chunks */
+typedef struct {
+    uint8_t *raw; size_t len, cap;
+    uint64_t *off; size_t n, offcap;
+} chunk_t;
+
+static void chunk_reserve_off(chunk_t *c, size_t n)
+{
+    if (n + 2 > c->offcap) { c->offcap = c->offcap ? c->offcap * 2 : 1 << 16; while (n + 2 > c->offcap) c->offcap *= 2; c->off = realloc(c->off, c->offcap * sizeof(uint64_t)); if (!c->off) mDie("Out of memory"); }
+}
+
+/* append records until the chunk holds `want_records` / `want_bytes` or the input ends; 1 = more input may follow */
+static int chunk_fill(chunk_t *c, bio_file *in, const bio_hdr *h, size_t want_records, size_t want_bytes, int *eof)
+{
+    while (c->n < want_records && c->len < want_bytes) {
+        chunk_reserve_off(c, c->n + 1);
+        c->off[c->n] = c->len;
+        int rc = bio_read_record(in, h, &c->raw, &c->cap, &c->len);
+        if (rc <= 0) { *eof = 1; break; }              /* EOF or unreadable record ends the stream (msam_filter.c:119) */
+        c->n++;
+    }
+    chunk_reserve_off(c, c->n);
+    c->off[c->n] = c->len;
+    return !*eof;
+}
+
+static void chunk_drop_front(chunk_t *c, size_t k)
+{
+    size_t base = (size_t)c->off[k];
+    memmove(c->raw, c->raw + base, c->len - base);
+    for (size_t i = k; i <= c->n; i++) c->off[i - k] = c->off[i] - base;
+    c->n -= k; c->len -= base;
+}
+
+static int names_differ(const chunk_t *c, size_t a, size_t b)
+{
+    const uint8_t *x = c->raw + c->off[a], *y = c->raw + c->off[b];
+    return x[12] != y[12] || memcmp(x + 36, y + 36, x[12]) != 0;
+}
+
+/* ============================================================ QNAME grouping pre-flight (msam_helper.c:295-484) */
+typedef enum { QN_NOT_REQUIRED = 0, QN_HEADER_CONFIRMED, QN_SAMPLE_OK, QN_SAMPLE_WARNING } qn_status;
+typedef struct { qn_status status; size_t qname_records_checked, input_records_checked, mapped_records_checked; } qn_result;
+
+static void qn_format(const qn_result *r, char *buf, size_t n)
+{   /* mFormatQNameCheck, msam_helper.c:88-137 */
+    switch (r->status) {
+    case QN_NOT_REQUIRED: snprintf(buf, n, "QNAME grouping check: not required for this operation"); break;
+    case QN_HEADER_CONFIRMED: snprintf(buf, n, "QNAME grouping check: confirmed by input header SO:queryname"); break;
+    case QN_SAMPLE_OK:
+        if (r->input_records_checked < QNAME_GROUP_CHECK_RECORDS)
+            snprintf(buf, n, "QNAME grouping check: no QNAME grouping violation detected in all %zu records", r->qname_records_checked);
+        else
+            snprintf(buf, n, "QNAME grouping check: no QNAME grouping violation detected in first %zu records", r->qname_records_checked);
+        break;
+    default:
+        snprintf(buf, n, "QNAME grouping check: WARNING - no QNAME grouping violation detected in first %zu records; %zu mapped records among the "
+                 "first %zu input records were consistent with coordinate ordering", r->qname_records_checked, r->mapped_records_checked, r->input_records_checked);
+    }
+}
+
+typedef struct { char **key; size_t *last; size_t cap, n; } nameset;
+static uint64_t fnv1a(const char *s) { uint64_t h = 1469598103934665603ull; for (; *s; s++) { h ^= (uint8_t)*s; h *= 1099511628211ull; } return h; }
+static size_t *nameset_slot(nameset *s, const char *k, int insert)
+{
+    if (s->cap == 0) { s->cap = 1 << 15; s->key = calloc(s->cap, sizeof(char *)); s->last = calloc(s->cap, sizeof(size_t)); }
+    size_t i = fnv1a(k) & (s->cap - 1);
+    while (s->key[i]) { if (!strcmp(s->key[i], k)) return &s->last[i]; i = (i + 1) & (s->cap - 1); }
+    if (!insert) return NULL;
+    s->key[i] = strdup(k); s->n++;
+    return &s->last[i];
+}
+
+/* works on the first chunk, which the caller fills with >= COORD_ORDER_CHECK_RECORDS records (or the whole input) */
+static qn_result qname_preflight(const bio_hdr *h, const chunk_t *c)
+{
+    qn_result r = { QN_SAMPLE_OK, 0, 0, 0 };
+    char *so = bio_hdr_find_hd_tag(h, "SO");
+    if (so) {
+        if (!strcmp(so, "queryname")) { free(so); r.status = QN_HEADER_CONFIRMED; return r; }
+        if (!strcmp(so, "coordinate")) {
+            free(so);
+            mDie("Input SAM/BAM declares 'SO:coordinate', but this operation requires records to be grouped by QNAME.\n"
+                 "             Please name-sort the input, for example with 'samtools sort -n input.bam -o input.name_sorted.bam'.");
+        }
+        free(so);
+    }
+    nameset closed = { 0 };
+    const char *cur = NULL; size_t cur_first = 0;
+    int coord_ordered = 1, coord_relevant = 0, have_prev = 0; int32_t ptid = -1, ppos = -1;
+    size_t lim = c->n < COORD_ORDER_CHECK_RECORDS ? c->n : COORD_ORDER_CHECK_RECORDS;
+    for (size_t i = 0; i < lim; i++) {
+        const uint8_t *rec = c->raw + c->off[i];
+        const char *qname = (const char *)rec + 36;
+        size_t recno = i + 1;
+        r.input_records_checked++;
+        if (recno <= QNAME_GROUP_CHECK_RECORDS) {
+            r.qname_records_checked++;
+            if (!cur) { cur = qname; cur_first = recno; }
+            else if (strcmp(qname, cur) != 0) {
+                *nameset_slot(&closed, cur, 1) = recno - 1;
+                size_t *re = nameset_slot(&closed, qname, 0);
+                if (re)
+                    mDie("SAM/BAM file is not grouped by QNAME. Read '%s' reappears at record %zu after its previous group ended at record %zu "
+                         "(%zu intervening records). Please name-sort the input, for example with 'samtools sort -n input.bam -o input.name_sorted.bam'.",
+                         qname, recno, *re, recno - *re - 1);
+                cur = qname; cur_first = recno;
+            }
+        }
+        uint32_t flag = (uint32_t)rec[18] | (uint32_t)rec[19] << 8;
+        int32_t tid = (int32_t)((uint32_t)rec[4] | (uint32_t)rec[5] << 8 | (uint32_t)rec[6] << 16 | (uint32_t)rec[7] << 24);
+        int32_t pos = (int32_t)((uint32_t)rec[8] | (uint32_t)rec[9] << 8 | (uint32_t)rec[10] << 16 | (uint32_t)rec[11] << 24);
+        if (!(flag & 4) && tid >= 0) {
+            r.mapped_records_checked++;
+            if (have_prev && (tid < ptid || (tid == ptid && pos < ppos))) coord_ordered = 0;
+            ptid = tid; ppos = pos; have_prev = 1;
+        }
+        if (flag & (1 | 256 | 2048)) coord_relevant = 1;
+    }
+    (void)cur_first;
+    for (size_t i = 0; i < closed.cap; i++) free(closed.key[i]);
+    free(closed.key); free(closed.last);
+    if (coord_ordered && coord_relevant && r.mapped_records_checked >= COORD_ORDER_MIN_RECORDS) {
+        char w[1024];
+        r.status = QN_SAMPLE_WARNING;
+        qn_format(&r, w, sizeof w);
+        fprintf(stderr, "WARNING: %s\n", w);
+    }
+    return r;
+}
+
+/* ============================================================ the GPU streaming loop shared by the three commands */
+typedef struct {
+    msg_config cfg;
+    bio_file *in; bio_hdr *hdr;
+    chunk_t chunk; int eof;
+    bio_file *out; bio_hdr *out_hdr;      /* filter only */
+} run_t;
+
+#define CHUNK_RECORDS ((size_t)4 << 20)
+#define CHUNK_BYTES   ((size_t)1536 << 20)
+
+static void gpu_die(msg_ctx *ctx) { mDie("%s", msg_last_error(ctx)); }
+
+static msg_ctx *run_stream(run_t *r)
+{
+    msg_ctx *ctx = NULL;
+    r->cfg.abi_version = MSG_ABI_VERSION;
+    r->cfg.n_ranks = 1;
+    if (getenv("MSAMTOOLS_DEVICE")) r->cfg.device = atoi(getenv("MSAMTOOLS_DEVICE"));
+    if (msg_create(&r->cfg, &ctx)) mDie("%s", msg_last_error(NULL));
+    uint8_t *outbuf = NULL; size_t outcap = 0;
+    size_t want_n = CHUNK_RECORDS, want_b = CHUNK_BYTES;
+    for (;;) {
+        if (!r->eof) chunk_fill(&r->chunk, r->in, r->hdr, want_n, want_b, &r->eof);
+        chunk_t *c = &r->chunk;
+        if (c->n == 0) break;
+        size_t k = c->n;
+        if (!r->eof) {
+            k = msg_split_point(c->raw, c->off, c->n, c->n - 1);
+            if (k == 0) {
+                if (c->n < 8 * CHUNK_RECORDS && c->len < 8 * CHUNK_BYTES) { want_n = c->n * 2; want_b = c->len * 2; continue; }
+                /* no mapped record closes a group for a very long stretch: cut at any QNAME change */
+                for (k = c->n - 1; k > 0 && !names_differ(c, k - 1, k); k--) ;
+                if (k == 0) { want_n = c->n * 2; want_b = c->len * 2; continue; }
+            }
+        }
+        if (msg_push(ctx, c->raw, (size_t)c->off[k], c->off, k)) gpu_die(ctx);
+        if (r->cfg.want_records) {
+            size_t nb = 0, nr = 0;
+            if (msg_pull_records(ctx, NULL, 0, &nb, &nr)) gpu_die(ctx);
+            if (nb > outcap) { outcap = nb + nb / 4; outbuf = realloc(outbuf, outcap); if (!outbuf) mDie("Out of memory"); }
+            if (msg_pull_records(ctx, outbuf, outcap, &nb, &nr)) gpu_die(ctx);
+            for (size_t o = 0; o < nb;) {
+                uint32_t bs = (uint32_t)outbuf[o] | (uint32_t)outbuf[o + 1] << 8 | (uint32_t)outbuf[o + 2] << 16 | (uint32_t)outbuf[o + 3] << 24;
+                if (bio_write_record(r->out, r->out_hdr, outbuf + o, 4 + (size_t)bs)) mDie("Cannot write alignment record");
+                o += 4 + (size_t)bs;
+            }
+        }
+        if (k == c->n) { c->n = 0; c->len = 0; } else chunk_drop_front(c, k);
+        want_n = CHUNK_RECORDS; want_b = CHUNK_BYTES;
+        if (r->eof && c->n == 0) break;
+    }
+    free(outbuf);
+    return ctx;
+}
+
+static void open_input(run_t *r, const char *infile)
+{
+    r->in = bio_open_read(infile);
+    if (!r->in) mDie("Cannot open %s for reading", infile);
+    r->hdr = bio_read_header(r->in);
+    if (!r->hdr) mDie("Cannot read header from %s", infile);
+}
+
+/* ============================================================ filter */
+static int filter_main(int argc, char *argv[])
+{
+    const char *sub = "filter";
+    struct arg_lit *a_b = arg_lit0("b", NULL, "output BAM (default: false)");
+    struct arg_lit *a_u = arg_lit0("u", NULL, "uncompressed BAM output (force -b) (default: false)");
+    struct arg_lit *a_h = arg_lit0("h", NULL, "print header for the SAM output (default: false)");
+    struct arg_lit *a_S = arg_lit0("S", NULL, "input is SAM (default: false)");
+    struct arg_file *a_file = arg_filen(NULL, NULL, "<bamfile>", 1, 1, "input SAM/BAM file");
+    struct arg_lit *a_help = arg_lit0(NULL, "help", "print this help and exit\n\nSpecific options:\n-----------------\n");
+    struct arg_int *a_l = arg_int0("l", NULL, NULL, "min. length of alignment (default: 0)");
+    struct arg_int *a_p = arg_int0("p", NULL, NULL, "min. sequence identity of alignment, in percent, integer in [0,100]; needs MD or NM (default: 0)");
+    struct arg_int *a_ppt = arg_int0(NULL, "ppt", NULL, "min (positive) or max (negative) sequence identity in parts per thousand, integer in [-1000,1000]; needs MD or NM (default: 0)");
+    struct arg_int *a_z = arg_int0("z", NULL, NULL, "min. percent of the query that must be aligned, integer in [0,100] (default: 0)");
+    struct arg_lit *a_k = arg_lit0("k", "keep_unmapped", "report unmapped reads, when filtering using upper-limit thresholds (default: false)");
+    struct arg_lit *a_v = arg_lit0("v", "invert", "invert the effect of the filter: report the complement among mapped alignments (default: false)");
+    struct arg_lit *a_rescore = arg_lit0(NULL, "rescore", "rescore alignments using MD or NM fields, in that order (default: false)\n\n"
+                                         "Special filters (need name-grouped input and AS, unless --rescore; cannot be combined with -v):\n");
+    struct arg_lit *a_best = arg_lit0(NULL, "besthit", "keep all highest scoring hit(s) per read (default: false)");
+    struct arg_lit *a_uniq = arg_lit0(NULL, "uniqhit", "keep only one highest scoring hit per read, only if it is unique (default: false)");
+    struct arg_end *end = arg_end(16);
+    void *argtable[] = { a_b, a_u, a_h, a_S, a_file, a_help, a_l, a_p, a_ppt, a_z, a_k, a_v, a_rescore, a_best, a_uniq, end };
+
+    if (arg_nullcheck(argtable) != 0) mDie("insufficient memory");
+    int nerrors = arg_parse(argc, argv, argtable);
+    if (a_help->count > 0 || argc < 2) { print_help(sub, argtable); exit(EXIT_SUCCESS); }
+    if (nerrors > 0) {
+        arg_print_errors(stderr, end, PROGRAM);
+        fprintf(stderr, "Use --help for usage instructions!\n");
+        mQuit("");
+    }
+    if (a_file->count > 1) multiple_file_error(sub, argtable);
+
+    int32_t PPT = 0, MAX_CLIP = 100, MIN_LENGTH = 0;
+#define USAGE_FAIL(msg) do { fprintf(stdout, msg "\n"); print_help(sub, argtable); mQuit(""); } while (0)
+    if (a_v->count > 0 && (a_best->count > 0 || a_uniq->count > 0)) USAGE_FAIL("--invert cannot be combined with --besthit or --uniqhit");
+    else if (a_best->count > 0 && a_uniq->count > 0) USAGE_FAIL("--besthit cannot be combined with --uniqhit");
+    else if (a_p->count > 0 && a_ppt->count > 0) USAGE_FAIL("-p cannot be combined with --ppt");
+    else if (!a_l->count && !a_p->count && !a_ppt->count && !a_uniq->count && !a_best->count && !a_z->count)
+        USAGE_FAIL("--mode filter needs -l, -p, --ppt, -z, --besthit or --uniqhit");
+    else {
+        if (a_p->count > 0) {
+            int pid = a_p->ival[0];
+            if (pid < 0 || pid > 100) USAGE_FAIL("-p must be in the range [0,100]");
+            PPT = 10 * pid;
+        } else if (a_ppt->count > 0) {
+            PPT = a_ppt->ival[0];
+            if (PPT < -1000 || PPT > 1000) USAGE_FAIL("--ppt must be in the range [-1000,1000]");
+        }
+        if (a_z->count > 0) {
+            MAX_CLIP = 100 - a_z->ival[0];
+            if (MAX_CLIP < 0 || MAX_CLIP > 100) USAGE_FAIL("-z must be in the range [0,100]");
+        }
+        if (a_l->count > 0) {
+            MIN_LENGTH = a_l->ival[0];
+            if (MIN_LENGTH < 0) USAGE_FAIL("-l must be a non-negative integer");
+        }
+    }
+    char outmode[6] = "w";
+    if (a_u->count > 0) strcat(outmode, "bu"); else if (a_b->count > 0) strcat(outmode, "b"); else if (a_h->count > 0) strcat(outmode, "h");
+
+    run_t r; memset(&r, 0, sizeof r);
+    open_input(&r, a_file->filename[0]);
+    const int hit = a_uniq->count > 0 ? MSG_HIT_UNIQUE : a_best->count > 0 ? MSG_HIT_BEST : MSG_HIT_NONE;
+    qn_result qn = { QN_NOT_REQUIRED, 0, 0, 0 };
+    if (hit) {
+        chunk_fill(&r.chunk, r.in, r.hdr, COORD_ORDER_CHECK_RECORDS, (size_t)-1, &r.eof);
+        qn = qname_preflight(r.hdr, &r.chunk);
+    }
+    /* provenance goes into a copy of the header (msam_filter.c:484-493) */
+    r.out_hdr = bio_hdr_dup(r.hdr);
+    if (!r.out_hdr) mDie("Cannot duplicate SAM header for output provenance");
+    {
+        char *cl = command_line(argc, argv), qmsg[1024], ds[1252];
+        qn_format(&qn, qmsg, sizeof qmsg);
+        snprintf(ds, sizeof ds, "git=%s; %s", MSAM_GIT_COMMIT, qmsg);
+        if (bio_hdr_add_pg(r.out_hdr, PROGRAM, PROGRAM, PACKAGE_VERSION, cl, ds) < 0) mDie("Cannot add msamtools @PG record to SAM/BAM header");
+        free(cl);
+    }
+    r.out = bio_open_write("-", outmode);
+    if (!r.out) mDie("Cannot open - for writing");
+    if (bio_write_header(r.out, r.out_hdr) < 0) mDie("Cannot write SAM header");
+
+    /* mFilterFileWrapper, msam_filter.c:79-84 */
+    if (!(MIN_LENGTH > 0) && PPT == 0 && !(MAX_CLIP < 100) && !hit)
+        mDie("'filter' command requires atleast one of --ppt, -l, -p, -z, --besthit or --uniqhit");
+
+    r.cfg.do_filter = 1; r.cfg.hit_mode = (uint8_t)hit; r.cfg.invert = a_v->count > 0; r.cfg.keep_unmapped = a_k->count > 0;
+    r.cfg.rescore = a_rescore->count > 0;
+    r.cfg.min_length = MIN_LENGTH; r.cfg.ppt = PPT; r.cfg.max_clip = MAX_CLIP;
+    r.cfg.want_records = 1;
+    r.cfg.n_targets = r.hdr->n_targets; r.cfg.n_features = r.hdr->n_targets;
+    msg_ctx *ctx = run_stream(&r);
+    msg_destroy(ctx);
+    bio_close(r.in);
+    if (bio_close(r.out)) mDie("Cannot write output");
+    return 0;
+}
+
+/* ============================================================ profile */
+static void print_insert_stats(gzFile s, int left, const char *type, int number, int total, const char *post)
+{   /* mPrintInsertStats, msam_profile.c:434-470 */
+    int width = 7;
+    if (total > 0) width = 1 + log10(total);
+    gzprintf(s, "# ");
+    if (left) gzprintf(s, "%-20s: ", type); else gzprintf(s, "%20s: ", type);
+    if (strcmp(type, "Total inserts") == 0 && number == -1) gzprintf(s, "%*s (", width, "NA"); else gzprintf(s, "%*d (", width, number);
+    if (total > 0) gzprintf(s, "%6.2f", 100.0 * number / total); else gzprintf(s, "%6s", "NA");
+    gzprintf(s, "%%)");
+    if (post) gzprintf(s, " %s\n", post); else gzprintf(s, "\n");
+}
+static void print_insert_stats_double(gzFile s, const char *type, double number, int total, const char *post)
+{   /* mPrintInsertStatsDouble, msam_profile.c:472-499 (always left aligned by its callers) */
+    gzprintf(s, "# ");
+    gzprintf(s, "%-20s: ", type);
+    gzprintf(s, "%10.7g (", number);
+    if (total > 0) gzprintf(s, "%6.2f", 100.0 * number / total); else gzprintf(s, "%6s", "NA");
+    gzprintf(s, "%%)");
+    if (post) gzprintf(s, " %s\n", post); else gzprintf(s, "\n");
+}
+
+static int profile_main(int argc, char *argv[])
+{
+    const char *sub = "profile";
+    struct arg_lit *a_S = arg_lit0("S", NULL, "input is SAM (default: false)");
+    struct arg_file *a_file = arg_filen(NULL, NULL, "<bamfile>", 1, 1, "input SAM/BAM file");
+    struct arg_lit *a_help = arg_lit0(NULL, "help", "print this help and exit\n\nSpecific options:\n-----------------\n");
+    struct arg_str *a_out = arg_str1("o", NULL, "<file>", "name of output file (required)");
+    struct arg_str *a_label = arg_str1(NULL, "label", NULL, "label to use for the profile; typically the sample id (required)");
+    struct arg_str *a_genome = arg_str0(NULL, "genome", NULL, "tab-delimited genome definition file - 'genome-id<tab>seq-id' (default: none)");
+    struct arg_int *a_mincount = arg_int0(NULL, "mincount", NULL, "minimum number of inserts mapped to a feature, below which the feature is counted as absent (default: 0)");
+    struct arg_int *a_total = arg_int0(NULL, "total", NULL, "number of high-quality inserts (mate-pairs/paired-ends) that were input to the aligner (default: unknown)");
+    struct arg_str *a_unit = arg_str0(NULL, "unit", NULL, "unit of abundance to report {ab | rel | fpkm | tpm} (default: rel)");
+    struct arg_lit *a_pandas = arg_lit0(NULL, "pandas", "print two columns (ID, sample-label) as header compatible with python pandas (default)");
+    struct arg_lit *a_nopandas = arg_lit0(NULL, "no-pandas", "use legacy profile header without the ID column");
+    struct arg_lit *a_nolen = arg_lit0(NULL, "nolen", "do not normalize the abundance (only relevant for ab or rel) for sequence length (default: normalize)");
+    struct arg_str *a_multi = arg_str0(NULL, "multi", NULL, "how to deal with multi-mappers {all | equal | proportional | ignore} (default: proportional)\n\n"
+                                       "Inserts (all alignments of one QNAME) are counted per reference sequence, or per genome with --genome.\n"
+                                       "An insert hitting N features adds 1 to each (all), 1/N to each (equal), a share proportional to the\n"
+                                       "features' current abundances (proportional), or nothing (ignore). Input must be grouped by QNAME and\n"
+                                       "already filtered (see 'filter').");
+    struct arg_end *end = arg_end(20);
+    void *argtable[] = { a_S, a_file, a_help, a_out, a_label, a_genome, a_total, a_mincount, a_unit, a_pandas, a_nopandas, a_nolen, a_multi, end };
+
+    if (arg_nullcheck(argtable) != 0) mDie("insufficient memory");
+    int nerrors = arg_parse(argc, argv, argtable);
+    if (a_help->count > 0 || argc < 2) { print_help(sub, argtable); exit(EXIT_SUCCESS); }
+    if (nerrors > 0) {
+        arg_print_errors(stdout, end, PROGRAM);
+        fprintf(stdout, "Use --help for usage instructions!\n");
+        mQuit("");
+    }
+    if (a_file->count > 1) multiple_file_error(sub, argtable);
+    if (a_label->count != 1 || a_out->count != 1) USAGE_FAIL("requires --label and -o");
+    if (a_pandas->count > 0 && a_nopandas->count > 0) USAGE_FAIL("--pandas and --no-pandas cannot be used together");
+    int total_inserts = -1;
+    if (a_total->count > 0) { total_inserts = a_total->ival[0]; if (total_inserts <= 0) USAGE_FAIL("--total must be a positive integer"); }
+    if (a_mincount->count > 0 && a_mincount->ival[0] < 0) USAGE_FAIL("--mincount must be a non-negative integer");
+
+    run_t r; memset(&r, 0, sizeof r);
+    open_input(&r, a_file->filename[0]);
+    chunk_fill(&r.chunk, r.in, r.hdr, COORD_ORDER_CHECK_RECORDS, (size_t)-1, &r.eof);
+    qn_result qn = qname_preflight(r.hdr, &r.chunk);
+
+    /* any prefix matches, first hit in this order (msam_profile.c:712-748) */
+    int share_type = MSG_MULTI_PROPORTIONAL, unit_type = 1;
+    if (a_multi->count > 0) {
+        const char *types[5] = { "", "all", "equal", "proportional", "ignore" };
+        share_type = -1;
+        for (int i = 1; i <= 4; i++) if (strncmp(a_multi->sval[0], types[i], strlen(a_multi->sval[0])) == 0) { share_type = i; break; }
+        if (share_type == -1) mDie("Do not understand --multi=%s", a_multi->sval[0]);
+    }
+    if (a_unit->count > 0) {
+        const char *types[5] = { "", "relative", "fpkm", "tpm", "abundance" };
+        unit_type = -1;
+        for (int i = 1; i <= 4; i++) if (strncmp(a_unit->sval[0], types[i], strlen(a_unit->sval[0])) == 0) { unit_type = i; break; }
+        if (unit_type == -1) mDie("Do not understand --unit=%s", a_unit->sval[0]);
+    }
+    int length_normalize = 1;
+    if (unit_type == 1 || unit_type == 4) length_normalize = (a_nolen->count == 0);
+
+    /* feature map: identity, or --genome in the reference's key order (msam_profile.c:757-852) */
+    const int n_targets = r.hdr->n_targets;
+    int32_t *fmap = malloc(sizeof(int32_t) * (size_t)(n_targets ? n_targets : 1));
+    for (int i = 0; i < n_targets; i++) fmap[i] = -1;
+    int n_features; char **feature_name; uint32_t *feature_len;
+    keyorder *genomes = NULL;
+    if (a_genome->count > 0) {
+        char line[4096], gname[4096], sname[4096];
+        FILE *def = fopen(a_genome->sval[0], "r");
+        if (!def) mDie("Cannot open file %s", a_genome->sval[0]);
+        genomes = ko_new();
+        while (fgets(line, sizeof line, def)) {
+            if (sscanf(line, "%s\t%s", gname, sname) != 2) mDie("GENOME DEFINITION LINE ERROR");
+            ko_add(genomes, gname);
+        }
+        rewind(def);
+        n_features = (int)ko_size(genomes);
+        while (fgets(line, sizeof line, def)) {
+            if (sscanf(line, "%s\t%s", gname, sname) != 2) mDie("GENOME DEFINITION LINE ERROR");
+            long gid = ko_find(genomes, gname);
+            int sid = bio_hdr_tid(r.hdr, sname);
+            if (gid < 0) mDie("Genome '%s' not found in BAM file", gname);
+            if (sid < 0) mDie("Sequence '%s' not found in BAM file", sname);
+            fmap[sid] = (int32_t)gid;
+        }
+        fclose(def);
+        feature_len = calloc((size_t)(n_features ? n_features : 1), sizeof(uint32_t));
+        for (int i = 0; i < n_targets; i++) {
+            if (fmap[i] == -1) mDie("Sequence '%s' not found in genome definition", r.hdr->target_name[i]);
+            feature_len[fmap[i]] += r.hdr->target_len[i];
+        }
+        feature_name = malloc(sizeof(char *) * (size_t)(n_features ? n_features : 1));
+        for (int i = 0; i < n_features; i++) feature_name[i] = (char *)ko_key(genomes, (size_t)i);
+    } else {
+        for (int i = 0; i < n_targets; i++) fmap[i] = i;
+        n_features = n_targets; feature_name = r.hdr->target_name; feature_len = r.hdr->target_len;
+    }
+
+    r.cfg.do_filter = 0; r.cfg.want_profile = 1; r.cfg.share_type = (uint8_t)share_type;
+    r.cfg.n_targets = n_targets; r.cfg.n_features = n_features; r.cfg.fmap = fmap;
+    msg_ctx *ctx = run_stream(&r);
+    double *ab = calloc((size_t)n_features + 1, sizeof(double));      /* ab[0] = Unknown, ab[1..] features */
+    msg_profile_stats st;
+    if (msg_finish_profile(ctx, ab + 1, &st)) gpu_die(ctx);
+    msg_destroy(ctx);
+    if (share_type == MSG_MULTI_PROPORTIONAL) {                        /* stderr side channel, msam_profile.c:330,381-390,405 */
+        fprintf(stderr, "# Start PropSharing:\n");
+        for (int k = 1; k <= st.em_iterations; k++) {
+            fprintf(stderr, "#     PropSharing Iteration: %2d; DELTA^2=%g", k, st.em_delta[k - 1]);
+            if (k == st.em_iterations && st.em_converged) fprintf(stderr, ". CONVERGED!\n"); else fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "# End   PropSharing!\n");
+        fprintf(stderr, "# Purged %d inserts that mapped to features without unique inserts.\n", (int)st.purged_insert_count);
+    }
+    int mapped_inserts = (int)st.mapped_inserts;
+    double purged_eq = 0;
+    if (a_mincount->count > 0) {                                       /* msam_profile.c:858-869 */
+        int mincount = a_mincount->ival[0];
+        for (int i = 1; i <= n_features; i++) if (ab[i] < mincount) { purged_eq += ab[i]; ab[i] = 0; }
+        fprintf(stderr, "# Purged %.7g insert-equivalents from low-abundance features based on --mincount.\n", purged_eq);
+    }
+    if (total_inserts > 0 && total_inserts < mapped_inserts) {
+        fprintf(stderr, "# Ignoring 'unknown' fraction, as total inserts (%d) < mapped inserts (%d)!\n", total_inserts, mapped_inserts);
+        total_inserts = -1;
+    }
+    gzFile out = strcmp(a_out->sval[0], "-") == 0 ? gzdopen(fileno(stdout), "wb") : gzopen(a_out->sval[0], "wb");
+    if (!out) mDie("Cannot open %s for writing", a_out->sval[0]);
+    {   /* mPrintProfileProvenanceGzip */
+        char *cl = command_line(argc, argv), qmsg[1024];
+        qn_format(&qn, qmsg, sizeof qmsg);
+        gzprintf(out, "# msamtools version: %s\n", PACKAGE_VERSION);
+        gzprintf(out, "# msamtools git commit: %s\n", MSAM_GIT_COMMIT);
+        gzprintf(out, "# Command line: %s\n", cl);
+        gzprintf(out, "# %s\n", qmsg);
+        free(cl);
+    }
+    double purged_inserts = st.purged_insert_count + purged_eq;
+    double effective = mapped_inserts - purged_inserts;
+    if (share_type == MSG_MULTI_IGNORE) effective -= st.multi_mapper_count;
+    print_insert_stats(out, 1, "Total inserts", total_inserts, total_inserts, NULL);
+    print_insert_stats(out, 1, "Mapped inserts", mapped_inserts, total_inserts, NULL);
+    print_insert_stats(out, 0, "- Multiple mapped ", (int)st.multi_mapper_count, total_inserts, NULL);
+    print_insert_stats(out, 0, "- Uniquely mapped ", (int)st.uniq_mapper_count, total_inserts, NULL);
+    print_insert_stats_double(out, "Purged inserts", purged_inserts, total_inserts, "due to ambiguous mapping or low abundance features");
+    print_insert_stats_double(out, "Effective inserts", effective, total_inserts, NULL);
+    if (total_inserts <= 0) gzprintf(out, "# Estimated seq. length for 'Unknown': NA\n");
+    if (total_inserts > 0) {                                           /* msam_profile.c:906-934 */
+        ab[0] = total_inserts - mapped_inserts + purged_inserts;
+        if (share_type == MSG_MULTI_IGNORE) ab[0] += st.multi_mapper_count;
+        if (length_normalize) {
+            int count = 0; uint64_t sum = 0;
+            for (int i = 0; i < n_features; i++) { sum += feature_len[i]; count++; }
+            uint32_t unknown_size = (uint32_t)(sum / (uint64_t)count);
+            gzprintf(out, "# Estimated seq. length for 'Unknown': %dbp\n", unknown_size);
+            ab[0] = 1.0 * ab[0] / unknown_size;
+        } else gzprintf(out, "# Estimated seq. length for 'Unknown': NA\n");
+    }
+    if (length_normalize) for (int i = 0; i < n_features; i++) ab[i + 1] /= feature_len[i];
+    if (unit_type == 2) {                                              /* fpkm */
+        double f = total_inserts > 0 ? 1.0E9 / total_inserts : 1.0E9 / mapped_inserts;
+        for (int i = 0; i <= n_features; i++) ab[i] *= f;
+    } else if (unit_type == 3 || unit_type == 1) {                     /* tpm / rel: row-normalise incl. Unknown (mMatrix.c:168-179) */
+        double sum = 0;
+        for (int i = 0; i <= n_features; i++) sum += ab[i];
+        for (int i = 0; i <= n_features; i++) ab[i] /= sum;
+        if (unit_type == 3) for (int i = 0; i <= n_features; i++) ab[i] *= 1.0E6;
+    }
+    if (a_nopandas->count == 0) gzprintf(out, "ID\t");                 /* mWriteMatrixTransposedGzip, mMatrix.c:359-376 */
+    gzprintf(out, "%s\n", a_label->sval[0]);
+    gzprintf(out, "%s\t%.8g\n", "Unknown", ab[0]);
+    for (int i = 0; i < n_features; i++) gzprintf(out, "%s\t%.8g\n", feature_name[i], ab[i + 1]);
+    gzclose(out);
+    bio_close(r.in);
+    return 0;
+}
+
+/* ============================================================ coverage */
+static int coverage_main(int argc, char *argv[])
+{
+    const char *sub = "coverage";
+    struct arg_lit *a_S = arg_lit0("S", NULL, "input is SAM (default: false)");
+    struct arg_file *a_file = arg_filen(NULL, NULL, "<bamfile>", 1, 1, "input SAM/BAM file");
+    struct arg_lit *a_help = arg_lit0(NULL, "help", "print this help and exit\n\nSpecific options:\n-----------------\n");
+    struct arg_str *a_out = arg_str1("o", NULL, "<file>", "name of output file (required)");
+    struct arg_lit *a_summary = arg_lit0(NULL, "summary", "do not report per-position coverage but report fraction of sequence covered (default: false)");
+    struct arg_lit *a_skip = arg_lit0("x", "skipuncovered", "do not report coverage for sequences without aligned reads (default: false)");
+    struct arg_int *a_w = arg_int0("w", "wordsize", NULL, "number of words (coverage values) per line (default: 17)");
+    struct arg_lit *a_gz = arg_lit0("z", "gzip", "compress output file using gzip (default; option retained for backward compatibility)\n\n"
+                                    "Coverage is aligned query-base depth per reference position: CIGAR M, = and X count, D and N do not.\n"
+                                    "Output is always gzip-compressed; no '.gz' is appended to the file name.");
+    struct arg_end *end = arg_end(20);
+    void *argtable[] = { a_S, a_file, a_help, a_out, a_summary, a_skip, a_w, a_gz, end };
+    int wordsize = 17;
+
+    if (arg_nullcheck(argtable) != 0) mDie("insufficient memory");
+    int nerrors = arg_parse(argc, argv, argtable);
+    if (a_help->count > 0 || argc < 2) { print_help(sub, argtable); exit(EXIT_SUCCESS); }
+    if (nerrors > 0) {
+        arg_print_errors(stderr, end, PROGRAM);
+        fprintf(stderr, "Use --help for usage instructions!\n");
+        mQuit("");
+    }
+    if (a_file->count > 1) multiple_file_error(sub, argtable);
+    if (a_w->count > 0) { wordsize = a_w->ival[0]; if (wordsize < 1) USAGE_FAIL("-w must be a non-zero positive integer"); }
+    if (a_out->count != 1) USAGE_FAIL("requires -o");
+
+    gzFile out = strcmp(a_out->sval[0], "-") == 0 ? gzdopen(fileno(stdout), "wb") : gzopen(a_out->sval[0], "wb");
+    if (!out) mDie("Cannot open %s for writing", a_out->sval[0]);
+    run_t r; memset(&r, 0, sizeof r);
+    open_input(&r, a_file->filename[0]);
+    const int T = r.hdr->n_targets;
+    r.cfg.do_filter = 0; r.cfg.want_coverage = 1; r.cfg.n_targets = T; r.cfg.n_features = T; r.cfg.target_len = r.hdr->target_len;
+    msg_ctx *ctx = run_stream(&r);
+    uint8_t *covered = calloc((size_t)(T ? T : 1), 1);
+    int64_t *touched = calloc((size_t)(T ? T : 1), sizeof(int64_t)), *sum = calloc((size_t)(T ? T : 1), sizeof(int64_t));
+    if (msg_finish_coverage(ctx, covered, touched, sum)) gpu_die(ctx);
+    const int skip = a_skip->count > 0;
+    if (a_summary->count > 0) {                                        /* mWriteCoverageSummaryToStream, msam_coverage.c:189-219 */
+        for (int t = 0; t < T; t++) {
+            int64_t tlen = r.hdr->target_len[t];
+            if (!covered[t]) { if (!skip) gzprintf(out, "%s\t%d\t%d\n", r.hdr->target_name[t], 0, 0); continue; }
+            gzprintf(out, "%s\t%.8f\t%.2f\n", r.hdr->target_name[t], 1.0 * touched[t] / tlen, 1.0 * sum[t] / tlen);
+        }
+    } else {                                                           /* mWriteCoverageToStream, msam_coverage.c:143-187 */
+        int32_t *depth = NULL; size_t dcap = 0;
+        for (int t = 0; t < T; t++) {
+            int64_t tlen = r.hdr->target_len[t];
+            if (!covered[t]) {
+                if (!skip) {
+                    gzprintf(out, ">%s\n", r.hdr->target_name[t]);
+                    for (int64_t i = 0; i < tlen - 1; i++) gzputs(out, (i + 1) % wordsize == 0 ? "0\n" : "0 ");
+                    gzputs(out, "0\n");
+                }
+                continue;
+            }
+            if ((size_t)tlen > dcap) { dcap = (size_t)tlen; depth = realloc(depth, dcap * sizeof(int32_t)); }
+            if (msg_pull_coverage(ctx, t, depth)) gpu_die(ctx);
+            gzprintf(out, ">%s\n", r.hdr->target_name[t]);
+            for (int64_t i = 0; i < tlen - 1; i++) gzprintf(out, (i + 1) % wordsize == 0 ? "%d\n" : "%d ", depth[i]);
+            gzprintf(out, "%d\n", depth[tlen - 1]);
+        }
+        free(depth);
+    }
+    gzclose(out);
+    msg_destroy(ctx);
+    bio_close(r.in);
+    return 0;
+}
+
+/* ============================================================ dispatch (msamtools.c:8-49) */
+static int usage(FILE *out)
+{
+    fprintf(out, "\n");
+    fprintf(out, "Program: %s (Metagenomics-related extension to samtools)\n", PROGRAM);
+    fprintf(out, "Version: %s (git %s; GPU hot path libmsamtools_b200 ABI %d, own BAM/SAM I/O over zlib %s)\n", PACKAGE_VERSION, MSAM_GIT_COMMIT, msg_abi_version(), zlibVersion());
+    fprintf(out, "\n");
+    fprintf(out, "Usage:   %s <command> [options]\n\n", PROGRAM);
+    fprintf(out, "Commands:\n");
+    fprintf(out, " -- Filtering\n");
+    fprintf(out, "     filter         filter alignments based on alignment statistics\n");
+    fprintf(out, "\n");
+    fprintf(out, " -- Profiling\n");
+    fprintf(out, "     profile        estimate relative abundance profile of reference sequences or genomes in bam file\n");
+    fprintf(out, "\n");
+    fprintf(out, " -- Coverage\n");
+    fprintf(out, "     coverage       estimate per-base or per-sequence read coverage of each reference sequence\n");
+    fprintf(out, "\n");
+    return 1;
+}
+
+int main(int argc, char *argv[])
+{
+    if (argc < 2) return usage(stderr);
+    if (strcmp(argv[1], "filter") == 0) return filter_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "profile") == 0) return profile_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "coverage") == 0) return coverage_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "help") == 0) { usage(stdout); return 0; }
+    else if (strcmp(argv[1], "summary") == 0) {
+        fprintf(stderr, "[msamtools] 'summary' is not part of the GPU-accelerated path; use the CPU msamtools for it\n");
+        return 1;
+    } else {
+        fprintf(stderr, "[msamtools] unrecognized command '%s'\n", argv[1]);
+        usage(stderr);
+        return 1;
+    }
+}

@@ -1,11 +1,10 @@
 /*
- * miniargtable.c -- the subset of argtable2 that msamtools v1.1.3 uses.  TEST INFRASTRUCTURE for
- * oracle/_ref only.  Grammar (argtable2 is a getopt_long front end): short flags may be bundled
- * ("-bu"), a short option's value may be attached or separate ("-l80", "-l 80"), long options take
- * "--opt=value" or "--opt value", a value may be a negative number ("--ppt -980"), "--" ends
- * options, everything else is positional and lands in the arg_file entry.
+ * margs.c -- table-driven option parser of the drop-in CLI (see margs.h).  Grammar: short flags may
+ * be bundled ("-bu"), a short option's value may be attached or separate ("-l80", "-l 80"), long
+ * options take "--opt=value" or "--opt value", a value may be a negative number ("--ppt -980"),
+ * "--" ends options, everything else is positional and lands in the arg_file entry.
  */
-#include "argtable2.h"
+#include "margs.h"
 #include <stdlib.h>
 #include <string.h>
 
