@@ -391,39 +391,119 @@ __device__ __forceinline__ RecResult finish_record(const DecodeParams &p, const 
     return r;
 }
 
+// Parse one staged record (thread t of the tile, record index i) and write its SoA row.
+// s_off[0..nrec] are the tile's offsets, off_prev the offset of the record before the tile.
+template <int SLOT_WORDS>
+__device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t, uint64_t i, bool active, const uint32_t *s_slot,
+                                               const uint64_t *s_off, uint64_t off_prev, uint32_t &alg, uint32_t &nslow)
+{
+    const uint32_t mode = p.mode;
+    const bool force_slow = mode & DM_FORCE_SLOW;
+    const uint32_t hc = p.head_chunks, tc = p.tail_chunks;
+    if (!active) return;
+    const uint32_t *slot = s_slot + t * SLOT_WORDS;
+    const uint64_t o = s_off[t], len = s_off[t + 1] - o;
+    const uint32_t rel = (uint32_t)(o & 15u);
+    uint32_t arel = 0;
+    bool slow = force_slow;
+    RecCore c = force_slow ? parse_core(GlAcc{p.raw + o}, len) : parse_core(SmAcc{slot, rel}, len);
+    // does the record fit its windows?
+    const uint32_t need_head = 36 + c.lq + ((mode & DM_NEED_CIGAR) ? 4 * c.nc : 0);
+    if (rel + need_head > 16 * hc) slow = true;
+    if ((mode & DM_NEED_AUX) && c.aux_len) {
+        const uint64_t wend = (o + c.rec_len + 15ull) & ~15ull;           // end of the tail window
+        const uint64_t astart = o + c.aux_off;
+        if (wend < 16ull * tc || astart < wend - 16ull * tc) slow = true;
+        else arel = (uint32_t)(astart - (wend - 16ull * tc));
+    }
+    RecResult r;
+    uint32_t h = 0; bool eq = false;
+    if (c.bad) {
+        r = RecResult{0, 0, 0, 0, 0, c.flag & FB_FLAG_MASK, false};
+        atomicOr(p.err, DERR_FORMAT); atomicMin(p.err + 1, (uint32_t)min(i, (uint64_t)0xffffffffu));
+    } else if (slow) {
+        GlAcc g{p.raw + o};
+        GlAcc gx{p.raw + o + c.aux_off};
+        r = finish_record(p, c, g, gx);
+        const uint64_t op = t ? s_off[t - 1] : off_prev;
+        GlAcc gp{p.raw + op};
+        h = name_hash_eq(g, c.lq, gp, i > 0 && gp.u8(12) == c.lq, &eq);
+        if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
+            if (c.tid < p.n_targets) cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
+            else atomicOr(p.err, DERR_FORMAT);
+        }
+        r.fbits |= FB_SLOW; nslow = 1;
+    } else {
+        SmAcc hd{slot, rel};
+        SmAcc ax{slot + hc * 4, arel};
+        r = finish_record(p, c, hd, ax);
+        // previous record's QNAME: from its slot when its head window holds the whole name, else from global memory
+        bool prev_staged = false; uint32_t prel = 0, plq = 0;
+        if (t > 0) {
+            prel = (uint32_t)(s_off[t - 1] & 15u);
+            SmAcc pv{slot - SLOT_WORDS, prel};
+            plq = pv.u32(12) & 0xffu;
+            prev_staged = (s_off[t] - s_off[t - 1] >= 36) && (prel + 36 + plq <= 16 * hc);
+        }
+        if (prev_staged) {
+            SmAcc pv{slot - SLOT_WORDS, prel};
+            h = name_hash_eq(hd, c.lq, pv, plq == c.lq, &eq);
+        } else {
+            const uint64_t op = t ? s_off[t - 1] : off_prev;
+            GlAcc gp{p.raw + op};
+            h = name_hash_eq(hd, c.lq, gp, i > 0 && gp.u8(12) == c.lq, &eq);
+        }
+        if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
+            if (c.tid < p.n_targets) cover_record(hd, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
+            else atomicOr(p.err, DERR_FORMAT);
+        }
+    }
+    if (r.notag) { atomicOr(p.err, DERR_NOTAG); atomicMin(p.err + 1, (uint32_t)min(i, (uint64_t)0xffffffffu)); }
+    if (eq) r.fbits |= FB_EQPREV;
+    if (p.tid)   p.tid[i] = c.tid;
+    if (p.fb)    p.fb[i] = r.fbits;
+    if (p.score) p.score[i] = r.score;
+    if (p.hash)  p.hash[i] = h;
+    if (p.alen)  { p.alen[i] = r.alen; p.qlen[i] = r.qlen; p.qclip[i] = r.qclip; p.edit[i] = r.edit; }
+    // algorithmic bytes A(rec) = 8 (index) + 36 + qname [+ cigar] [+ aux]   
+    uint32_t a = 8u + 36u + c.lq + ((mode & DM_NEED_CIGAR) ? 4u * c.nc : 0u) + ((mode & DM_NEED_AUX) ? c.aux_len : 0u);
+    alg += a > (1u << 20) ? (1u << 20) : a;                          // keeps the per-warp sum inside 32 bits
+}
+
+// One CTA per tile of 128 records; ~11 CTAs are resident per SM, which is what hides the two
+// dependent DRAM latencies (offsets -> windows) and keeps the issue slots of the (low-ILP) parser
+// busy.  A persistent, register-staged software pipeline was measured and lost (profiles/r01_notes.md):
+// at the 4 CTAs/SM its 123 registers allow, the parser alone cannot fill the schedulers.
 template <int LPR>
 __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ DecodeParams p)
 {
     constexpr int SLOT_WORDS = LPR * 4 + 1;            // odd stride: thread-per-slot reads are conflict-free
     __shared__ uint32_t s_slot[DEC_R * SLOT_WORDS + 2];
     __shared__ uint64_t s_off[DEC_R + 1];
-    __shared__ uint64_t s_offprev;
     __shared__ uint32_t s_hb[DEC_R], s_tb[DEC_R];
-    __shared__ uint8_t  s_slow[DEC_R], s_lq[DEC_R];
 
     const uint32_t t = threadIdx.x;
     const uint64_t t0 = (uint64_t)blockIdx.x * DEC_R;
     const uint32_t nrec = (uint32_t)min((uint64_t)DEC_R, p.n - t0);
     const uint64_t i = t0 + t;
     const bool active = t < nrec;
-    const uint32_t mode = p.mode;
-    const bool force_slow = mode & DM_FORCE_SLOW;
     const uint32_t hc = p.head_chunks, tc = p.tail_chunks;
 
     // offsets: one coalesced load; each thread also fetches its successor's offset so that the
     // 16-byte chunk indices of both windows are known without a second barrier round
+    uint64_t off_prev = 0;
     if (active) {
         const uint64_t o = p.off[i], o1 = p.off[i + 1];
         s_off[t] = o;
         if (t == nrec - 1) s_off[nrec] = o1;
         s_hb[t] = (uint32_t)(o >> 4);                                       // head window: first chunk
         s_tb[t] = (uint32_t)((o1 + 15ull) >> 4) - (hc + tc);                // tail window: chunk index of lane `sub` is s_tb + sub
+        if (t == 0 && t0) off_prev = p.off[t0 - 1];
     }
-    if (t == 0) s_offprev = t0 ? p.off[t0 - 1] : 0;
     __syncthreads();
 
     // ---- stage both windows of every record: LPR lanes per record, one 16-byte load each
-    if (!force_slow) {
+    if (!(p.mode & DM_FORCE_SLOW)) {
         const uint32_t nchunks = (uint32_t)(p.nbytes_readable >> 4);
         const uint32_t sub = t % LPR, r0 = t / LPR;
         const bool head = sub < hc, go = sub < hc + tc;
@@ -442,80 +522,9 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
     }
     __syncthreads();
 
-    // ---- core fields; does the record fit its windows?
-    RecCore c; c.bad = false; c.lq = 0; c.nc = 0; c.aux_len = 0; c.aux_off = 0; c.flag = 0; c.tid = -1; c.pos = 0; c.lseq = 0; c.rec_len = 0;
-    bool slow = force_slow;
-    uint32_t rel = 0, arel = 0;
-    const uint32_t *slot = s_slot + t * SLOT_WORDS;
-    if (active) {
-        const uint64_t o = s_off[t], len = s_off[t + 1] - o;
-        rel = (uint32_t)(o & 15u);
-        if (force_slow) c = parse_core(GlAcc{p.raw + o}, len);
-        else            c = parse_core(SmAcc{slot, rel}, len);
-        const uint32_t need_head = 36 + c.lq + ((mode & DM_NEED_CIGAR) ? 4 * c.nc : 0);
-        if (rel + need_head > 16 * hc) slow = true;
-        if ((mode & DM_NEED_AUX) && c.aux_len) {
-            const uint64_t wend = (o + c.rec_len + 15ull) & ~15ull;           // end of the tail window
-            const uint64_t astart = o + c.aux_off;
-            if (wend < 16ull * tc || astart < wend - 16ull * tc) slow = true;
-            else arel = (uint32_t)(astart - (wend - 16ull * tc));
-        }
-        s_slow[t] = slow;
-        s_lq[t]   = (uint8_t)c.lq;
-    }
-    __syncthreads();
-
     uint32_t alg = 0, nslow = 0;
-    if (active) {
-        const uint64_t o = s_off[t];
-        RecResult r;
-        uint32_t h = 0; bool eq = false;
-        if (c.bad) {
-            r = RecResult{0, 0, 0, 0, 0, c.flag & FB_FLAG_MASK, false};
-            atomicOr(p.err, DERR_FORMAT); atomicMin(p.err + 1, (uint32_t)min(i, (uint64_t)0xffffffffu));
-        } else if (slow) {
-            GlAcc g{p.raw + o};
-            GlAcc gx{p.raw + o + c.aux_off};
-            r = finish_record(p, c, g, gx);
-            {
-                const uint64_t op = t ? s_off[t - 1] : s_offprev;
-                GlAcc gp{p.raw + op};
-                h = name_hash_eq(g, c.lq, gp, i > 0 && gp.u8(12) == c.lq, &eq);
-            }
-            if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
-                if (c.tid < p.n_targets) cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
-                else atomicOr(p.err, DERR_FORMAT);
-            }
-            r.fbits |= FB_SLOW; nslow = 1;
-        } else {
-            SmAcc hd{slot, rel};
-            SmAcc ax{slot + hc * 4, arel};
-            r = finish_record(p, c, hd, ax);
-            if (t > 0 && !s_slow[t - 1]) {
-                SmAcc pv{slot - SLOT_WORDS, (uint32_t)(s_off[t - 1] & 15u)};
-                h = name_hash_eq(hd, c.lq, pv, s_lq[t - 1] == c.lq, &eq);
-            } else {
-                const uint64_t op = t ? s_off[t - 1] : s_offprev;
-                GlAcc gp{p.raw + op};
-                h = name_hash_eq(hd, c.lq, gp, i > 0 && gp.u8(12) == c.lq, &eq);
-            }
-            if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
-                if (c.tid < p.n_targets) cover_record(hd, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
-                else atomicOr(p.err, DERR_FORMAT);
-            }
-        }
-        if (r.notag) { atomicOr(p.err, DERR_NOTAG); atomicMin(p.err + 1, (uint32_t)min(i, (uint64_t)0xffffffffu)); }
-        if (eq) r.fbits |= FB_EQPREV;
-        if (p.tid)   p.tid[i] = c.tid;
-        if (p.fb)    p.fb[i] = r.fbits;
-        if (p.score) p.score[i] = r.score;
-        if (p.hash)  p.hash[i] = h;
-        if (p.alen)  { p.alen[i] = r.alen; p.qlen[i] = r.qlen; p.qclip[i] = r.qclip; p.edit[i] = r.edit; }
-        // algorithmic bytes A(rec) = 8 (index) + 36 + qname [+ cigar] [+ aux]   
-        alg = 8u + 36u + c.lq + ((mode & DM_NEED_CIGAR) ? 4u * c.nc : 0u) + ((mode & DM_NEED_AUX) ? c.aux_len : 0u);
-        if (alg > (1u << 26)) alg = 1u << 26;                       // keeps the 32-lane sum inside 32 bits
-    }
-    alg = __reduce_add_sync(0xffffffffu, alg);                      // REDUX: one instruction per warp
+    parse_and_emit<SLOT_WORDS>(p, t, i, active, s_slot, s_off, off_prev, alg, nslow);
+    alg = __reduce_add_sync(0xffffffffu, alg);         // REDUX: one instruction per warp
     nslow = __reduce_add_sync(0xffffffffu, nslow);
     if ((t & 31u) == 0) {
         if (alg) atomicAdd(p.acct, (unsigned long long)alg);
