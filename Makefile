@@ -21,7 +21,7 @@ $(SYNTH): $(CSRC)/synth.c
 # drop-in CLI: plain C host (own BAM/SAM/BGZF I/O over zlib) linked against the CUDA library
 $(CLI): $(CSRC)/cli/msamtools_main.c $(HOSTSRC) $(wildcard $(CSRC)/host/*.h) include/msamtools_b200.h $(LIB)
 	mkdir -p msamtools_b200/bin
-	$(CC) -O2 -g -std=gnu99 -Wall -Wextra -o $@ $(CSRC)/cli/msamtools_main.c $(HOSTSRC) -Lmsamtools_b200 -lmsamtools_b200 -Wl,-rpath,'$$ORIGIN/..' -lz -lm
+	$(CC) -O2 -g -std=gnu99 -Wall -Wextra -o $@ $(CSRC)/cli/msamtools_main.c $(HOSTSRC) -Lmsamtools_b200 -lmsamtools_b200 -Wl,-rpath,'$$ORIGIN/..' -lz -lm -lpthread
 
 oracle:
 	$(MAKE) -C oracle

@@ -21,6 +21,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "../../../include/msamtools_b200.h"
@@ -232,6 +234,7 @@ static msg_ctx *run_stream(run_t *r)
     if (msg_create(&r->cfg, &ctx)) mDie("%s", msg_last_error(NULL));
     uint8_t *outbuf = NULL; size_t outcap = 0;
     size_t want_n = CHUNK_RECORDS, want_b = CHUNK_BYTES;
+    double t_push = 0; size_t n_pushed = 0;
     for (;;) {
         if (!r->eof) chunk_fill(&r->chunk, r->in, r->hdr, want_n, want_b, &r->eof);
         chunk_t *c = &r->chunk;
@@ -246,7 +249,12 @@ static msg_ctx *run_stream(run_t *r)
                 if (k == 0) { want_n = c->n * 2; want_b = c->len * 2; continue; }
             }
         }
-        if (msg_push(ctx, c->raw, (size_t)c->off[k], c->off, k)) gpu_die(ctx);
+        {
+            struct timespec a, b; clock_gettime(CLOCK_MONOTONIC, &a);
+            if (msg_push(ctx, c->raw, (size_t)c->off[k], c->off, k)) gpu_die(ctx);
+            clock_gettime(CLOCK_MONOTONIC, &b);
+            t_push += (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec); n_pushed += k;
+        }
         if (r->cfg.want_records) {
             size_t nb = 0, nr = 0;
             if (msg_pull_records(ctx, NULL, 0, &nb, &nr)) gpu_die(ctx);
@@ -263,6 +271,13 @@ static msg_ctx *run_stream(run_t *r)
         if (r->eof && c->n == 0) break;
     }
     free(outbuf);
+    if (getenv("MSAMTOOLS_TIMING")) {      /* host-ingest vs GPU time, reported separately (BASELINE.json north_star) */
+        uint64_t ib = 0; double isec = 0; msg_timing tm;
+        bio_ingest_stats(r->in, &ib, &isec);
+        msg_get_timing(ctx, &tm, 0);
+        fprintf(stderr, "# timing: host ingest %.3f GB in %.3f s (%.2f GB/s, read+inflate); push loop %.3f s (H2D %.3f GB, GPU kernels %.1f ms); %llu records\n",
+                ib / 1e9, isec, isec > 0 ? ib / 1e9 / isec : 0.0, t_push, tm.h2d_bytes / 1e9, tm.total_ms, (unsigned long long)n_pushed);
+    }
     return ctx;
 }
 
@@ -270,6 +285,11 @@ static void open_input(run_t *r, const char *infile)
 {
     r->in = bio_open_read(infile);
     if (!r->in) mDie("Cannot open %s for reading", infile);
+    {   /* BGZF blocks are inflated on worker threads (MSAMTOOLS_THREADS, default: online cores, at most 16) */
+        long n = sysconf(_SC_NPROCESSORS_ONLN);
+        if (getenv("MSAMTOOLS_THREADS")) n = atol(getenv("MSAMTOOLS_THREADS"));
+        bio_set_threads(r->in, n > 16 ? 16 : (int)n);
+    }
     r->hdr = bio_read_header(r->in);
     if (!r->hdr) mDie("Cannot read header from %s", infile);
 }

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <time.h>
 #include <zlib.h>
 
 #define BGZF_BLOCK 0xff00          /* payload bytes per BGZF block, as htslib */
@@ -19,6 +21,10 @@ struct bio_file {
     uint8_t *in; size_t in_len;
     uint8_t *dec; size_t dec_len, dec_pos, dec_cap;
     char *line; size_t line_cap;
+    /* parallel BGZF inflate */
+    int threads, bgzf;
+    uint8_t *cin; size_t cin_len, cin_cap;
+    uint64_t ingest_bytes; double ingest_sec;
     /* name -> tid hash for SAM parsing */
     int32_t *ht; size_t ht_size; const bio_hdr *ht_hdr;
     /* writer */
@@ -48,9 +54,102 @@ static int grow(uint8_t **buf, size_t *cap, size_t need)
 }
 
 /* ============================================================ decompressed byte stream */
+static double now_sec(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+void bio_set_threads(bio_file *f, int n) { if (f && !f->writing) f->threads = n < 1 ? 1 : (n > 64 ? 64 : n); }
+void bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds) { if (bytes) *bytes = f->ingest_bytes; if (seconds) *seconds = f->ingest_sec; }
+
+/* ---- BGZF blocks are independent gzip members: inflate a batch of them on worker threads */
+typedef struct { size_t in_off, in_len, out_off; uint32_t isize, crc; } bgzf_blk;
+typedef struct { const uint8_t *in; uint8_t *out; const bgzf_blk *blk; size_t nblk; int id, nthr; int err; } bgzf_job;
+
+static void *bgzf_worker(void *arg)
+{
+    bgzf_job *j = arg;
+    z_stream zs; memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) { j->err = 1; return NULL; }
+    for (size_t k = (size_t)j->id; k < j->nblk; k += (size_t)j->nthr) {
+        const bgzf_blk *b = &j->blk[k];
+        if (b->isize == 0) continue;
+        inflateReset(&zs);
+        zs.next_in = (Bytef *)(j->in + b->in_off); zs.avail_in = (uInt)b->in_len;
+        zs.next_out = j->out + b->out_off; zs.avail_out = b->isize;
+        int rc = inflate(&zs, Z_FINISH);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) { j->err = 1; break; }
+        if ((uint32_t)crc32(crc32(0L, NULL, 0), j->out + b->out_off, b->isize) != b->crc) { j->err = 1; break; }
+    }
+    inflateEnd(&zs);
+    return NULL;
+}
+
+#define BGZF_BATCH ((size_t)48 << 20)
+
+static int rd_fill_bgzf(bio_file *f)
+{   /* refill f->dec with the inflated payload of the next batch of whole blocks; 0 = EOF, 1 = ok, -1 = error */
+    for (;;) {
+        if (!f->in_eof && f->cin_len < BGZF_BATCH) {
+            if (grow(&f->cin, &f->cin_cap, BGZF_BATCH + (1 << 17))) { set_err(f, "out of memory"); return -1; }
+            size_t got = fread(f->cin + f->cin_len, 1, BGZF_BATCH + (1 << 16) - f->cin_len, f->fp);
+            f->cin_len += got;
+            if (got == 0 || feof(f->fp)) f->in_eof = 1;
+        }
+        /* split into whole blocks */
+        size_t p = 0, nblk = 0, out = 0, cap = 0; bgzf_blk *blk = NULL;
+        while (p + 18 <= f->cin_len) {
+            const uint8_t *h = f->cin + p;
+            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { free(blk); set_err(f, "corrupt BGZF block header"); return -1; }
+            size_t xlen = h[10] | (size_t)h[11] << 8, q = 12, bsize = 0;
+            if (p + 12 + xlen > f->cin_len) break;
+            while (q + 4 <= 12 + xlen) {
+                size_t slen = h[q + 2] | (size_t)h[q + 3] << 8;
+                if (h[q] == 'B' && h[q + 1] == 'C' && slen == 2) bsize = (h[q + 4] | (size_t)h[q + 5] << 8) + 1;
+                q += 4 + slen;
+            }
+            if (!bsize || bsize < 12 + xlen + 8) { free(blk); set_err(f, "corrupt BGZF block header"); return -1; }
+            if (p + bsize > f->cin_len) break;
+            if (nblk == cap) { cap = cap ? 2 * cap : 1024; blk = realloc(blk, cap * sizeof *blk); }
+            blk[nblk].in_off = p + 12 + xlen; blk[nblk].in_len = bsize - 12 - xlen - 8; blk[nblk].out_off = out;
+            blk[nblk].crc = le32(h + bsize - 8); blk[nblk].isize = le32(h + bsize - 4);
+            out += blk[nblk].isize; nblk++; p += bsize;
+        }
+        if (nblk == 0) {
+            free(blk);
+            if (!f->in_eof) continue;
+            if (f->cin_len) { set_err(f, "truncated BGZF block"); return -1; }
+            return 0;
+        }
+        if (grow(&f->dec, &f->dec_cap, out + 16)) { free(blk); set_err(f, "out of memory"); return -1; }
+        int nthr = f->threads; if ((size_t)nthr > nblk) nthr = (int)nblk;
+        pthread_t th[64]; bgzf_job job[64];
+        for (int i = 0; i < nthr; i++) {
+            job[i] = (bgzf_job){ f->cin, f->dec, blk, nblk, i, nthr, 0 };
+            if (i && pthread_create(&th[i], NULL, bgzf_worker, &job[i])) { job[i].err = 2; }
+        }
+        bgzf_worker(&job[0]);
+        int err = job[0].err;
+        for (int i = 1; i < nthr; i++) { if (job[i].err == 2) { job[i].err = 0; bgzf_worker(&job[i]); } else pthread_join(th[i], NULL); err |= job[i].err; }
+        free(blk);
+        if (err) { set_err(f, "corrupt BGZF block (inflate/CRC)"); return -1; }
+        memmove(f->cin, f->cin + p, f->cin_len - p); f->cin_len -= p;
+        f->dec_pos = 0; f->dec_len = out;
+        if (out) return 1;           /* a batch of empty (EOF-marker) blocks: look at the next one */
+    }
+}
+
+static int rd_fill_inner(bio_file *f);
 static int rd_fill(bio_file *f)
-{   /* make at least one more byte available in dec[dec_pos..dec_len); 0 = EOF, 1 = ok, -1 = error */
+{
     if (f->dec_pos < f->dec_len) return 1;
+    const double t0 = now_sec();
+    const int rc = rd_fill_inner(f);
+    f->ingest_sec += now_sec() - t0;
+    if (rc == 1) f->ingest_bytes += f->dec_len;
+    return rc;
+}
+
+static int rd_fill_inner(bio_file *f)
+{   /* make at least one more byte available in dec[dec_pos..dec_len); 0 = EOF, 1 = ok, -1 = error */
+    if (f->bgzf) return rd_fill_bgzf(f);
     f->dec_pos = f->dec_len = 0;
     if (grow(&f->dec, &f->dec_cap, IN_CHUNK * 4)) { set_err(f, "out of memory"); return -1; }
     if (!f->detected) {
@@ -58,6 +157,12 @@ static int rd_fill(bio_file *f)
         if (f->in_len < IN_CHUNK) f->in_eof = 1;
         f->compressed = f->in_len >= 2 && f->in[0] == 0x1f && f->in[1] == 0x8b;
         f->detected = 1;
+        if (f->compressed && f->threads > 1 && f->in_len >= 18 && (f->in[3] & 4) && f->in[12] == 'B' && f->in[13] == 'C') {
+            f->bgzf = 1;
+            if (grow(&f->cin, &f->cin_cap, BGZF_BATCH + (1 << 17))) { set_err(f, "out of memory"); return -1; }
+            memcpy(f->cin, f->in, f->in_len); f->cin_len = f->in_len;
+            return rd_fill_bgzf(f);
+        }
         if (f->compressed) {
             memset(&f->zs, 0, sizeof f->zs);
             if (inflateInit2(&f->zs, 15 + 32) != Z_OK) { set_err(f, "inflateInit failed"); return -1; }
@@ -148,6 +253,7 @@ bio_file *bio_open_read(const char *path)
     if (!f->fp) { free(f); return NULL; }
     f->in = malloc(IN_CHUNK);
     if (!f->in) { if (f->own_fp) fclose(f->fp); free(f); return NULL; }
+    f->threads = 1;
     return f;
 }
 
@@ -674,7 +780,7 @@ int bio_close(bio_file *f)
         if (fflush(f->fp)) rc = -1;
     } else if (f->z_init) inflateEnd(&f->zs);
     if (f->own_fp && fclose(f->fp)) rc = -1;
-    free(f->in); free(f->dec); free(f->line); free(f->ht); free(f->wbuf); free(f->fmt); free(f);
+    free(f->in); free(f->dec); free(f->line); free(f->cin); free(f->ht); free(f->wbuf); free(f->fmt); free(f);
     return rc;
 }
 

@@ -29,6 +29,11 @@ bio_hdr  *bio_read_header(bio_file *f);                       /* NULL on error *
 /* next record as a raw BAM record appended at (*buf)+(*len); grows *buf. 1 = record, 0 = EOF, <0 = error */
 int       bio_read_record(bio_file *f, const bio_hdr *h, uint8_t **buf, size_t *cap, size_t *len);
 const char *bio_error(const bio_file *f);
+/* BGZF input only: inflate blocks on `n` worker threads (blocks are independent gzip members).
+ * Default 1 (streaming inflate on the caller's thread).  Call before bio_read_header.          */
+void      bio_set_threads(bio_file *f, int n);
+/* bytes of decompressed input produced so far / seconds spent producing them (read + inflate)  */
+void      bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds);
 
 /* ---- writing: mode "w" SAM, "wh" SAM+header, "wb" BAM, "wbu" BAM in level-0 BGZF (msam_filter.c:464-470) */
 bio_file *bio_open_write(const char *path, const char *mode);
