@@ -291,7 +291,8 @@ def run_ours(args):
 
     raw, off, tlen, gen = make_batch(args.records, rank)
     n = len(off) - 1
-    ctx = m.Context(profile=True, multi=MULTI, n_targets=len(tlen), device=local, n_ranks=world, rank=rank,
+    # kept=False: the profile is the filter stage's only consumer (the reference pipe's output is the profile, not the records)
+    ctx = m.Context(profile=True, multi=MULTI, kept=False, n_targets=len(tlen), device=local, n_ranks=world, rank=rank,
                     nccl_unique_id=uid, **FILTER_OPTS)
 
     def barrier():

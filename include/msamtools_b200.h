@@ -91,7 +91,8 @@ typedef struct msg_config {
     int32_t  max_clip;           /* 100 - z; 100 when -z absent (MAX_CLIP, :439-447)   */
 
     /* ---- stage 2 consumers of the (filtered) record stream ---- */
-    uint8_t  want_kept;          /* keep the kept-record index list for msg_pull_kept  */
+    uint8_t  want_kept;          /* keep the kept-record index list for msg_pull_kept; with 0, best-hit + profile
+                                    runs as one fused pass and only msg_kept_count is available          */
     uint8_t  want_records;       /* materialise filtered record bytes (msg_pull_records) */
     uint8_t  want_profile;       /* msam_profile.c                                     */
     uint8_t  want_coverage;      /* msam_coverage.c                                    */
@@ -201,6 +202,8 @@ typedef struct msg_timing {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t alg_bytes;      /* sum over pushed records of A(rec)                    */
     uint64_t slow_records;   /* records parsed by the global-memory slow path                    */
+    uint64_t fused_chunks;   /* chunks that went through the fused besthit->profile pass          */
+    uint64_t fused_fallbacks;/* ... of which the guard sent to the general pipeline               */
 } msg_timing;
 int  msg_get_timing(msg_ctx *ctx, msg_timing *t, int reset);
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of this

@@ -8,6 +8,7 @@
 #include "profile.cuh"
 #include "coverage.cuh"
 #include "gather.cuh"
+#include "fused.cuh"
 
 #include <nccl.h>        // types only; the library itself is dlopen'ed (no link-time dependency)
 #include <dlfcn.h>
@@ -95,6 +96,9 @@ struct msg_ctx {
     DevBuf raw, off, tid, fb, score, hash, nid, st_alen, st_qlen, st_qclip, st_edit;
     DevBuf kbase, worklist, gmeta, out_idx, tile_sums, pcount, scanv, biglist;
     uint32_t *d_wl = nullptr;                  // [0] best-hit worklist length [1] profile worklist length
+    // fused filter+besthit -> profile path (fused.cuh): chunk-local accumulators, list cursors, window summaries
+    uint32_t *d_ui_tmp = nullptr; double *d_d_tmp = nullptr; uint32_t *d_fcnt = nullptr, *d_cursor = nullptr; DevBuf win;
+    bool fused_enabled = false; uint64_t fused_chunks = 0, fused_fallbacks = 0;
     DevBuf out_len, out_off, plan, out_rec;
     const uint8_t *cur_raw = nullptr; const uint64_t *cur_off = nullptr;
     uint64_t cur_n = 0, cur_nbytes = 0;
@@ -108,7 +112,7 @@ struct msg_ctx {
 
     // profile accumulators
     uint32_t *d_ui = nullptr; double *d_d = nullptr; uint32_t *d_counters = nullptr;   // counters[8]
-    DevBuf csr_off, csr_fid; uint64_t csr_lists = 0, csr_ent = 0;     // multi-mapper lists (CSR), appended per chunk
+    DevBuf csr_off, csr_len, csr_fid; uint64_t csr_lists = 0, csr_ent = 0;     // multi-mapper lists (CSR), appended per chunk
     DevBuf t_ui, t_d, t_cnt, t_cov;                                    // allreduce staging (n_ranks > 1)
     uint32_t *d_stamp = nullptr; uint32_t stamp_next = 0;
     double *d_U = nullptr, *d_a = nullptr, *d_inc = nullptr, *d_partial = nullptr, *d_delta = nullptr;
@@ -237,15 +241,14 @@ int profile_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
         const uint32_t nl = (uint32_t)(tot >> 32), ne = (uint32_t)tot;
         if (nl) {
             if (c->csr_lists + nl >= 0xffffffffull || c->csr_ent + ne >= 0xffffffffull) return fail(c, MSG_ERANGE, "multi-mapper CSR exceeds 2^32 entries on one GPU");
-            CU(c->csr_off.reserve_keep((c->csr_lists + nl + 1) * 4, (c->csr_lists + 1) * 4, c->stream));
+            CU(c->csr_off.reserve_keep((c->csr_lists + nl + 1) * 4, c->csr_lists * 4, c->stream));
+            CU(c->csr_len.reserve_keep((c->csr_lists + nl + 1) * 4, c->csr_lists * 4, c->stream));
             CU(c->csr_fid.reserve_keep((c->csr_ent + ne + 1) * 4, c->csr_ent * 4, c->stream));
             profile_warp_fill_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(p, gmeta, c->scanv.as<unsigned long long>(), c->csr_off.as<uint32_t>(),
-                                                                             c->csr_fid.as<int32_t>(), (uint32_t)c->csr_lists, (uint32_t)c->csr_ent); LAUNCHED(c);
-            profile_walk_fill_kernel<<<pgrid, 256, 0, c->stream>>>(p, c->scanv.as<unsigned long long>(), c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(),
-                                                                   (uint32_t)c->csr_lists, (uint32_t)c->csr_ent, c->worklist.as<uint32_t>(), c->d_wl + 1); LAUNCHED(c);
+                                                                             c->csr_len.as<uint32_t>(), c->csr_fid.as<int32_t>(), (uint32_t)c->csr_lists, (uint32_t)c->csr_ent); LAUNCHED(c);
+            profile_walk_fill_kernel<<<pgrid, 256, 0, c->stream>>>(p, c->scanv.as<unsigned long long>(), c->csr_off.as<uint32_t>(), c->csr_len.as<uint32_t>(),
+                                                                   c->csr_fid.as<int32_t>(), (uint32_t)c->csr_lists, (uint32_t)c->csr_ent, c->worklist.as<uint32_t>(), c->d_wl + 1); LAUNCHED(c);
             c->csr_lists += nl; c->csr_ent += ne;
-            const uint32_t endv = (uint32_t)c->csr_ent;
-            CU(cudaMemcpyAsync(c->csr_off.as<uint32_t>() + c->csr_lists, &endv, 4, cudaMemcpyHostToDevice, c->stream));
         }
     }
     CU(cudaMemcpyAsync(&nbig, c->d_counters + 3, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -256,7 +259,7 @@ int profile_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
         if (!c->d_stamp) { CU(cudaMalloc(&c->d_stamp, (size_t)(g.n_features > 0 ? g.n_features : 1) * 4));
                            CU(cudaMemsetAsync(c->d_stamp, 0, (size_t)(g.n_features > 0 ? g.n_features : 1) * 4, c->stream)); }
         uint32_t *d_tot = reinterpret_cast<uint32_t *>(c->d_total);
-        profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, nullptr, nullptr, d_tot, 0, 0, 0); LAUNCHED(c);
+        profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, nullptr, nullptr, nullptr, d_tot, 0, 0, 0); LAUNCHED(c);
         c->stamp_next += nbig + 1;
         if (prop) {
             uint32_t tot[2];
@@ -264,9 +267,10 @@ int profile_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
             CU(cudaStreamSynchronize(c->stream));
             if (tot[0]) {
                 if (c->csr_lists + tot[0] >= 0xffffffffull || c->csr_ent + tot[1] >= 0xffffffffull) return fail(c, MSG_ERANGE, "multi-mapper CSR exceeds 2^32 entries on one GPU");
-                CU(c->csr_off.reserve_keep((c->csr_lists + tot[0] + 1) * 4, (c->csr_lists + 1) * 4, c->stream));
+                CU(c->csr_off.reserve_keep((c->csr_lists + tot[0] + 1) * 4, c->csr_lists * 4, c->stream));
+                CU(c->csr_len.reserve_keep((c->csr_lists + tot[0] + 1) * 4, c->csr_lists * 4, c->stream));
                 CU(c->csr_fid.reserve_keep((c->csr_ent + tot[1] + 2) * 4, c->csr_ent * 4, c->stream));
-                profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(),
+                profile_big_kernel<<<1, 1, 0, c->stream>>>(p, nbig, c->d_stamp, c->stamp_next, c->csr_off.as<uint32_t>(), c->csr_len.as<uint32_t>(), c->csr_fid.as<int32_t>(),
                                                            d_tot, 1, (uint32_t)c->csr_lists, (uint32_t)c->csr_ent); LAUNCHED(c);
                 c->stamp_next += nbig + 1;
                 c->csr_lists += tot[0]; c->csr_ent += tot[1];
@@ -293,6 +297,61 @@ int records_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
                                                                    c->out_len.as<uint32_t>(), c->plan.as<GatherPlan>(),
                                                                    c->score.as<int32_t>(), c->out_rec.as<uint8_t>()); LAUNCHED(c);
     c->out_bytes = tot;
+    return MSG_OK;
+}
+
+// filter+besthit -> profile without materialising the kept stream (fused.cuh).  Returns MSG_OK with
+// *done = true when the chunk was fully handled, *done = false when the guard asked for the general
+// pipeline (accumulators untouched in that case).
+int fused_stage(msg_ctx *c, const DecodeParams &dp, uint64_t n, bool *done)
+{
+    const msg_config &g = c->cfg;
+    *done = false;
+    const bool prop = g.share_type == MSG_MULTI_PROPORTIONAL;
+    const uint32_t nwin = nblocks(n, 32);
+    CU(c->worklist.reserve(((size_t)nwin + 2) * 4));
+    CU(c->win.reserve((size_t)nwin * sizeof(WinInfo)));
+    if (prop) {
+        if (c->csr_lists + n / 2 + 2 >= 0xffffffffull || c->csr_ent + n + 2 >= 0xffffffffull) return MSG_OK;       // general path reports the overflow
+        CU(c->csr_off.reserve_keep((c->csr_lists + n / 2 + 2) * 4, c->csr_lists * 4, c->stream));
+        CU(c->csr_len.reserve_keep((c->csr_lists + n / 2 + 2) * 4, c->csr_lists * 4, c->stream));
+        CU(c->csr_fid.reserve_keep((c->csr_ent + n + 2) * 4, c->csr_ent * 4, c->stream));
+    }
+    const uint32_t cur[2] = {(uint32_t)c->csr_lists, (uint32_t)c->csr_ent};
+    CU(cudaMemcpyAsync(c->d_cursor, cur, 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_fcnt, 0, 32, c->stream));
+    CU(cudaMemsetAsync(c->d_wl, 0, 4, c->stream));
+    FusedParams p;
+    p.fb = dp.fb; p.score = dp.score; p.tid = dp.tid; p.hash = dp.hash;
+    p.fmap = c->d_fmap; p.n_targets = g.n_targets; p.n_features = g.n_features; p.n = n;
+    p.uniq = g.hit_mode == MSG_HIT_UNIQUE; p.share_type = g.share_type;
+    p.ui = c->d_ui_tmp; p.d = c->d_d_tmp; p.cnt = c->d_fcnt; p.cursor = c->d_cursor;
+    p.l_start = c->csr_off.as<uint32_t>(); p.l_len = c->csr_len.as<uint32_t>(); p.l_fid = c->csr_fid.as<int32_t>();
+    p.worklist = c->worklist.as<uint32_t>(); p.wl_count = c->d_wl; p.win = c->win.as<WinInfo>();
+    p.big_threshold = 1024; p.err = c->d_err;
+    if ((uint32_t)g.n_features <= 4096u) fused_warp_kernel<true><<<nblocks(n, 256), 256, (size_t)g.n_features * 4, c->stream>>>(p);
+    else                                  fused_warp_kernel<false><<<nblocks(n, 256), 256, 0, c->stream>>>(p);
+    LAUNCHED(c);
+    fused_walk_kernel<<<std::min<uint32_t>(nblocks(nwin, 128), 148u * 8u), 128, 0, c->stream>>>(p); LAUNCHED(c);
+    fused_guard_kernel<<<nblocks(nwin, 256), 256, 0, c->stream>>>(p.win, nwin, c->d_fcnt + 3); LAUNCHED(c);
+    uint32_t h[8];
+    CU(cudaMemcpyAsync(h, c->d_fcnt, 20, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h + 5, c->d_cursor, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += 28;
+    c->fused_chunks++;
+    const size_t F = (size_t)(g.n_features > 0 ? g.n_features : 1);
+    if (h[3]) {            // guard tripped: drop this chunk's partial sums, keep the list cursors where they were
+        c->fused_fallbacks++;
+        CU(cudaMemsetAsync(c->d_ui_tmp, 0, F * 4, c->stream));
+        CU(cudaMemsetAsync(c->d_d_tmp, 0, F * 8, c->stream));
+        return MSG_OK;
+    }
+    fused_commit_kernel<<<nblocks(F < 3 ? 3 : F, 256), 256, 0, c->stream>>>(c->d_ui, c->d_d, c->d_ui_tmp, c->d_d_tmp, (uint32_t)g.n_features,
+                                                                           g.share_type == MSG_MULTI_EQUAL, c->d_counters, c->d_fcnt); LAUNCHED(c);
+    c->csr_lists = h[5]; c->csr_ent = h[6];
+    c->n_kept = h[4]; c->have_stream = false;
+    *done = true;
     return MSG_OK;
 }
 
@@ -390,9 +449,19 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
     CU(cudaEventRecord(k1, c->stream));
     c->ev_decode.push_back({k0, k1});
 
+    int rc = MSG_OK;
+    if (c->fused_enabled && g.want_profile) {
+        bool done = false;
+        rc = fused_stage(c, p, n, &done);
+        if (rc) return rc;
+        if (done) {
+            CU(cudaEventRecord(t1, c->stream));
+            c->ev_total.push_back({t0, t1});
+            return check_device_errors(c);
+        }
+    }
     // ---- filter stage -> stream of kept records in reference output order
     const uint32_t *stream = nullptr; uint64_t m = n;
-    int rc = MSG_OK;
     if (g.do_filter) {
         CU(c->out_idx.reserve(n * 4));
         uint32_t tot = 0;
@@ -523,6 +592,10 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
         CUC(cudaMalloc(&ctx->d_ui, F * 4)); CUC(cudaMalloc(&ctx->d_d, F * 8)); CUC(cudaMalloc(&ctx->d_counters, 32));
         CUC(cudaMalloc(&ctx->d_U, F * 8)); CUC(cudaMalloc(&ctx->d_a, F * 8)); CUC(cudaMalloc(&ctx->d_inc, F * 8));
         CUC(cudaMalloc(&ctx->d_partial, ((F + 255) / 256) * 8)); CUC(cudaMalloc(&ctx->d_delta, 8 * 20)); CUC(cudaMalloc(&ctx->d_purged, 4));
+        CUC(cudaMalloc(&ctx->d_ui_tmp, F * 4)); CUC(cudaMalloc(&ctx->d_d_tmp, F * 8)); CUC(cudaMalloc(&ctx->d_fcnt, 32)); CUC(cudaMalloc(&ctx->d_cursor, 8));
+        CUC(cudaMemset(ctx->d_ui_tmp, 0, F * 4)); CUC(cudaMemset(ctx->d_d_tmp, 0, F * 8));
+        // the fused pass applies when the profile is the filter stage's only consumer (MSG_NO_FUSED=1 forces the general pipeline)
+        ctx->fused_enabled = g.do_filter && g.hit_mode != MSG_HIT_NONE && !g.want_records && !g.want_kept && !g.want_coverage && !getenv("MSG_NO_FUSED");
     }
     if (g.want_coverage) {
         std::vector<uint64_t> base(T + 1, 0);
@@ -558,10 +631,10 @@ void msg_destroy(msg_ctx *c)
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     DevBuf *bufs[] = {&c->raw, &c->off, &c->tid, &c->fb, &c->score, &c->hash, &c->nid, &c->st_alen, &c->st_qlen, &c->st_qclip, &c->st_edit,
                       &c->kbase, &c->worklist, &c->gmeta, &c->out_idx, &c->tile_sums, &c->pcount, &c->scanv, &c->biglist, &c->out_len, &c->out_off, &c->plan, &c->out_rec,
-                      &c->csr_off, &c->csr_fid, &c->t_ui, &c->t_d, &c->t_cnt, &c->t_cov};
+                      &c->csr_off, &c->csr_len, &c->csr_fid, &c->win, &c->t_ui, &c->t_d, &c->t_cnt, &c->t_cov};
     for (DevBuf *b : bufs) b->release();
     void *ptrs[] = {c->d_fmap, c->d_tlen, c->d_covbase, c->d_err, c->d_acct, c->d_total, c->d_ui, c->d_d, c->d_counters, c->d_stamp, c->d_U, c->d_a,
-                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_wl, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
+                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_wl, c->d_ui_tmp, c->d_d_tmp, c->d_fcnt, c->d_cursor, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &pr : c->ev_decode) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto &pr : c->ev_total) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -697,6 +770,7 @@ int msg_pull_kept(msg_ctx *c, uint32_t *idx, size_t cap, size_t *n_kept)
     CU(cudaSetDevice(c->cfg.device));
     if (n_kept) *n_kept = c->n_kept;
     if (!idx) return MSG_OK;
+    if (c->cfg.do_filter && !c->cfg.want_kept) return fail(c, MSG_ESTATE, "context was created without want_kept");
     if (cap < c->n_kept) return fail(c, MSG_ERANGE, "kept buffer too small (%zu < %llu)", cap, (unsigned long long)c->n_kept);
     if (c->have_stream) {
         CU(cudaMemcpyAsync(idx, c->out_idx.p, c->n_kept * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -795,13 +869,46 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
             CU(cudaStreamSynchronize(c->stream));
         }
         const uint32_t nb = nblocks(F, 256);
-        for (int k = 1; k < 20; k++) {                                                            // msam_profile.c:331
+        bool looped = false;
+        if (g.n_ranks <= 1 && F > 0 && !getenv("MSG_EM_HOST_LOOP")) {
+            // single GPU: the whole loop is one cooperative launch (grid-wide barriers, no host round trips)
+            const bool sm = F <= EM_SMEM_F;
+            const size_t shm = sm ? (size_t)F * 16 : 0;
+            int per_sm = 0, nsm = 0;
+            CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, g.device));
+            if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<true>, 256, shm));
+            else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<false>, 256, shm));
+            if (per_sm > 4) per_sm = 4;
+            if (per_sm >= 1) {
+                uint32_t grid = (uint32_t)(nsm * per_sm);
+                CU(c->tile_sums.reserve((size_t)grid * 8 + 16));
+                double *partial = c->tile_sums.as<double>();
+                int32_t *d_res = reinterpret_cast<int32_t *>(c->d_total);
+                const uint32_t *a0 = c->csr_off.as<uint32_t>(), *a1 = c->csr_len.as<uint32_t>(); const int32_t *a2 = c->csr_fid.as<int32_t>();
+                uint32_t nl_arg = nl32, F_arg = F;
+                const double *U = c->d_U; double *av = c->d_a, *inc = c->d_inc, *dout = c->d_delta;
+                void *args[] = {&a0, &a1, &a2, &nl_arg, &U, &av, &inc, &partial, &F_arg, &dout, &d_res};
+                CU(cudaMemsetAsync(c->d_inc, 0, (size_t)F * 8, c->stream));
+                CU(cudaMemsetAsync(c->d_delta, 0, 8 * 20, c->stream));
+                if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<true>, dim3(grid), dim3(256), args, shm, c->stream));
+                else    CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
+                LAUNCHED(c);
+                int32_t res[2];
+                CU(cudaMemcpyAsync(res, d_res, 8, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaMemcpyAsync(s.em_delta, c->d_delta, 8 * 20, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                c->d2h_bytes += 168;
+                s.em_iterations = res[0]; s.em_converged = res[1];
+                looped = true;
+            }
+        }
+        for (int k = 1; !looped && k < 20; k++) {                                                            // msam_profile.c:331
             CU(cudaMemsetAsync(c->d_inc, 0, (size_t)F * 8, c->stream));
             if (nl32) {
                 if (F <= EM_SMEM_F) {
-                    em_gather_smem_kernel<<<em_grid, 256, (size_t)F * 16, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_inc, F);
+                    em_gather_smem_kernel<<<em_grid, 256, (size_t)F * 16, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_len.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_inc, F);
                 } else {
-                    em_gather_kernel<<<em_grid, 256, 0, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_inc);
+                    em_gather_kernel<<<em_grid, 256, 0, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_len.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_inc);
                 }
                 LAUNCHED(c);
             }
@@ -818,7 +925,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
             if (delta < 1e-10) { s.em_converged = 1; break; }                                     // :383
         }
         CU(cudaMemsetAsync(c->d_purged, 0, 4, c->stream));
-        if (nl32) { em_purged_kernel<<<em_grid, 256, 0, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_purged); LAUNCHED(c); }
+        if (nl32) { em_purged_kernel<<<em_grid, 256, 0, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_len.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_purged); LAUNCHED(c); }
         if ((rc = allreduce(c, c->d_purged, 1, ncclUint32, ncclSum))) return rc;
         CU(cudaMemcpyAsync(&s.purged_insert_count, c->d_purged, 4, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -888,8 +995,10 @@ int msg_get_timing(msg_ctx *c, msg_timing *t, int reset)
     t->decode_ms = c->decode_ms; t->decode_launches = c->decode_launches; t->total_ms = c->total_ms;
     t->kernel_launches = c->kernel_launches; t->h2d_bytes = c->h2d_bytes; t->d2h_bytes = c->d2h_bytes;
     t->alg_bytes = acct[0]; t->slow_records = acct[1];
+    t->fused_chunks = c->fused_chunks; t->fused_fallbacks = c->fused_fallbacks;
     if (reset) {
         c->decode_ms = c->total_ms = 0; c->decode_launches = c->kernel_launches = 0; c->h2d_bytes = c->d2h_bytes = 0;
+        c->fused_chunks = c->fused_fallbacks = 0;
         CU(cudaMemset(c->d_acct, 0, 16));
     }
     return MSG_OK;

@@ -17,6 +17,7 @@
 // lists into a CSR that the EM kernels iterate.
 #pragma once
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace msg {
 
@@ -160,13 +161,16 @@ __global__ void __launch_bounds__(256) profile_walk_count_kernel(const ProfParam
         const uint32_t pc = count_group_walk(p, j, stream_at(p, j), ins, uq, mu);
         if (p.pcount) p.pcount[j] = pc;
     }
-    if (ins) atomicAdd(p.counters + 0, ins);
-    if (uq)  atomicAdd(p.counters + 1, uq);
-    if (mu)  atomicAdd(p.counters + 2, mu);
+    ins = __reduce_add_sync(0xffffffffu, ins); uq = __reduce_add_sync(0xffffffffu, uq); mu = __reduce_add_sync(0xffffffffu, mu);
+    if ((threadIdx.x & 31u) == 0) {      // one set of atomics per warp, not per thread
+        if (ins) atomicAdd(p.counters + 0, ins);
+        if (uq)  atomicAdd(p.counters + 1, uq);
+        if (mu)  atomicAdd(p.counters + 2, mu);
+    }
 }
 
 // proportional: worklist heads with pcount>0 write their list; scanv[j] = (lists before << 32) | entries before
-__global__ void __launch_bounds__(256) profile_walk_fill_kernel(const ProfParams p, const unsigned long long *scanv, uint32_t *mm_off, int32_t *mm_fid,
+__global__ void __launch_bounds__(256) profile_walk_fill_kernel(const ProfParams p, const unsigned long long *scanv, uint32_t *mm_off, uint32_t *mm_len, int32_t *mm_fid,
                                                                 uint32_t list_base, uint32_t ent_base, const uint32_t *worklist, const uint32_t *wl_count)
 {
     const uint32_t nw = *wl_count;
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(256) profile_walk_fill_kernel(const ProfParams
         if (p.pcount[j] == 0) continue;
         const unsigned long long sv = scanv[j];
         const uint32_t li = list_base + (uint32_t)(sv >> 32), eo = ent_base + (uint32_t)sv;
-        mm_off[li] = eo;
+        mm_off[li] = eo; mm_len[li] = p.pcount[j];
         uint32_t size;
         walk_group(p, j, stream_at(p, j), &size, ActStore{mm_fid + eo}, p.big_threshold);
     }
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(256) profile_warp_count_kernel(const ProfParam
 // proportional: first-appearance lanes of in-window multi groups write their feature at
 // (list offset of the head) + (rank among the group's first appearances)
 __global__ void __launch_bounds__(256) profile_warp_fill_kernel(const ProfParams p, const uint8_t *gmeta, const unsigned long long *scanv,
-                                                                uint32_t *mm_off, int32_t *mm_fid, uint32_t list_base, uint32_t ent_base)
+                                                                uint32_t *mm_off, uint32_t *mm_len, int32_t *mm_fid, uint32_t list_base, uint32_t ent_base)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t w0 = j & ~31ull;
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(256) profile_warp_fill_kernel(const ProfParams
     sv = __shfl_sync(0xffffffffu, sv, (int)gs);
     if (member && le && hpc) {
         const uint32_t li = list_base + (uint32_t)(sv >> 32), eo = ent_base + (uint32_t)sv;
-        if (head) mm_off[li] = eo;
+        if (head) { mm_off[li] = eo; mm_len[li] = hpc; }
         if (first) {
             const uint32_t rank = __popc(fmask & span & ((1u << lane) - 1u));
             mm_fid[eo + rank] = feature_of(p, p.tid[stream_at(p, j)]);
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(256) profile_warp_fill_kernel(const ProfParams
 // ub_target_hit stamp algorithm (msam_profile.c:131-145) with a u32 stamp per feature.
 // Lists for proportional mode are appended to big_fid / big_off.
 __global__ void profile_big_kernel(const ProfParams p, uint32_t nbig, uint32_t *stamp, uint32_t stamp_base,
-                                   uint32_t *big_off, int32_t *big_fid, uint32_t *big_tot /*[0]=lists,[1]=entries*/, int fill,
+                                   uint32_t *big_off, uint32_t *big_len, int32_t *big_fid, uint32_t *big_tot /*[0]=lists,[1]=entries*/, int fill,
                                    uint32_t list_base, uint32_t ent_base)
 {
     if (blockIdx.x || threadIdx.x) return;
@@ -393,11 +397,10 @@ __global__ void profile_big_kernel(const ProfParams p, uint32_t nbig, uint32_t *
             if (p.share_type == 3 && nd > 1) nl++;
         } else {
             if (nd == 1 || p.share_type != 3) ne = e0;
-            else { big_off[nl] = e0; nl++; }
+            else { big_off[nl] = e0; big_len[nl] = ne - e0; nl++; }
         }
     }
     if (!fill) { big_tot[0] = nl; big_tot[1] = ne; }
-    else if (p.share_type == 3) big_off[nl] = ne;
 }
 
 // ---------------------------------------------------------------- abundance / EM (msam_profile.c:284-404)
@@ -418,11 +421,11 @@ __global__ void em_init_from_U_kernel(const double *U, double *a, uint32_t n)
 // one thread per multi-mapper list: s = sum a[f] in list order; inc[f] += a[f]/s   (:341-365)
 // Large catalogs (F up to 1e6): the F-sized vectors live in L2, contention per address is low,
 // so the adds go straight to global memory.
-__global__ void __launch_bounds__(256) em_gather_kernel(const uint32_t *mm_off, const int32_t *mm_fid, uint32_t nlists,
+__global__ void __launch_bounds__(256) em_gather_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
                                                         const double *a, double *inc)
 {
     for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < nlists; l += gridDim.x * blockDim.x) {
-        uint32_t b = mm_off[l], e = mm_off[l + 1];
+        uint32_t b = mm_off[l], e = b + mm_len[l];
         double s = 0;
         for (uint32_t k = b; k < e; k++) s += a[mm_fid[k]];
         if (s > 0) for (uint32_t k = b; k < e; k++) { int32_t f = mm_fid[k]; atomicAdd(inc + f, a[f] / s); }
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(256) em_gather_kernel(const uint32_t *mm_off, 
 // Small feature sets (genomes, F <= EM_SMEM_F): millions of lists hit a few hundred addresses.
 // Each CTA keeps a private copy of a[] and inc[] in shared memory and flushes inc once.
 constexpr uint32_t EM_SMEM_F = 2048;
-__global__ void __launch_bounds__(256) em_gather_smem_kernel(const uint32_t *mm_off, const int32_t *mm_fid, uint32_t nlists,
+__global__ void __launch_bounds__(256) em_gather_smem_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
                                                              const double *a, double *inc, uint32_t F)
 {
     extern __shared__ double s_em[];
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(256) em_gather_smem_kernel(const uint32_t *mm_
     for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { sa[i] = a[i]; si[i] = 0.0; }
     __syncthreads();
     for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < nlists; l += gridDim.x * blockDim.x) {
-        uint32_t b = mm_off[l], e = mm_off[l + 1];
+        uint32_t b = mm_off[l], e = b + mm_len[l];
         double s = 0;
         for (uint32_t k = b; k < e; k++) s += sa[mm_fid[k]];
         if (s > 0) for (uint32_t k = b; k < e; k++) { int32_t f = mm_fid[k]; atomicAdd(si + f, sa[f] / s); }
@@ -476,14 +479,77 @@ __global__ void __launch_bounds__(256) em_delta_kernel(const double *partial, ui
     for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
     if (threadIdx.x == 0) *delta_out = s[0] / n;                        // :380
 }
+// The whole PropSharing loop (msam_profile.c:331-389) in ONE cooperative launch (single-GPU case): grid-wide
+// barriers replace the per-iteration launches and the host's read of delta.  Every CTA recomputes delta from the
+// per-CTA partials in the same fixed order, so all of them take the same stop decision.  result[0] = last k,
+// result[1] = converged flag; delta_out[k-1] = DELTA^2 of iteration k.
+template <bool SMEM>
+__global__ void __launch_bounds__(256) em_loop_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
+                                                      const double *U, double *a, double *inc, double *partial, uint32_t F,
+                                                      double *delta_out, int32_t *result)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double s_em[];
+    __shared__ double s_red[256];
+    double *sa = s_em, *si = s_em + F;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    int k = 1, conv = 0;
+    for (; k < 20; k++) {
+        // gather: s = sum a[f] in list order; inc[f] += a[f]/s            (:341-365)
+        if (SMEM) {
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { sa[i] = a[i]; si[i] = 0.0; }
+            __syncthreads();
+        }
+        const double *av = SMEM ? sa : a;
+        double *iv = SMEM ? si : inc;
+        for (uint32_t l = gtid; l < nlists; l += gsz) {
+            const uint32_t b = mm_off[l], e = b + mm_len[l];
+            double sum = 0;
+            for (uint32_t q = b; q < e; q++) sum += av[mm_fid[q]];
+            if (sum > 0) for (uint32_t q = b; q < e; q++) { const int32_t f = mm_fid[q]; atomicAdd(iv + f, av[f] / sum); }
+        }
+        if (SMEM) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { const double v = si[i]; if (v != 0.0) atomicAdd(inc + i, v); }
+        }
+        grid.sync();
+        // update: a = U + inc, flush < 1e-20, per-CTA partial of sum diff^2; inc is cleared for the next iteration   (:369-379)
+        double dd = 0;
+        for (uint32_t i = gtid; i < F; i += gsz) {
+            double an = U[i] + inc[i];
+            if (an < 1e-20) an = 0;
+            const double diff = an - a[i];
+            dd += diff * diff;
+            a[i] = an; inc[i] = 0.0;
+        }
+        s_red[threadIdx.x] = dd;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+        if (threadIdx.x == 0) partial[blockIdx.x] = s_red[0];
+        grid.sync();
+        // delta (every CTA, same order)                                   (:380-383)
+        double acc = 0;
+        for (uint32_t b = threadIdx.x; b < gridDim.x; b += 256) acc += partial[b];
+        s_red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+        const double delta = s_red[0] / F;
+        __syncthreads();
+        if (gtid == 0) delta_out[k - 1] = delta;
+        if (delta < 1e-10) { conv = 1; break; }
+    }
+    if (gtid == 0) { result[0] = k < 20 ? k : 19; result[1] = conv; }
+}
+
 // purged = #lists whose final abundances sum to exactly 0  (:394-404)
-__global__ void __launch_bounds__(256) em_purged_kernel(const uint32_t *mm_off, const int32_t *mm_fid, uint32_t nlists,
+__global__ void __launch_bounds__(256) em_purged_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
                                                         const double *a, uint32_t *purged)
 {
     uint32_t z = 0;
     for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < nlists; l += gridDim.x * blockDim.x) {
         double s = 0;
-        for (uint32_t k = mm_off[l]; k < mm_off[l + 1]; k++) s += a[mm_fid[k]];
+        for (uint32_t k = mm_off[l]; k < mm_off[l] + mm_len[l]; k++) s += a[mm_fid[k]];
         z += (s == 0);
     }
     z = warp_sum_u32(z);

@@ -53,12 +53,12 @@ def test_golden_filter(m, c, force_slow):
         assert ((st["flags"] & 2) != 0).tolist() == has_as.tolist()
 
 
-@pytest.mark.parametrize("force_slow", [False, True], ids=["staged", "slowpath"])
+@pytest.mark.parametrize("force_slow,kept", [(False, True), (True, True), (False, False)], ids=["staged", "slowpath", "fused"])
 @pytest.mark.parametrize("c", G.cases("profile"), ids=G.case_id)
-def test_golden_profile(m, c, force_slow):
+def test_golden_profile(m, c, force_slow, kept):
     s = G.fixture(c["fixture"])
     pre = c["pre"] or {}
-    with m.Context(profile=True, multi=c["mode"], n_targets=len(s.ref_names), force_slow=force_slow, **pre) as ctx:
+    with m.Context(profile=True, multi=c["mode"], kept=kept, n_targets=len(s.ref_names), force_slow=force_slow, **pre) as ctx:
         ctx.push(s.raw, s.off)
         ui, d = ctx.pull_counts()
         ab, st = ctx.finish_profile()
@@ -143,6 +143,51 @@ def test_synth_profile(m, oracle, mixed, mode, pre):
     assert np.array_equal(ui, eui)
     assert close(d, ed) and close(ab, eab)
     assert est["multi"] > 0 and est["uniq"] > 0
+
+
+FUSED_PRE = [dict(l=80, p=95, z=80, besthit=True), dict(besthit=True), dict(uniqhit=True), dict(p=97, uniqhit=True),
+             dict(l=100, rescore=True, besthit=True)]
+
+
+@pytest.mark.parametrize("mode", ["all", "equal", "proportional", "ignore"])
+@pytest.mark.parametrize("pre", FUSED_PRE, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
+def test_synth_profile_fused(m, oracle, mixed, mode, pre):
+    """kept=False: best-hit + profile run as the fused single pass (fused.cuh); same results as the oracle."""
+    raw, off, tlen, p = mixed
+    idx = oracle.filter_stream(raw, off, oracle.filter_cfg(**pre))
+    eab, est, eui, ed = oracle.profile(raw, off, idx, len(tlen), SHARE[mode])
+    with m.Context(profile=True, multi=mode, kept=False, n_targets=len(tlen), **pre) as ctx:
+        ctx.push(raw, off)
+        assert ctx.kept_count() == len(idx)
+        ui, d = ctx.pull_counts()
+        ab, st = ctx.finish_profile()
+        t = ctx.timing()
+    assert t["fused_chunks"] == 1 and t["fused_fallbacks"] == 0
+    for k in ("mapped_inserts", "uniq", "multi", "purged", "iterations", "converged", "n_lists", "n_entries"):
+        assert st[k] == est[k], k
+    assert np.array_equal(ui, eui)
+    assert close(d, ed) and close(ab, eab)
+
+
+def test_fused_chunked_and_genome_map(m, oracle, mixed):
+    raw, off, tlen, p = mixed
+    n = len(off) - 1
+    opts = dict(l=80, p=95, z=80, besthit=True)
+    fmap = (np.arange(len(tlen)) % 7).astype(np.int32)
+    eidx = oracle.filter_stream(raw, off, oracle.filter_cfg(**opts))
+    eab, est, eui, _ = oracle.profile(raw, off, eidx, len(tlen), 3, fmap=fmap, n_features=7)
+    cuts = [0, m.split_point(raw, off, n // 4), m.split_point(raw, off, n // 2), n]
+    with m.Context(profile=True, multi="proportional", kept=False, n_targets=len(tlen), n_features=7, fmap=fmap, **opts) as ctx:
+        kept = 0
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            ctx.push(raw[int(off[a]):int(off[b])], off[a:b + 1] - off[a])
+            kept += ctx.kept_count()
+        ab, st = ctx.finish_profile()
+        ui, _ = ctx.pull_counts()
+        assert ctx.timing()["fused_chunks"] == 3
+    assert kept == len(eidx) and np.array_equal(ui, eui) and close(ab, eab)
+    assert (st["mapped_inserts"], st["uniq"], st["multi"], st["purged"], st["n_lists"], st["n_entries"]) == \
+           (est["mapped_inserts"], est["uniq"], est["multi"], est["purged"], est["n_lists"], est["n_entries"])
 
 
 def test_synth_profile_genome_map(m, oracle, mixed):
@@ -290,6 +335,42 @@ def test_reopened_qname_and_unmapped_between(m, oracle):
             ab, st = ctx.finish_profile()
         assert ui.tolist() == eui.tolist() and close(ab, eab) and close(d, ed)
         assert (st["mapped_inserts"], st["uniq"], st["multi"]) == (est["mapped_inserts"], est["uniq"], est["multi"])
+        # besthit | profile on the same non-grouped input: pools x(A) and x(B) are separate for the filter but the
+        # profile merges their winners into one group -> the fused pass must notice and fall back
+        idx = oracle.filter_stream(s.raw, s.off, oracle.filter_cfg(besthit=True))
+        eab, est, eui, ed = oracle.profile(s.raw, s.off, idx, 3, SHARE[mode])
+        with m.Context(profile=True, multi=mode, kept=False, besthit=True, n_targets=3) as ctx:
+            ctx.push(s.raw, s.off)
+            ui, d = ctx.pull_counts()
+            ab, st = ctx.finish_profile()
+            t = ctx.timing()
+        assert ui.tolist() == eui.tolist() and close(ab, eab) and close(d, ed)
+        assert (st["mapped_inserts"], st["uniq"], st["multi"]) == (est["mapped_inserts"], est["uniq"], est["multi"])
+        assert t["fused_chunks"] == 1
+
+
+def test_fused_guard_fallback(m, oracle):
+    # x(A) | y (dropped by -l) | x(B): two pools for the filter, ONE insert for the profile (msam_profile.c:226 compares
+    # with the previous surviving record).  The fused pass must detect the equal QNAME hashes and hand the chunk to the
+    # general pipeline; counts must match the oracle either way.
+    a = "\t0\t%s\t10\t60\t%dM\t*\t0\t0\t%s\t%s\tNM:i:0\tAS:i:%d"
+    rec = lambda n, ref, ln, sc: n + a % (ref, ln, "A" * ln, "I" * ln, sc)
+    text = HDR + "\n".join([rec("u", "C", 20, 9), rec("x", "A", 20, 10), rec("y", "A", 5, 5), rec("x", "B", 20, 20), rec("z", "C", 20, 7)]) + "\n"
+    s = _sam(text)
+    opts = dict(l=8, besthit=True)
+    idx = oracle.filter_stream(s.raw, s.off, oracle.filter_cfg(**opts))
+    assert s.name_flags(idx) == "u:0,x:0,x:0,z:0"
+    for mode in ("all", "equal", "proportional", "ignore"):
+        eab, est, eui, ed = oracle.profile(s.raw, s.off, idx, 3, SHARE[mode])
+        assert (est["mapped_inserts"], est["multi"]) == (3, 1)
+        with m.Context(profile=True, multi=mode, kept=False, n_targets=3, **opts) as ctx:
+            ctx.push(s.raw, s.off)
+            ui, d = ctx.pull_counts()
+            ab, st = ctx.finish_profile()
+            t = ctx.timing()
+        assert (t["fused_chunks"], t["fused_fallbacks"]) == (1, 1)
+        assert ui.tolist() == eui.tolist() and close(ab, eab) and close(d, ed)
+        assert (st["mapped_inserts"], st["uniq"], st["multi"], st["purged"]) == (est["mapped_inserts"], est["uniq"], est["multi"], est["purged"])
 
 
 def test_huge_group(m, oracle):
@@ -311,6 +392,15 @@ def test_huge_group(m, oracle):
             ctx.push(s.raw, s.off)
             ui, d = ctx.pull_counts()
             ab, st = ctx.finish_profile()
+        assert ui.tolist() == eui.tolist() and close(d, ed) and close(ab, eab), mode
+        assert (st["mapped_inserts"], st["uniq"], st["multi"], st["purged"]) == (est["mapped_inserts"], est["uniq"], est["multi"], est["purged"])
+        # a 5000-record pool is beyond the fused pass's walk limit -> general pipeline, same numbers
+        eab, est, eui, ed = oracle.profile(s.raw, s.off, exp, 40, SHARE[mode])
+        with m.Context(profile=True, multi=mode, kept=False, besthit=True, n_targets=40) as ctx:
+            ctx.push(s.raw, s.off)
+            ui, d = ctx.pull_counts()
+            ab, st = ctx.finish_profile()
+            assert ctx.timing()["fused_fallbacks"] == 1
         assert ui.tolist() == eui.tolist() and close(d, ed) and close(ab, eab), mode
         assert (st["mapped_inserts"], st["uniq"], st["multi"], st["purged"]) == (est["mapped_inserts"], est["uniq"], est["multi"], est["purged"])
 
