@@ -60,6 +60,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string &err) {
@@ -70,6 +71,7 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl is missing required symbols"; return false; }
@@ -125,6 +127,8 @@ struct msg_ctx {
 
     // multi-GPU
     ncclComm_t comm = nullptr;
+    // peer-memory exchange for the fused EM loop (profile.cuh em_loop_multi_kernel): CUDA IPC mappings of every rank's region
+    unsigned char *peer_region = nullptr; PeerTable peer_tab; std::vector<void *> ipc_opened; bool p2p_ok = false; uint32_t em_epoch = 0;
 
     // timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_decode, ev_total;
@@ -615,6 +619,34 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
         ncclUniqueId id; memcpy(&id, cfg->nccl_unique_id, 128);
         ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, g.n_ranks, id, g.rank);
         if (r != ncclSuccess) { int rc = fail(nullptr, MSG_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); msg_destroy(ctx); return rc; }
+        if (g.want_profile && g.n_ranks <= 16 && g_nccl.AllGather) {
+            // Map every rank's publish region into this process (CUDA IPC over NVLink).  If any rank cannot, all ranks
+            // agree (allreduce-min) to keep the NCCL-per-iteration loop instead.
+            const size_t region = 128 + 2 * F * 8;
+            int ok = 1;
+            cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof mine);
+            unsigned char *d_hs = nullptr; int *d_ok = nullptr;
+            std::vector<cudaIpcMemHandle_t> hs((size_t)g.n_ranks);
+            CUC(cudaMalloc(&ctx->peer_region, region)); CUC(cudaMemset(ctx->peer_region, 0, region));
+            CUC(cudaMalloc(&d_hs, sizeof(cudaIpcMemHandle_t) * (size_t)g.n_ranks)); CUC(cudaMalloc(&d_ok, 4));
+            if ((getenv("MSG_NO_P2P") && atoi(getenv("MSG_NO_P2P"))) || cudaIpcGetMemHandle(&mine, ctx->peer_region) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            CUC(cudaMemcpy(d_hs + sizeof mine * (size_t)g.rank, &mine, sizeof mine, cudaMemcpyHostToDevice));
+            if (g_nccl.AllGather(d_hs + sizeof mine * (size_t)g.rank, d_hs, sizeof mine, ncclUint8, ctx->comm, ctx->stream) != ncclSuccess) ok = 0;
+            CUC(cudaStreamSynchronize(ctx->stream));
+            CUC(cudaMemcpy(hs.data(), d_hs, sizeof mine * (size_t)g.n_ranks, cudaMemcpyDeviceToHost));
+            for (int pr = 0; pr < g.n_ranks && ok; pr++) {
+                if (pr == g.rank) { ctx->peer_tab.base[pr] = ctx->peer_region; continue; }
+                void *pp = nullptr;
+                if (cudaIpcOpenMemHandle(&pp, hs[(size_t)pr], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+                ctx->ipc_opened.push_back(pp); ctx->peer_tab.base[pr] = (const unsigned char *)pp;
+            }
+            CUC(cudaMemcpy(d_ok, &ok, 4, cudaMemcpyHostToDevice));
+            if (g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream) != ncclSuccess) ok = 0;
+            CUC(cudaStreamSynchronize(ctx->stream));
+            int all_ok = 0; CUC(cudaMemcpy(&all_ok, d_ok, 4, cudaMemcpyDeviceToHost));
+            ctx->p2p_ok = ok && all_ok;
+            cudaFree(d_hs); cudaFree(d_ok);
+        }
     }
 #undef CUC
     int rc = msg_reset(ctx);
@@ -628,6 +660,8 @@ void msg_destroy(msg_ctx *c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void *pp : c->ipc_opened) cudaIpcCloseMemHandle(pp);
+    if (c->peer_region) cudaFree(c->peer_region);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     DevBuf *bufs[] = {&c->raw, &c->off, &c->tid, &c->fb, &c->score, &c->hash, &c->nid, &c->st_alen, &c->st_qlen, &c->st_qclip, &c->st_edit,
                       &c->kbase, &c->worklist, &c->gmeta, &c->out_idx, &c->tile_sums, &c->pcount, &c->scanv, &c->biglist, &c->out_len, &c->out_off, &c->plan, &c->out_rec,
@@ -840,44 +874,48 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
     int rc;
     // work on copies so that finish can be called again after more chunks
     uint32_t *ui = c->d_ui; double *dd = c->d_d; uint32_t *cnt = c->d_counters;
-    DevBuf &t_ui = c->t_ui, &t_d = c->t_d, &t_cnt = c->t_cnt;
+    DevBuf &t_ui = c->t_ui, &t_d = c->t_d;
+    unsigned long long nl_global = c->csr_lists;
+    uint32_t hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (g.n_ranks > 1) {
-        CU(t_ui.reserve((size_t)(F ? F : 1) * 4)); CU(t_d.reserve((size_t)(F ? F : 1) * 8)); CU(t_cnt.reserve(32));
-        CU(cudaMemcpyAsync(t_ui.p, c->d_ui, (size_t)F * 4, cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemcpyAsync(t_d.p, c->d_d, (size_t)F * 8, cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemcpyAsync(t_cnt.p, c->d_counters, 32, cudaMemcpyDeviceToDevice, c->stream));
-        ui = t_ui.as<uint32_t>(); dd = t_d.as<double>(); cnt = t_cnt.as<uint32_t>();
-        // the one allreduce of per-reference counts over NVLink (+ the scalar counters)
-        if ((rc = allreduce(c, ui, F, ncclUint32, ncclSum))) return rc;
-        if (g.share_type == MSG_MULTI_EQUAL && (rc = allreduce(c, dd, F, ncclFloat64, ncclSum))) return rc;
-        if ((rc = allreduce(c, cnt, 4, ncclUint32, ncclSum))) return rc;
-    }
-    uint32_t hc[4];
-    CU(cudaMemcpyAsync(hc, cnt, 16, cudaMemcpyDeviceToHost, c->stream));
+        // ONE allreduce over NVLink for everything that is additive across ranks: per-reference counts,
+        // the insert counters and the number of multi-mapper lists, packed as u32[F + 8]
+        CU(t_ui.reserve(((size_t)F + 8) * 4));
+        ui = t_ui.as<uint32_t>(); cnt = ui + F;
+        CU(cudaMemcpyAsync(ui, c->d_ui, (size_t)F * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(cnt, c->d_counters, 16, cudaMemcpyDeviceToDevice, c->stream));
+        const uint32_t nl_lo[2] = {(uint32_t)(c->csr_lists & 0xffffu), (uint32_t)(c->csr_lists >> 16)};   // two 16-bit halves: sums stay exact in u32 for up to 65536 ranks
+        CU(cudaMemcpyAsync(cnt + 4, nl_lo, 8, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = allreduce(c, ui, (size_t)F + 6, ncclUint32, ncclSum))) return rc;
+        if (g.share_type == MSG_MULTI_EQUAL) {
+            CU(t_d.reserve((size_t)(F ? F : 1) * 8));
+            CU(cudaMemcpyAsync(t_d.p, c->d_d, (size_t)F * 8, cudaMemcpyDeviceToDevice, c->stream));
+            dd = t_d.as<double>();
+            if ((rc = allreduce(c, dd, F, ncclFloat64, ncclSum))) return rc;
+        }
+        CU(cudaMemcpyAsync(hc, cnt, 24, cudaMemcpyDeviceToHost, c->stream));
+    } else CU(cudaMemcpyAsync(hc, cnt, 16, cudaMemcpyDeviceToHost, c->stream));
     if (F) { em_init_kernel<<<nblocks(F, 256), 256, 0, c->stream>>>(ui, dd, g.share_type == MSG_MULTI_EQUAL, c->d_U, c->d_a, F); LAUNCHED(c); }
-    uint64_t nl_local = 0, ne_local = 0;
-    nl_local = c->csr_lists; ne_local = c->csr_ent;
+    const uint64_t ne_local = c->csr_ent;
     const uint32_t nl32 = (uint32_t)c->csr_lists;
     const uint32_t em_grid = nl32 ? (nblocks(nl32, 256) < 148u * 8u ? nblocks(nl32, 256) : 148u * 8u) : 0;
-    unsigned long long nl_global = nl_local;
+    bool purged_done = false;
     if (g.share_type == MSG_MULTI_PROPORTIONAL) {
-        if (g.n_ranks > 1) {
-            unsigned long long *d_nl = reinterpret_cast<unsigned long long *>(c->d_total);
-            CU(cudaMemcpyAsync(d_nl, &nl_global, 8, cudaMemcpyHostToDevice, c->stream));
-            if ((rc = allreduce(c, d_nl, 1, ncclUint64, ncclSum))) return rc;
-            CU(cudaMemcpyAsync(&nl_global, d_nl, 8, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-        }
         const uint32_t nb = nblocks(F, 256);
         bool looped = false;
-        if (g.n_ranks <= 1 && F > 0 && !getenv("MSG_EM_HOST_LOOP")) {
+        if ((g.n_ranks <= 1 || c->p2p_ok) && F > 0 && !getenv("MSG_EM_HOST_LOOP")) {
             // single GPU: the whole loop is one cooperative launch (grid-wide barriers, no host round trips)
             const bool sm = F <= EM_SMEM_F;
             const size_t shm = sm ? (size_t)F * 16 : 0;
             int per_sm = 0, nsm = 0;
             CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, g.device));
-            if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<true>, 256, shm));
-            else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<false>, 256, shm));
+            if (g.n_ranks > 1) {
+                if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_multi_kernel<true>, 256, shm));
+                else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_multi_kernel<false>, 256, shm));
+            } else {
+                if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<true>, 256, shm));
+                else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<false>, 256, shm));
+            }
             if (per_sm > 4) per_sm = 4;
             if (per_sm >= 1) {
                 uint32_t grid = (uint32_t)(nsm * per_sm);
@@ -887,18 +925,30 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 const uint32_t *a0 = c->csr_off.as<uint32_t>(), *a1 = c->csr_len.as<uint32_t>(); const int32_t *a2 = c->csr_fid.as<int32_t>();
                 uint32_t nl_arg = nl32, F_arg = F;
                 const double *U = c->d_U; double *av = c->d_a, *inc = c->d_inc, *dout = c->d_delta;
-                void *args[] = {&a0, &a1, &a2, &nl_arg, &U, &av, &inc, &partial, &F_arg, &dout, &d_res};
+                PeerTable pt = c->peer_tab; int nr = g.n_ranks, rk = g.rank; uint32_t epoch = c->em_epoch;
+                void *args[] = {&a0, &a1, &a2, &nl_arg, &U, &av, &inc, &partial, &F_arg, &dout, &d_res, &pt, &nr, &rk, &epoch};
                 CU(cudaMemsetAsync(c->d_inc, 0, (size_t)F * 8, c->stream));
                 CU(cudaMemsetAsync(c->d_delta, 0, 8 * 20, c->stream));
-                if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<true>, dim3(grid), dim3(256), args, shm, c->stream));
-                else    CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
+                CU(cudaMemsetAsync(d_res, 0, 16, c->stream));
+                if (g.n_ranks > 1) {
+                    // compute + collective in one kernel: increments are exchanged through peer memory inside the loop
+                    CU(cudaMemsetAsync(c->peer_region + 64, 0, 4, c->stream));
+                    if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<true>, dim3(grid), dim3(256), args, shm, c->stream));
+                    else    CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
+                    c->em_epoch += 32;
+                } else {
+                    if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<true>, dim3(grid), dim3(256), args, shm, c->stream));
+                    else    CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
+                }
                 LAUNCHED(c);
-                int32_t res[2];
-                CU(cudaMemcpyAsync(res, d_res, 8, cudaMemcpyDeviceToHost, c->stream));
+                int32_t res[4];
+                CU(cudaMemcpyAsync(res, d_res, 16, cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaMemcpyAsync(s.em_delta, c->d_delta, 8 * 20, cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
                 c->d2h_bytes += 168;
+                if (g.n_ranks > 1 && res[2]) return fail(c, MSG_ENCCL, "timed out waiting for a peer GPU inside the PropSharing loop");
                 s.em_iterations = res[0]; s.em_converged = res[1];
+                if (g.n_ranks > 1) { s.purged_insert_count = (uint32_t)res[3]; purged_done = true; }
                 looped = true;
             }
         }
@@ -924,14 +974,17 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
             s.em_delta[k - 1] = delta; s.em_iterations = k;
             if (delta < 1e-10) { s.em_converged = 1; break; }                                     // :383
         }
+        if (!purged_done) {
         CU(cudaMemsetAsync(c->d_purged, 0, 4, c->stream));
         if (nl32) { em_purged_kernel<<<em_grid, 256, 0, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_len.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_purged); LAUNCHED(c); }
         if ((rc = allreduce(c, c->d_purged, 1, ncclUint32, ncclSum))) return rc;
         CU(cudaMemcpyAsync(&s.purged_insert_count, c->d_purged, 4, cudaMemcpyDeviceToHost, c->stream));
+        }
     }
     if (abundance && F) CU(cudaMemcpyAsync(abundance, c->d_a, (size_t)F * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += (size_t)F * 8 + 20;
+    if (g.n_ranks > 1) nl_global = (unsigned long long)hc[4] + ((unsigned long long)hc[5] << 16);
     s.mapped_inserts = hc[0]; s.uniq_mapper_count = hc[1]; s.multi_mapper_count = hc[2];
     s.multi_lists = nl_global; s.multi_entries = ne_local;
     if (st) *st = s;

@@ -542,6 +542,127 @@ __global__ void __launch_bounds__(256) em_loop_kernel(const uint32_t *mm_off, co
     if (gtid == 0) { result[0] = k < 20 ? k : 19; result[1] = conv; }
 }
 
+// Multi-GPU PropSharing loop: compute + collective in ONE cooperative kernel per GPU.  Every rank gathers its own
+// lists into `inc`, publishes the vector in a peer-visible buffer (CUDA IPC mapping, NVLink/NVSwitch loads), raises its
+// flag, waits for the other ranks' flags, and then every rank adds the N published vectors in rank order -- the same
+// order everywhere, so abundances, delta and the stop decision are bit-identical on all ranks without any NCCL call or
+// host round trip inside the loop.  Publish buffers alternate by iteration parity: a rank can only overwrite buffer
+// k%2 at iteration k+2, i.e. after every peer has published k+1, which it does only after it finished reading k.
+struct PeerTable { const unsigned char *base[16]; };      // region of rank r: [flag u32 | pad to 128 B | pub0 f64[F] | pub1 f64[F]]
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
+                                                            const double *U, double *a, double *inc, double *partial, uint32_t F,
+                                                            double *delta_out, int32_t *result,
+                                                            PeerTable peers, int n_ranks, int rank, uint32_t epoch)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double s_em[];
+    __shared__ double s_red[256];
+    double *sa = s_em, *si = s_em + F;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    unsigned char *mine = const_cast<unsigned char *>(peers.base[rank]);
+    int k = 1, conv = 0, timeout = 0;
+    for (; k < 20; k++) {
+        if (SMEM) {
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { sa[i] = a[i]; si[i] = 0.0; }
+            __syncthreads();
+        }
+        const double *av = SMEM ? sa : a;
+        double *iv = SMEM ? si : inc;
+        for (uint32_t l = gtid; l < nlists; l += gsz) {
+            const uint32_t b = mm_off[l], e = b + mm_len[l];
+            double sum = 0;
+            for (uint32_t q = b; q < e; q++) sum += av[mm_fid[q]];
+            if (sum > 0) for (uint32_t q = b; q < e; q++) { const int32_t f = mm_fid[q]; atomicAdd(iv + f, av[f] / sum); }
+        }
+        if (SMEM) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { const double v = si[i]; if (v != 0.0) atomicAdd(inc + i, v); }
+        }
+        grid.sync();
+        // publish my increments, then tell the peers
+        double *pub = reinterpret_cast<double *>(mine + 128) + (size_t)(k & 1) * F;
+        for (uint32_t i = gtid; i < F; i += gsz) { pub[i] = inc[i]; inc[i] = 0.0; }
+        __threadfence_system();
+        grid.sync();
+        if (gtid == 0) st_release_sys(reinterpret_cast<uint32_t *>(mine), epoch + (uint32_t)k);
+        if (blockIdx.x == 0 && threadIdx.x < (uint32_t)n_ranks) {
+            const uint32_t *pf = reinterpret_cast<const uint32_t *>(peers.base[threadIdx.x]);
+            unsigned long long spins = 0;
+            while ((int32_t)(ld_acquire_sys(pf) - (epoch + (uint32_t)k)) < 0) { if (++spins > (1ull << 28)) { timeout = 1; break; } __nanosleep(64); }
+            if (timeout) result[2] = 1;
+        }
+        grid.sync();
+        // a = U + sum over ranks (rank order) ; per-CTA partial of sum diff^2
+        double dd = 0;
+        for (uint32_t i = gtid; i < F; i += gsz) {
+            double tot = 0;
+            for (int r = 0; r < n_ranks; r++) tot += (reinterpret_cast<const double *>(peers.base[r] + 128) + (size_t)(k & 1) * F)[i];
+            double an = U[i] + tot;
+            if (an < 1e-20) an = 0;
+            const double diff = an - a[i];
+            dd += diff * diff;
+            a[i] = an;
+        }
+        s_red[threadIdx.x] = dd;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+        if (threadIdx.x == 0) partial[blockIdx.x] = s_red[0];
+        grid.sync();
+        double acc = 0;
+        for (uint32_t b = threadIdx.x; b < gridDim.x; b += 256) acc += partial[b];
+        s_red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+        const double delta = s_red[0] / F;
+        __syncthreads();
+        if (gtid == 0) delta_out[k - 1] = delta;
+        if (delta < 1e-10) { conv = 1; break; }
+    }
+    // purged = #lists whose final abundances sum to exactly 0 (:394-404), summed over ranks through the same regions
+    {
+        __shared__ uint32_t s_z;
+        if (threadIdx.x == 0) s_z = 0;
+        __syncthreads();
+        uint32_t z = 0;
+        for (uint32_t l = gtid; l < nlists; l += gsz) {
+            double sum = 0;
+            for (uint32_t q = mm_off[l]; q < mm_off[l] + mm_len[l]; q++) sum += a[mm_fid[q]];
+            z += (sum == 0);
+        }
+        z = __reduce_add_sync(0xffffffffu, z);
+        if ((threadIdx.x & 31u) == 0 && z) atomicAdd(&s_z, z);
+        __syncthreads();
+        uint32_t *mycount = reinterpret_cast<uint32_t *>(mine + 64);
+        if (threadIdx.x == 0 && s_z) atomicAdd(mycount, s_z);      // region word 16 was zeroed by the host before the launch
+        __threadfence_system();
+        grid.sync();
+        if (gtid == 0) st_release_sys(reinterpret_cast<uint32_t *>(mine), epoch + 24u);
+        if (gtid == 0) {
+            uint32_t tot = 0;
+            for (int r = 0; r < n_ranks; r++) {
+                const uint32_t *pf = reinterpret_cast<const uint32_t *>(peers.base[r]);
+                unsigned long long spins = 0;
+                while ((int32_t)(ld_acquire_sys(pf) - (epoch + 24u)) < 0) { if (++spins > (1ull << 28)) { result[2] = 1; break; } __nanosleep(64); }
+                tot += ld_acquire_sys(pf + 16);
+            }
+            result[3] = (int32_t)tot;
+        }
+    }
+    if (gtid == 0) { result[0] = k < 20 ? k : 19; result[1] = conv; }
+}
+
 // purged = #lists whose final abundances sum to exactly 0  (:394-404)
 __global__ void __launch_bounds__(256) em_purged_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
                                                         const double *a, uint32_t *purged)
