@@ -35,29 +35,49 @@ __global__ void __launch_bounds__(256) coverage_stream_kernel(const uint8_t *raw
 // Each thread owns SPAN consecutive cells; target lookup by binary search on covbase.
 constexpr int COV_SPAN = 16;
 
+__device__ __forceinline__ void cov_flush(unsigned long long *touched, long long *sum, int32_t t, unsigned long long tc, long long sm)
+{
+    // consecutive threads cover consecutive cells, so a warp usually sits inside ONE target: combine the 32 partial
+    // results first and issue one pair of atomics per warp instead of per thread (a few hundred targets would otherwise
+    // serialise tens of millions of same-address atomics).  Called by all 32 lanes (t = -1: nothing to add).
+    const int32_t t0 = __shfl_sync(0xffffffffu, t, 0);
+    if (__all_sync(0xffffffffu, t == t0)) {
+        if (t0 < 0) return;
+        tc = warp_sum_u64(tc);
+        sm = (long long)warp_sum_u64((unsigned long long)sm);
+        if ((threadIdx.x & 31u) == 0 && (tc | (unsigned long long)sm)) {
+            atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm);
+        }
+    } else if (t >= 0 && (tc | (unsigned long long)sm)) {
+        atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm);
+    }
+}
+
 __global__ void __launch_bounds__(256) coverage_reduce_kernel(const int32_t *depth, uint64_t total_cells, const uint64_t *covbase,
                                                               const uint32_t *tlen, int32_t n_targets,
                                                               unsigned long long *touched, long long *sum)
 {
     const uint64_t start = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * COV_SPAN;
-    if (start >= total_cells) return;
-    const uint64_t stop = min(total_cells, start + COV_SPAN);
-    // largest t with covbase[t] <= start
-    int32_t lo = 0, hi = n_targets - 1;
-    while (lo < hi) { int32_t mid = (lo + hi + 1) >> 1; if (covbase[mid] <= start) lo = mid; else hi = mid - 1; }
-    int32_t t = lo;
-    uint64_t tend = covbase[t] + tlen[t];          // first cell that is NOT a position of t (the spill cell)
+    int32_t t = -1;
     unsigned long long tc = 0; long long sm = 0;
-    for (uint64_t x = start; x < stop; x++) {
-        while (x > tend) {                         // moved past t's spill cell
-            if (tc | (unsigned long long)sm) { atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm); }
-            tc = 0; sm = 0; t++; tend = covbase[t] + tlen[t];
+    if (start < total_cells) {
+        const uint64_t stop = min(total_cells, start + COV_SPAN);
+        // largest t with covbase[t] <= start
+        int32_t lo = 0, hi = n_targets - 1;
+        while (lo < hi) { int32_t mid = (lo + hi + 1) >> 1; if (covbase[mid] <= start) lo = mid; else hi = mid - 1; }
+        t = lo;
+        uint64_t tend = covbase[t] + tlen[t];          // first cell that is NOT a position of t (the spill cell)
+        for (uint64_t x = start; x < stop; x++) {
+            while (x > tend) {                         // moved past t's spill cell: rare (target boundary inside my span)
+                if (tc | (unsigned long long)sm) { atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm); }
+                tc = 0; sm = 0; t++; tend = covbase[t] + tlen[t];
+            }
+            if (x == tend) continue;                   // spill cell
+            int32_t v = depth[x];
+            tc += (v != 0); sm += v;
         }
-        if (x == tend) continue;                   // spill cell
-        int32_t v = depth[x];
-        tc += (v != 0); sm += v;
     }
-    if (tc | (unsigned long long)sm) { atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm); }
+    cov_flush(touched, sum, t, tc, sm);
 }
 
 struct InI32 { const int32_t *v; __device__ __forceinline__ int32_t operator()(uint64_t i) const { return v[i]; } };
