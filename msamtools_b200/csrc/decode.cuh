@@ -507,17 +507,21 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
         const uint32_t nchunks = (uint32_t)(p.nbytes_readable >> 4);
         const uint32_t sub = t % LPR, r0 = t / LPR;
         const bool head = sub < hc, go = sub < hc + tc;
+        // all LPR loads are issued before the first store so that every thread keeps LPR x 16 B in flight
+        uint4 v[LPR];
 #pragma unroll
         for (uint32_t it = 0; it < LPR; it++) {
             const uint32_t r = it * (DEC_R / LPR) + r0;
+            v[it] = make_uint4(0, 0, 0, 0);
             if (go && r < nrec) {
                 const uint32_t cidx = (head ? s_hb[r] : s_tb[r]) + sub;     // a tail window that starts before the buffer wraps to a huge index
-                if (cidx < nchunks) {
-                    const uint4 v = ldg_stream128(reinterpret_cast<const uint4 *>(p.raw) + cidx);
-                    uint32_t *d = s_slot + r * SLOT_WORDS + sub * 4;
-                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-                }
+                if (cidx < nchunks) v[it] = ldg_stream128(reinterpret_cast<const uint4 *>(p.raw) + cidx);
             }
+        }
+#pragma unroll
+        for (uint32_t it = 0; it < LPR; it++) {
+            const uint32_t r = it * (DEC_R / LPR) + r0;
+            if (go && r < nrec) { uint32_t *d = s_slot + r * SLOT_WORDS + sub * 4; d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w; }
         }
     }
     __syncthreads();
