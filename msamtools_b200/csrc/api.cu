@@ -906,7 +906,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
         if ((g.n_ranks <= 1 || c->p2p_ok) && F > 0 && !getenv("MSG_EM_HOST_LOOP")) {
             // single GPU: the whole loop is one cooperative launch (grid-wide barriers, no host round trips)
             const bool sm = F <= EM_SMEM_F;
-            const size_t shm = sm ? (size_t)F * 16 : 0;
+            const size_t shm = sm ? (size_t)F * 8 * (1 + em_copies(F)) : 0;
             int per_sm = 0, nsm = 0;
             CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, g.device));
             if (g.n_ranks > 1) {

@@ -434,6 +434,8 @@ __global__ void __launch_bounds__(256) em_gather_kernel(const uint32_t *mm_off, 
 // Small feature sets (genomes, F <= EM_SMEM_F): millions of lists hit a few hundred addresses.
 // Each CTA keeps a private copy of a[] and inc[] in shared memory and flushes inc once.
 constexpr uint32_t EM_SMEM_F = 2048;
+// private inc copies per CTA in the cooperative loop kernels: one per warp while that stays under ~40 KB
+__host__ __device__ __forceinline__ uint32_t em_copies(uint32_t F) { return F <= 512 ? 8u : 1u; }
 __global__ void __launch_bounds__(256) em_gather_smem_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
                                                              const double *a, double *inc, uint32_t F)
 {
@@ -492,17 +494,21 @@ __global__ void __launch_bounds__(256) em_loop_kernel(const uint32_t *mm_off, co
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double s_em[];
     __shared__ double s_red[256];
+    // shared layout: a[F] | inc copies [ncopy][F].  With few features every warp gets a private copy of inc, so the
+    // (CAS-loop) f64 shared atomics only collide inside a warp.
+    const uint32_t ncopy = SMEM ? em_copies(F) : 1u;
     double *sa = s_em, *si = s_em + F;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     int k = 1, conv = 0;
     for (; k < 20; k++) {
         // gather: s = sum a[f] in list order; inc[f] += a[f]/s            (:341-365)
         if (SMEM) {
-            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { sa[i] = a[i]; si[i] = 0.0; }
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) sa[i] = a[i];
+            for (uint32_t i = threadIdx.x; i < F * ncopy; i += blockDim.x) si[i] = 0.0;
             __syncthreads();
         }
         const double *av = SMEM ? sa : a;
-        double *iv = SMEM ? si : inc;
+        double *iv = SMEM ? si + (size_t)((threadIdx.x >> 5) % ncopy) * F : inc;
         for (uint32_t l = gtid; l < nlists; l += gsz) {
             const uint32_t b = mm_off[l], e = b + mm_len[l];
             double sum = 0;
@@ -511,7 +517,11 @@ __global__ void __launch_bounds__(256) em_loop_kernel(const uint32_t *mm_off, co
         }
         if (SMEM) {
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { const double v = si[i]; if (v != 0.0) atomicAdd(inc + i, v); }
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) {
+                double v = 0.0;
+                for (uint32_t cp = 0; cp < ncopy; cp++) v += si[(size_t)cp * F + i];
+                if (v != 0.0) atomicAdd(inc + i, v);
+            }
         }
         grid.sync();
         // update: a = U + inc, flush < 1e-20, per-CTA partial of sum diff^2; inc is cleared for the next iteration   (:369-379)
@@ -569,17 +579,19 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double s_em[];
     __shared__ double s_red[256];
+    const uint32_t ncopy = SMEM ? em_copies(F) : 1u;
     double *sa = s_em, *si = s_em + F;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     unsigned char *mine = const_cast<unsigned char *>(peers.base[rank]);
     int k = 1, conv = 0, timeout = 0;
     for (; k < 20; k++) {
         if (SMEM) {
-            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { sa[i] = a[i]; si[i] = 0.0; }
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) sa[i] = a[i];
+            for (uint32_t i = threadIdx.x; i < F * ncopy; i += blockDim.x) si[i] = 0.0;
             __syncthreads();
         }
         const double *av = SMEM ? sa : a;
-        double *iv = SMEM ? si : inc;
+        double *iv = SMEM ? si + (size_t)((threadIdx.x >> 5) % ncopy) * F : inc;
         for (uint32_t l = gtid; l < nlists; l += gsz) {
             const uint32_t b = mm_off[l], e = b + mm_len[l];
             double sum = 0;
@@ -588,7 +600,11 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
         }
         if (SMEM) {
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) { const double v = si[i]; if (v != 0.0) atomicAdd(inc + i, v); }
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) {
+                double v = 0.0;
+                for (uint32_t cp = 0; cp < ncopy; cp++) v += si[(size_t)cp * F + i];
+                if (v != 0.0) atomicAdd(inc + i, v);
+            }
         }
         grid.sync();
         // publish my increments, then tell the peers
