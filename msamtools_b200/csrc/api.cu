@@ -109,6 +109,8 @@ struct msg_ctx {
 
     // device scalars: err[2], scan totals, accounting
     uint32_t *d_err = nullptr;                 // [0] flags [1] first bad record
+    uint32_t *h_pin = nullptr;                 // 512 B of pinned host memory: small results land here with ONE stream sync
+    double *h_ab = nullptr;                    // pinned staging for the abundance vector (F doubles)
     unsigned long long *d_acct = nullptr;      // [0] alg bytes [1] slow records
     void *d_total = nullptr;                   // 16 bytes scratch for scan totals
 
@@ -191,12 +193,20 @@ int run_scan(msg_ctx *c, In in, Out out, uint64_t n, T *h_total)
     return MSG_OK;
 }
 
+int report_device_errors(msg_ctx *c, const uint32_t *h);
+static const int EM_CTAS_PER_SM = getenv("MSG_EM_CTAS") ? atoi(getenv("MSG_EM_CTAS")) : 4;
+
 int check_device_errors(msg_ctx *c)
 {
-    uint32_t h[2];
-    CU(cudaMemcpyAsync(h, c->d_err, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t *h = c->h_pin + 8;
+    CU(cudaMemcpyAsync(h, c->d_err, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->d2h_bytes += sizeof h;
+    c->d2h_bytes += 8;
+    return report_device_errors(c, h);
+}
+
+int report_device_errors(msg_ctx *c, const uint32_t *h)
+{
     if (h[0] & DERR_FORMAT) return fail(c, MSG_EFORMAT, "malformed BAM record or reference id out of range (first near record %u)", h[1]);
     if (h[0] & DERR_NOTAG)  return fail(c, MSG_ENOTAG, "Either NM or MD must be present in SAM/BAM input for 'filter' command. Type 'msamtools filter -h' for details.");
     if (h[0] & DERR_NOAS)   return fail(c, MSG_ENOAS, "Required field AS not found in SAM/BAM input. Type 'msamtools -h' for details.");
@@ -338,11 +348,14 @@ int fused_stage(msg_ctx *c, const DecodeParams &dp, uint64_t n, bool *done)
     LAUNCHED(c);
     fused_walk_kernel<<<std::min<uint32_t>(nblocks(nwin, 128), 148u * 8u), 128, 0, c->stream>>>(p); LAUNCHED(c);
     fused_guard_kernel<<<nblocks(nwin, 256), 256, 0, c->stream>>>(p.win, nwin, c->d_fcnt + 3); LAUNCHED(c);
-    uint32_t h[8];
+    // the chunk's only host round trip: guard flag, counters, list cursors and the error word, into pinned memory
+    uint32_t *h = c->h_pin;
     CU(cudaMemcpyAsync(h, c->d_fcnt, 20, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(h + 5, c->d_cursor, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h + 8, c->d_err, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->d2h_bytes += 28;
+    c->d2h_bytes += 36;
+    { int erc = report_device_errors(c, h + 8); if (erc) return erc; }
     c->fused_chunks++;
     const size_t F = (size_t)(g.n_features > 0 ? g.n_features : 1);
     if (h[3]) {            // guard tripped: drop this chunk's partial sums, keep the list cursors where they were
@@ -458,10 +471,10 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
         bool done = false;
         rc = fused_stage(c, p, n, &done);
         if (rc) return rc;
-        if (done) {
+        if (done) {                                  // device errors were already checked with the guard readback
             CU(cudaEventRecord(t1, c->stream));
             c->ev_total.push_back({t0, t1});
-            return check_device_errors(c);
+            return MSG_OK;
         }
     }
     // ---- filter stage -> stream of kept records in reference output order
@@ -583,6 +596,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     ctx->decode_mode = mode;
 
     CUC(cudaMalloc(&ctx->d_err, 8)); CUC(cudaMalloc(&ctx->d_acct, 16)); CUC(cudaMalloc(&ctx->d_total, 16));
+    CUC(cudaHostAlloc((void **)&ctx->h_pin, 512, cudaHostAllocPortable)); memset(ctx->h_pin, 0, 512);
     CUC(cudaMemset(ctx->d_acct, 0, 16));
     CUC(cudaMalloc(&ctx->d_wl, 8));
     const size_t T = (size_t)(g.n_targets > 0 ? g.n_targets : 1), F = (size_t)(g.n_features > 0 ? g.n_features : 1);
@@ -595,6 +609,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     if (g.want_profile) {
         CUC(cudaMalloc(&ctx->d_ui, F * 4)); CUC(cudaMalloc(&ctx->d_d, F * 8)); CUC(cudaMalloc(&ctx->d_counters, 32));
         CUC(cudaMalloc(&ctx->d_U, F * 8)); CUC(cudaMalloc(&ctx->d_a, F * 8)); CUC(cudaMalloc(&ctx->d_inc, F * 8));
+        CUC(cudaHostAlloc((void **)&ctx->h_ab, F * 8, cudaHostAllocPortable));
         CUC(cudaMalloc(&ctx->d_partial, ((F + 255) / 256) * 8)); CUC(cudaMalloc(&ctx->d_delta, 8 * 20)); CUC(cudaMalloc(&ctx->d_purged, 4));
         CUC(cudaMalloc(&ctx->d_ui_tmp, F * 4)); CUC(cudaMalloc(&ctx->d_d_tmp, F * 8)); CUC(cudaMalloc(&ctx->d_fcnt, 32)); CUC(cudaMalloc(&ctx->d_cursor, 8));
         CUC(cudaMemset(ctx->d_ui_tmp, 0, F * 4)); CUC(cudaMemset(ctx->d_d_tmp, 0, F * 8));
@@ -670,6 +685,8 @@ void msg_destroy(msg_ctx *c)
     void *ptrs[] = {c->d_fmap, c->d_tlen, c->d_covbase, c->d_err, c->d_acct, c->d_total, c->d_ui, c->d_d, c->d_counters, c->d_stamp, c->d_U, c->d_a,
                     c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_wl, c->d_ui_tmp, c->d_d_tmp, c->d_fcnt, c->d_cursor, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_ab) cudaFreeHost(c->h_ab);
     for (auto &pr : c->ev_decode) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto &pr : c->ev_total) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : c->ev_free) cudaEventDestroy(e);
@@ -876,7 +893,10 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
     uint32_t *ui = c->d_ui; double *dd = c->d_d; uint32_t *cnt = c->d_counters;
     DevBuf &t_ui = c->t_ui, &t_d = c->t_d;
     unsigned long long nl_global = c->csr_lists;
-    uint32_t hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // every small result is copied into pinned memory and read after ONE stream sync at the end
+    uint32_t *hc = c->h_pin + 20; int32_t *res = reinterpret_cast<int32_t *>(c->h_pin + 16); uint32_t *h_purged = c->h_pin + 26;
+    double *h_delta = reinterpret_cast<double *>(c->h_pin + 32);
+    memset(c->h_pin + 16, 0, 4 * (72 - 16));
     if (g.n_ranks > 1) {
         // ONE allreduce over NVLink for everything that is additive across ranks: per-reference counts,
         // the insert counters and the number of multi-mapper lists, packed as u32[F + 8]
@@ -916,7 +936,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<true>, 256, shm));
                 else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<false>, 256, shm));
             }
-            if (per_sm > 4) per_sm = 4;
+            if (per_sm > EM_CTAS_PER_SM) per_sm = EM_CTAS_PER_SM;
             if (per_sm >= 1) {
                 uint32_t grid = (uint32_t)(nsm * per_sm);
                 CU(c->tile_sums.reserve((size_t)grid * 8 + 16));
@@ -941,14 +961,10 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                     else    CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
                 }
                 LAUNCHED(c);
-                int32_t res[4];
                 CU(cudaMemcpyAsync(res, d_res, 16, cudaMemcpyDeviceToHost, c->stream));
-                CU(cudaMemcpyAsync(s.em_delta, c->d_delta, 8 * 20, cudaMemcpyDeviceToHost, c->stream));
-                CU(cudaStreamSynchronize(c->stream));
-                c->d2h_bytes += 168;
-                if (g.n_ranks > 1 && res[2]) return fail(c, MSG_ENCCL, "timed out waiting for a peer GPU inside the PropSharing loop");
-                s.em_iterations = res[0]; s.em_converged = res[1];
-                if (g.n_ranks > 1) { s.purged_insert_count = (uint32_t)res[3]; purged_done = true; }
+                CU(cudaMemcpyAsync(h_delta, c->d_delta, 8 * 20, cudaMemcpyDeviceToHost, c->stream));
+                c->d2h_bytes += 176;
+                purged_done = true;                              // both loop kernels count the purged lists themselves
                 looped = true;
             }
         }
@@ -974,21 +990,33 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
             s.em_delta[k - 1] = delta; s.em_iterations = k;
             if (delta < 1e-10) { s.em_converged = 1; break; }                                     // :383
         }
+        const bool coop = looped;
         if (!purged_done) {
         CU(cudaMemsetAsync(c->d_purged, 0, 4, c->stream));
         if (nl32) { em_purged_kernel<<<em_grid, 256, 0, c->stream>>>(c->csr_off.as<uint32_t>(), c->csr_len.as<uint32_t>(), c->csr_fid.as<int32_t>(), nl32, c->d_a, c->d_purged); LAUNCHED(c); }
         if ((rc = allreduce(c, c->d_purged, 1, ncclUint32, ncclSum))) return rc;
-        CU(cudaMemcpyAsync(&s.purged_insert_count, c->d_purged, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(h_purged, c->d_purged, 4, cudaMemcpyDeviceToHost, c->stream));
         }
+        if (abundance && F) CU(cudaMemcpyAsync(c->h_ab, c->d_a, (size_t)F * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_pin + 8, c->d_err, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (coop) {
+            if (g.n_ranks > 1 && res[2]) return fail(c, MSG_ENCCL, "timed out waiting for a peer GPU inside the PropSharing loop");
+            s.em_iterations = res[0]; s.em_converged = res[1]; s.purged_insert_count = (uint32_t)res[3];
+            memcpy(s.em_delta, h_delta, sizeof s.em_delta);
+        } else s.purged_insert_count = *h_purged;
+    } else {
+        if (abundance && F) CU(cudaMemcpyAsync(c->h_ab, c->d_a, (size_t)F * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_pin + 8, c->d_err, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     }
-    if (abundance && F) CU(cudaMemcpyAsync(abundance, c->d_a, (size_t)F * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    c->d2h_bytes += (size_t)F * 8 + 20;
+    if (abundance && F) memcpy(abundance, c->h_ab, (size_t)F * 8);
+    c->d2h_bytes += (size_t)F * 8 + 28;
     if (g.n_ranks > 1) nl_global = (unsigned long long)hc[4] + ((unsigned long long)hc[5] << 16);
     s.mapped_inserts = hc[0]; s.uniq_mapper_count = hc[1]; s.multi_mapper_count = hc[2];
     s.multi_lists = nl_global; s.multi_entries = ne_local;
     if (st) *st = s;
-    return check_device_errors(c);
+    return report_device_errors(c, c->h_pin + 8);
 }
 
 int msg_finish_coverage(msg_ctx *c, uint8_t *covered, int64_t *touched, int64_t *sum)

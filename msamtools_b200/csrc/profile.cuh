@@ -550,6 +550,16 @@ __global__ void __launch_bounds__(256) em_loop_kernel(const uint32_t *mm_off, co
         if (delta < 1e-10) { conv = 1; break; }
     }
     if (gtid == 0) { result[0] = k < 20 ? k : 19; result[1] = conv; }
+    // purged = #lists whose final abundances sum to exactly 0  (:394-404); a[] is final and visible (second grid.sync above)
+    uint32_t z = 0;
+    for (uint32_t l = gtid; l < nlists; l += gsz) {
+        const uint32_t b = mm_off[l], e = b + mm_len[l];
+        double sum = 0;
+        for (uint32_t q = b; q < e; q++) sum += a[mm_fid[q]];
+        z += (sum == 0);
+    }
+    z = warp_sum_u32(z);
+    if ((threadIdx.x & 31) == 0 && z) atomicAdd(reinterpret_cast<uint32_t *>(result + 3), z);
 }
 
 // Multi-GPU PropSharing loop: compute + collective in ONE cooperative kernel per GPU.  Every rank gathers its own
