@@ -62,8 +62,29 @@ struct BestHitParams {
     uint32_t *wl_count;
 };
 
+// Winners of every complete pool inside one 32-record window.  Best score per (pool, mate class) is a shared-memory
+// max per slot (pool's first lane * 4 + class; sb = 128 words owned by this warp).  A __reduce_max_sync over
+// __match_any groups gives the same answer but executes once per distinct group (~16 serialized REDUX per window at
+// 2-3 records per pool: 22 % of the fused kernel's stall samples).  Called by all 32 lanes.
+__device__ __forceinline__ bool pool_winner(int32_t *sb, uint32_t lane, bool act, int32_t score, uint32_t slot, bool uniq)
+{
+    *reinterpret_cast<int4 *>(sb + lane * 4) = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN);
+    __syncwarp();
+    if (act) atomicMax(sb + slot, score);                                         // msam_filter.c:212-230
+    __syncwarp();
+    const bool tie = act && score == sb[slot];
+    if (!uniq) return tie;
+    __syncwarp();                                                                  // :232-244 winners must be alone in their class
+    *reinterpret_cast<int4 *>(sb + lane * 4) = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    if (tie) atomicAdd(sb + slot, 1);
+    __syncwarp();
+    return tie && sb[slot] == 1;
+}
+
 __global__ void __launch_bounds__(256) besthit_warp_select_kernel(const BestHitParams p)
 {
+    __shared__ __align__(16) int32_t s_best[8][128];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t w0 = i & ~31ull;
     if (w0 >= p.n) return;                                                        // whole warp out of range
@@ -83,13 +104,8 @@ __global__ void __launch_bounds__(256) besthit_warp_select_kernel(const BestHitP
     const bool paired = (__ballot_sync(0xffffffffu, pooled && cls != 0) & v.segmask) != 0;
     const bool act = pooled && (paired ? (cls == 1 || cls == 2) : true);
     if (act && !(f & FB_HAS_AS)) atomicOr(p.err, DERR_NOAS);                       // :219-221
-    const uint32_t key = act ? (v.s * 4u + (uint32_t)cls) : (0x100u + lane);
-    const uint32_t m = __match_any_sync(0xffffffffu, key);
     const int32_t sc = act ? p.score[i] : INT32_MIN;
-    const int32_t best = __reduce_max_sync(m, sc);                                // :212-230
-    const bool tie = act && sc == best;
-    const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, tie) & m);
-    const bool keep = tie && (!p.uniq || cnt == 1);                               // :232-244
+    const bool keep = pool_winner(s_best[threadIdx.x >> 5], lane, act, sc, v.s * 4u + (uint32_t)cls, p.uniq);
     if (mine) {
         const uint32_t out = keep ? (f | FB_KEEP) : (f & ~FB_KEEP);
         if (out != f) p.fb[i] = out;

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) fused_warp_kernel(const FusedParams p)
 {
     extern __shared__ uint32_t s_hist[];
     __shared__ uint32_t s_cnt[4];
+    __shared__ __align__(16) int32_t s_best[8][128];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     if (SMEM_HIST) for (uint32_t k = threadIdx.x; k < (uint32_t)p.n_features; k += blockDim.x) s_hist[k] = 0;
     __syncthreads();
@@ -72,13 +73,8 @@ __global__ void __launch_bounds__(256) fused_warp_kernel(const FusedParams p)
         const bool paired = (__ballot_sync(0xffffffffu, pooled && cls != 0) & v.segmask) != 0;
         const bool act = pooled && (paired ? (cls == 1 || cls == 2) : true);
         if (act && !(f & FB_HAS_AS)) atomicOr(p.err, DERR_NOAS);
-        const uint32_t key = act ? (v.s * 4u + (uint32_t)cls) : (0x100u + lane);
-        const uint32_t m = __match_any_sync(0xffffffffu, key);
         const int32_t sc = act ? p.score[i] : INT32_MIN;
-        const int32_t best = __reduce_max_sync(m, sc);
-        const bool tie = act && sc == best;
-        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, tie) & m);
-        const bool keep = tie && (!p.uniq || cnt == 1);
+        const bool keep = pool_winner(s_best[threadIdx.x >> 5], lane, act, sc, v.s * 4u + (uint32_t)cls, p.uniq);
 
         // ---- profile group = the pool's winners with tid != -1, READ1-class first
         int32_t t = keep ? p.tid[i] : -1;
