@@ -194,7 +194,7 @@ int run_scan(msg_ctx *c, In in, Out out, uint64_t n, T *h_total)
 }
 
 int report_device_errors(msg_ctx *c, const uint32_t *h);
-static const int EM_CTAS_PER_SM = getenv("MSG_EM_CTAS") ? atoi(getenv("MSG_EM_CTAS")) : 4;
+static const int EM_CTAS_PER_SM = getenv("MSG_EM_CTAS") ? atoi(getenv("MSG_EM_CTAS")) : 3;
 
 int check_device_errors(msg_ctx *c)
 {
