@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256) fused_warp_kernel(const FusedParams p)
 // class, then the winners) and finishes the group from a small local list.  Pools longer than
 // big_threshold records or with more than FUSED_MAXM winners send the chunk to the general pipeline.
 constexpr int FUSED_MAXM = 48;
+constexpr int FUSED_PF = 8;       // records whose columns are prefetched per walked pool
 
 __global__ void __launch_bounds__(128) fused_walk_kernel(const FusedParams p)
 {
@@ -182,46 +183,56 @@ __global__ void __launch_bounds__(128) fused_walk_kernel(const FusedParams p)
       uint64_t i = 0;
       if (q < nw) do {
         i = p.worklist[q];
+        // The walk is latency bound (one thread per pool, dependent loads), so the first FUSED_PF records' columns are
+        // fetched up front with independent loads; both passes then run out of registers for the usual short pool
+        // and only touch memory again for the rare records beyond the prefetch.
+        uint32_t fr[FUSED_PF]; int32_t sr[FUSED_PF], tr[FUSED_PF];
+#pragma unroll
+        for (int k = 0; k < FUSED_PF; k++) {
+            const uint64_t j = i + k; const bool ok = j < p.n;
+            fr[k] = ok ? p.fb[j] : 0u; sr[k] = ok ? p.score[j] : 0; tr[k] = ok ? p.tid[j] : -1;
+        }
+        uint32_t len = 1; bool open = true;                                  // run = i plus the following FB_EQPREV records
+#pragma unroll
+        for (int k = 1; k < FUSED_PF; k++) { open = open && (fr[k] & FB_EQPREV); len += open; }
+        uint64_t end = i + len;
+        if (open) { while (end < p.n && (p.fb[end] & FB_EQPREV)) end++; }
+        if (end - i > p.big_threshold) { atomicOr(p.cnt + 3, 1u); break; }
         // pass 1: per mate class best / ties, pairedness (msam_filter.c:196-230)
         int32_t b0 = INT32_MIN, b1 = INT32_MIN, b2 = INT32_MIN; uint32_t c0 = 0, c1 = 0, c2 = 0;
         uint32_t noas = 0; bool paired = false;
-        uint64_t j = i; uint32_t f = p.fb[i];
-        for (;;) {
-            if (f & FB_INPOOL) {
-                const int c = mate_class(f);
-                paired |= (c != 0);
-                if (!(f & FB_HAS_AS)) noas |= 1u << c;
-                const int32_t s = p.score[j];
-                if (c == 0) { if (s > b0) { b0 = s; c0 = 1; } else if (s == b0) c0++; }
-                else if (c == 1) { if (s > b1) { b1 = s; c1 = 1; } else if (s == b1) c1++; }
-                else if (c == 2) { if (s > b2) { b2 = s; c2 = 1; } else if (s == b2) c2++; }
-            }
-            if (++j >= p.n) break;
-            f = p.fb[j];
-            if (!(f & FB_EQPREV)) break;
-        }
-        const uint64_t end = j;
-        if (end - i > p.big_threshold) { atomicOr(p.cnt + 3, 1u); break; }
+        auto pass1 = [&](uint32_t f, int32_t sc) {
+            if (!(f & FB_INPOOL)) return;
+            const int c = mate_class(f);
+            paired |= (c != 0);
+            if (!(f & FB_HAS_AS)) noas |= 1u << c;
+            if (c == 0) { if (sc > b0) { b0 = sc; c0 = 1; } else if (sc == b0) c0++; }
+            else if (c == 1) { if (sc > b1) { b1 = sc; c1 = 1; } else if (sc == b1) c1++; }
+            else if (c == 2) { if (sc > b2) { b2 = sc; c2 = 1; } else if (sc == b2) c2++; }
+        };
+#pragma unroll
+        for (int k = 0; k < FUSED_PF; k++) if ((uint32_t)k < len) pass1(fr[k], sr[k]);
+        for (uint64_t j = i + FUSED_PF; j < end; j++) pass1(p.fb[j], p.score[j]);
         if (paired ? (noas & 6u) : (noas & 1u)) atomicOr(p.err, DERR_NOAS);
         // pass 2: winners with tid != -1, as (feature, READ2-class?) in input order
         int32_t mf[FUSED_MAXM]; uint32_t r2bits_lo = 0, r2bits_hi = 0; bool overflow = false;
-        for (j = i; j < end; j++) {
-            f = p.fb[j];
-            if (!(f & FB_INPOOL)) continue;
+        auto pass2 = [&](uint32_t f, int32_t sc, int32_t tt) {
+            if (overflow || !(f & FB_INPOOL)) return;
             const int c = mate_class(f);
-            if (paired ? !(c == 1 || c == 2) : c != 0) continue;
-            const int32_t s = p.score[j];
+            if (paired ? !(c == 1 || c == 2) : c != 0) return;
             const int32_t bb = c == 0 ? b0 : (c == 1 ? b1 : b2); const uint32_t cc = c == 0 ? c0 : (c == 1 ? c1 : c2);
-            if (s != bb || (p.uniq && cc != 1)) continue;
+            if (sc != bb || (p.uniq && cc != 1)) return;
             keptn++;
-            const int32_t tt = p.tid[j];
-            if (tt == -1) continue;
-            if (tt < 0 || tt >= p.n_targets) { atomicOr(p.err, DERR_FORMAT); continue; }
-            if (nm >= FUSED_MAXM) { overflow = true; break; }
+            if (tt == -1) return;
+            if (tt < 0 || tt >= p.n_targets) { atomicOr(p.err, DERR_FORMAT); return; }
+            if (nm >= FUSED_MAXM) { overflow = true; return; }
             mf[nm] = fused_feature(p, tt);
             if (c == 2) { if (nm < 32) r2bits_lo |= 1u << nm; else r2bits_hi |= 1u << (nm - 32); }
             nm++;
-        }
+        };
+#pragma unroll
+        for (int k = 0; k < FUSED_PF; k++) if ((uint32_t)k < len) pass2(fr[k], sr[k], tr[k]);
+        for (uint64_t j = i + FUSED_PF; j < end; j++) pass2(p.fb[j], p.score[j], p.tid[j]);
         if (overflow) { atomicOr(p.cnt + 3, 1u); nm = 0; break; }
         if (nm == 0) break;
         // distinct features in the order READ1-class winners, then READ2-class winners (msam_filter.c:247-254 -> msam_profile.c:136-142)
