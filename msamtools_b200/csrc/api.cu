@@ -348,6 +348,9 @@ int fused_stage(msg_ctx *c, const DecodeParams &dp, uint64_t n, bool *done)
     LAUNCHED(c);
     fused_walk_kernel<<<std::min<uint32_t>(nblocks(nwin, 128), 148u * 8u), 128, 0, c->stream>>>(p); LAUNCHED(c);
     fused_guard_kernel<<<nblocks(nwin, 256), 256, 0, c->stream>>>(p.win, nwin, c->d_fcnt + 3); LAUNCHED(c);
+    const size_t F = (size_t)(g.n_features > 0 ? g.n_features : 1);
+    fused_commit_kernel<<<nblocks(F < 3 ? 3 : F, 256), 256, 0, c->stream>>>(c->d_ui, c->d_d, c->d_ui_tmp, c->d_d_tmp, (uint32_t)g.n_features,
+                                                                           g.share_type == MSG_MULTI_EQUAL, c->d_counters, c->d_fcnt); LAUNCHED(c);
     // the chunk's only host round trip: guard flag, counters, list cursors and the error word, into pinned memory
     uint32_t *h = c->h_pin;
     CU(cudaMemcpyAsync(h, c->d_fcnt, 20, cudaMemcpyDeviceToHost, c->stream));
@@ -357,15 +360,10 @@ int fused_stage(msg_ctx *c, const DecodeParams &dp, uint64_t n, bool *done)
     c->d2h_bytes += 36;
     { int erc = report_device_errors(c, h + 8); if (erc) return erc; }
     c->fused_chunks++;
-    const size_t F = (size_t)(g.n_features > 0 ? g.n_features : 1);
-    if (h[3]) {            // guard tripped: drop this chunk's partial sums, keep the list cursors where they were
+    if (h[3]) {            // guard tripped: the commit kernel dropped this chunk's partial sums; keep the list cursors where they were
         c->fused_fallbacks++;
-        CU(cudaMemsetAsync(c->d_ui_tmp, 0, F * 4, c->stream));
-        CU(cudaMemsetAsync(c->d_d_tmp, 0, F * 8, c->stream));
         return MSG_OK;
     }
-    fused_commit_kernel<<<nblocks(F < 3 ? 3 : F, 256), 256, 0, c->stream>>>(c->d_ui, c->d_d, c->d_ui_tmp, c->d_d_tmp, (uint32_t)g.n_features,
-                                                                           g.share_type == MSG_MULTI_EQUAL, c->d_counters, c->d_fcnt); LAUNCHED(c);
     c->csr_lists = h[5]; c->csr_ent = h[6];
     c->n_kept = h[4]; c->have_stream = false;
     *done = true;
@@ -915,7 +913,12 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
         }
         CU(cudaMemcpyAsync(hc, cnt, 24, cudaMemcpyDeviceToHost, c->stream));
     } else CU(cudaMemcpyAsync(hc, cnt, 16, cudaMemcpyDeviceToHost, c->stream));
-    if (F) { em_init_kernel<<<nblocks(F, 256), 256, 0, c->stream>>>(ui, dd, g.share_type == MSG_MULTI_EQUAL, c->d_U, c->d_a, F); LAUNCHED(c); }
+    if (F) {
+        em_init_kernel<<<nblocks(F, 256), 256, 0, c->stream>>>(ui, dd, g.share_type == MSG_MULTI_EQUAL, c->d_U, c->d_a, F, c->d_inc, c->d_delta,
+                                                              reinterpret_cast<int32_t *>(c->d_total),
+                                                              c->peer_region ? reinterpret_cast<uint32_t *>(c->peer_region + 64) : nullptr);
+        LAUNCHED(c);
+    }
     const uint64_t ne_local = c->csr_ent;
     const uint32_t nl32 = (uint32_t)c->csr_lists;
     const uint32_t em_grid = nl32 ? (nblocks(nl32, 256) < 148u * 8u ? nblocks(nl32, 256) : 148u * 8u) : 0;
@@ -947,12 +950,9 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 const double *U = c->d_U; double *av = c->d_a, *inc = c->d_inc, *dout = c->d_delta;
                 PeerTable pt = c->peer_tab; int nr = g.n_ranks, rk = g.rank; uint32_t epoch = c->em_epoch;
                 void *args[] = {&a0, &a1, &a2, &nl_arg, &U, &av, &inc, &partial, &F_arg, &dout, &d_res, &pt, &nr, &rk, &epoch};
-                CU(cudaMemsetAsync(c->d_inc, 0, (size_t)F * 8, c->stream));
-                CU(cudaMemsetAsync(c->d_delta, 0, 8 * 20, c->stream));
-                CU(cudaMemsetAsync(d_res, 0, 16, c->stream));
+                // inc, delta, d_res and the peer region's purged word were cleared by em_init_kernel
                 if (g.n_ranks > 1) {
                     // compute + collective in one kernel: increments are exchanged through peer memory inside the loop
-                    CU(cudaMemsetAsync(c->peer_region + 64, 0, 4, c->stream));
                     if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<true>, dim3(grid), dim3(256), args, shm, c->stream));
                     else    CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
                     c->em_epoch += 32;

@@ -38,9 +38,11 @@
 
 __device__ __forceinline__ uint4 ldg_stream128(const uint4 *p)
 {
-    // streaming 16-byte load: record bytes are touched once, keep them out of L1
+    // streaming 16-byte load: record bytes are touched once, keep them out of L1.  The L2::64B qualifier matters: a
+    // plain load makes B200's L2 fill whole 128-byte lines from HBM (measured: 2.34 GB of DRAM reads per 10 M records,
+    // 1.70 GB with the qualifier) although the decode windows only need ~129 B of 32-byte sectors per 295-byte record.
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }

@@ -404,13 +404,20 @@ __global__ void profile_big_kernel(const ProfParams p, uint32_t nbig, uint32_t *
 }
 
 // ---------------------------------------------------------------- abundance / EM (msam_profile.c:284-404)
-__global__ void em_init_kernel(const uint32_t *ui, const double *d, int use_d, double *U, double *a, uint32_t n)
+// also clears what the loop kernels expect to find zeroed (inc[F], delta[20], result[4], one peer-region word), so
+// that PropSharing needs no separate memset launches
+__global__ void em_init_kernel(const uint32_t *ui, const double *d, int use_d, double *U, double *a, uint32_t n,
+                               double *inc, double *delta, int32_t *result, uint32_t *peer_word)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 20 && delta) delta[i] = 0.0;
+    if (i < 4 && result) result[i] = 0;
+    if (i == 0 && peer_word) *peer_word = 0u;
     if (i >= n) return;
     double u = 1.0 * ui[i] / 2;                                         // :286
     if (use_d) u += d[i];                                               // :305
     U[i] = u; a[i] = u;
+    if (inc) inc[i] = 0.0;
 }
 __global__ void em_init_from_U_kernel(const double *U, double *a, uint32_t n)
 {
