@@ -130,7 +130,7 @@ struct msg_ctx {
     // multi-GPU
     ncclComm_t comm = nullptr;
     // peer-memory exchange for the fused EM loop (profile.cuh em_loop_multi_kernel): CUDA IPC mappings of every rank's region
-    unsigned char *peer_region = nullptr; PeerTable peer_tab; std::vector<void *> ipc_opened; bool p2p_ok = false; uint32_t em_epoch = 0;
+    unsigned char *peer_region = nullptr; PeerTable peer_tab; std::vector<void *> ipc_opened; bool p2p_ok = false; uint32_t em_epoch = 32;
 
     // timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_decode, ev_total;
@@ -635,7 +635,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
         if (g.want_profile && g.n_ranks <= 16 && g_nccl.AllGather) {
             // Map every rank's publish region into this process (CUDA IPC over NVLink).  If any rank cannot, all ranks
             // agree (allreduce-min) to keep the NCCL-per-iteration loop instead.
-            const size_t region = 128 + 2 * F * 8;
+            const size_t region = 128 + 2 * (size_t)g.n_ranks * (F + 8) * 16;    // profile.cuh: purged[16] u64, slot[2][n_ranks][F + 8][2] u64
             int ok = 1;
             cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof mine);
             unsigned char *d_hs = nullptr; int *d_ok = nullptr;
@@ -651,7 +651,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
                 if (pr == g.rank) { ctx->peer_tab.base[pr] = ctx->peer_region; continue; }
                 void *pp = nullptr;
                 if (cudaIpcOpenMemHandle(&pp, hs[(size_t)pr], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
-                ctx->ipc_opened.push_back(pp); ctx->peer_tab.base[pr] = (const unsigned char *)pp;
+                ctx->ipc_opened.push_back(pp); ctx->peer_tab.base[pr] = (unsigned char *)pp;
             }
             CUC(cudaMemcpy(d_ok, &ok, 4, cudaMemcpyHostToDevice));
             if (g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream) != ncclSuccess) ok = 0;
@@ -891,11 +891,19 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
     uint32_t *ui = c->d_ui; double *dd = c->d_d; uint32_t *cnt = c->d_counters;
     DevBuf &t_ui = c->t_ui, &t_d = c->t_d;
     unsigned long long nl_global = c->csr_lists;
+    // MSG_TRACE_FINISH=1: device-side time of each phase, printed to stderr (diagnostics only)
+    static const bool trace = getenv("MSG_TRACE_FINISH") != nullptr;
+    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto tmark = [&](int k) { if (trace) { if (!tev[k]) cudaEventCreate(&tev[k]); cudaEventRecord(tev[k], c->stream); } };
+    tmark(0);
     // every small result is copied into pinned memory and read after ONE stream sync at the end
     uint32_t *hc = c->h_pin + 20; int32_t *res = reinterpret_cast<int32_t *>(c->h_pin + 16); uint32_t *h_purged = c->h_pin + 26;
     double *h_delta = reinterpret_cast<double *>(c->h_pin + 32);
     memset(c->h_pin + 16, 0, 4 * (72 - 16));
-    if (g.n_ranks > 1) {
+    // proportional sharing over peer memory: the loop kernel also exchanges the counts, so no NCCL call and no em_init
+    const bool coop_multi = g.n_ranks > 1 && c->p2p_ok && F > 0 && g.share_type == MSG_MULTI_PROPORTIONAL && !getenv("MSG_EM_HOST_LOOP");
+    if (coop_multi) {
+    } else if (g.n_ranks > 1) {
         // ONE allreduce over NVLink for everything that is additive across ranks: per-reference counts,
         // the insert counters and the number of multi-mapper lists, packed as u32[F + 8]
         CU(t_ui.reserve(((size_t)F + 8) * 4));
@@ -911,14 +919,15 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
             dd = t_d.as<double>();
             if ((rc = allreduce(c, dd, F, ncclFloat64, ncclSum))) return rc;
         }
+        tmark(1);
         CU(cudaMemcpyAsync(hc, cnt, 24, cudaMemcpyDeviceToHost, c->stream));
     } else CU(cudaMemcpyAsync(hc, cnt, 16, cudaMemcpyDeviceToHost, c->stream));
-    if (F) {
+    if (F && !coop_multi) {
         em_init_kernel<<<nblocks(F, 256), 256, 0, c->stream>>>(ui, dd, g.share_type == MSG_MULTI_EQUAL, c->d_U, c->d_a, F, c->d_inc, c->d_delta,
-                                                              reinterpret_cast<int32_t *>(c->d_total),
-                                                              c->peer_region ? reinterpret_cast<uint32_t *>(c->peer_region + 64) : nullptr);
+                                                              reinterpret_cast<int32_t *>(c->d_total));
         LAUNCHED(c);
     }
+    tmark(2);
     const uint64_t ne_local = c->csr_ent;
     const uint32_t nl32 = (uint32_t)c->csr_lists;
     const uint32_t em_grid = nl32 ? (nblocks(nl32, 256) < 148u * 8u ? nblocks(nl32, 256) : 148u * 8u) : 0;
@@ -939,6 +948,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<true>, 256, shm));
                 else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<false>, 256, shm));
             }
+            if (per_sm < 1 && coop_multi) return fail(c, MSG_ECUDA, "cannot launch the cooperative PropSharing kernel (F = %u needs too much shared memory?)", F);
             if (per_sm > EM_CTAS_PER_SM) per_sm = EM_CTAS_PER_SM;
             if (per_sm >= 1) {
                 uint32_t grid = (uint32_t)(nsm * per_sm);
@@ -949,18 +959,26 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 uint32_t nl_arg = nl32, F_arg = F;
                 const double *U = c->d_U; double *av = c->d_a, *inc = c->d_inc, *dout = c->d_delta;
                 PeerTable pt = c->peer_tab; int nr = g.n_ranks, rk = g.rank; uint32_t epoch = c->em_epoch;
-                void *args[] = {&a0, &a1, &a2, &nl_arg, &U, &av, &inc, &partial, &F_arg, &dout, &d_res, &pt, &nr, &rk, &epoch};
+                void *args[] = {&a0, &a1, &a2, &nl_arg, &U, &av, &inc, &partial, &F_arg, &dout, &d_res};
+                // multi-GPU kernel: (lists..., ui, counters, nl_lo, nl_hi, U, a, inc, partial, F, delta, result, hc_out, peers, n_ranks, rank, epoch)
+                const uint32_t *ui_arg = c->d_ui, *cnt_arg = c->d_counters; double *Uw = c->d_U;
+                uint32_t nl_lo = (uint32_t)(c->csr_lists & 0xffffu), nl_hi = (uint32_t)(c->csr_lists >> 16);   // two 16-bit halves, as in the NCCL path
+                uint32_t *hc_dev = nullptr;
+                if (g.n_ranks > 1) { CU(c->t_cnt.reserve(64)); hc_dev = c->t_cnt.as<uint32_t>(); }
+                void *margs[] = {&a0, &a1, &a2, &nl_arg, &ui_arg, &cnt_arg, &nl_lo, &nl_hi, &Uw, &av, &inc, &partial, &F_arg, &dout, &d_res, &hc_dev, &pt, &nr, &rk, &epoch};
                 // inc, delta, d_res and the peer region's purged word were cleared by em_init_kernel
                 if (g.n_ranks > 1) {
                     // compute + collective in one kernel: increments are exchanged through peer memory inside the loop
-                    if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<true>, dim3(grid), dim3(256), args, shm, c->stream));
-                    else    CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
+                    if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<true>, dim3(grid), dim3(256), margs, shm, c->stream));
+                    else    CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<false>, dim3(grid), dim3(256), margs, shm, c->stream));
                     c->em_epoch += 32;
+                    CU(cudaMemcpyAsync(hc, hc_dev, 24, cudaMemcpyDeviceToHost, c->stream));
                 } else {
                     if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<true>, dim3(grid), dim3(256), args, shm, c->stream));
                     else    CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
                 }
                 LAUNCHED(c);
+                tmark(3);
                 CU(cudaMemcpyAsync(res, d_res, 16, cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaMemcpyAsync(h_delta, c->d_delta, 8 * 20, cudaMemcpyDeviceToHost, c->stream));
                 c->d2h_bytes += 176;
@@ -1009,6 +1027,18 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
         if (abundance && F) CU(cudaMemcpyAsync(c->h_ab, c->d_a, (size_t)F * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(c->h_pin + 8, c->d_err, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+    }
+    if (trace) {
+        tmark(4); cudaEventSynchronize(tev[4]);
+        float ms[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; k++) if (tev[k] && tev[k + 1]) cudaEventElapsedTime(&ms[k], tev[k], tev[k + 1]);
+        if (tev[0] && tev[2] && !tev[1]) cudaEventElapsedTime(&ms[1], tev[0], tev[2]);
+        float chunk = 0, gap = 0, dec = 0;
+        if (!c->ev_total.empty()) { cudaEventElapsedTime(&chunk, c->ev_total.back().first, c->ev_total.back().second); cudaEventElapsedTime(&gap, c->ev_total.back().second, tev[0]); }
+        if (!c->ev_decode.empty()) cudaEventElapsedTime(&dec, c->ev_decode.back().first, c->ev_decode.back().second);
+        fprintf(stderr, "[msg finish rank %d] last chunk %.3f ms (decode %.3f), gap %.3f ms, allreduce %.3f ms, init %.3f ms, loop %.3f ms, tail %.3f ms\n",
+                g.rank, chunk, dec, gap, ms[0], ms[1], ms[2], ms[3]);
+        for (auto e : tev) if (e) cudaEventDestroy(e);
     }
     if (abundance && F) memcpy(abundance, c->h_ab, (size_t)F * 8);
     c->d2h_bytes += (size_t)F * 8 + 28;

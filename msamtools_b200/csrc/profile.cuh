@@ -404,15 +404,14 @@ __global__ void profile_big_kernel(const ProfParams p, uint32_t nbig, uint32_t *
 }
 
 // ---------------------------------------------------------------- abundance / EM (msam_profile.c:284-404)
-// also clears what the loop kernels expect to find zeroed (inc[F], delta[20], result[4], one peer-region word), so
+// also clears what the single-GPU loop kernel expects to find zeroed (inc[F], delta[20], result[4]), so
 // that PropSharing needs no separate memset launches
 __global__ void em_init_kernel(const uint32_t *ui, const double *d, int use_d, double *U, double *a, uint32_t n,
-                               double *inc, double *delta, int32_t *result, uint32_t *peer_word)
+                               double *inc, double *delta, int32_t *result)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 20 && delta) delta[i] = 0.0;
     if (i < 4 && result) result[i] = 0;
-    if (i == 0 && peer_word) *peer_word = 0u;
     if (i >= n) return;
     double u = 1.0 * ui[i] / 2;                                         // :286
     if (use_d) u += d[i];                                               // :305
@@ -581,27 +580,44 @@ __global__ void __launch_bounds__(256) em_loop_kernel(const uint32_t *mm_off, co
     if ((threadIdx.x & 31) == 0 && z) atomicAdd(reinterpret_cast<uint32_t *>(result + 3), z);
 }
 
-// Multi-GPU PropSharing loop: compute + collective in ONE cooperative kernel per GPU.  Every rank gathers its own
-// lists into `inc`, publishes the vector in a peer-visible buffer (CUDA IPC mapping, NVLink/NVSwitch loads), raises its
-// flag, waits for the other ranks' flags, and then every rank adds the N published vectors in rank order -- the same
-// order everywhere, so abundances, delta and the stop decision are bit-identical on all ranks without any NCCL call or
-// host round trip inside the loop.  Publish buffers alternate by iteration parity: a rank can only overwrite buffer
-// k%2 at iteration k+2, i.e. after every peer has published k+1, which it does only after it finished reading k.
-struct PeerTable { const unsigned char *base[16]; };      // region of rank r: [flag u32 | pad to 128 B | pub0 f64[F] | pub1 f64[F]]
+// Multi-GPU PropSharing: counts exchange + the whole loop + the purged total in ONE cooperative kernel per GPU, with
+// no NCCL call and no host round trip.  Collective = push over peer memory (CUDA IPC mappings, NVLink/NVSwitch) in a
+// low-latency flagged format: every value travels as two 8-byte words {epoch tag : 32 | half of the f64 : 32}.  A rank
+// STORES its vector into its slot of every peer's region and is done -- no fence, no separate flag; a receiver polls
+// its OWN memory until both words of an element carry the expected tag (8-byte stores are single-copy atomic, so a
+// matching tag proves the payload).  An exchange therefore costs one one-way NVLink latency.  Every rank then adds the
+// N vectors in rank order -- the same order everywhere -- so abundances, delta and the stop decision are bit-identical
+// on all ranks.
+//
+// Region of rank r (lives in r's memory, written by its peers):
+//   [0,128)   purged[s]  u64   {tag : 32 | sender s's purged-list count : 32}
+//   [128, )   slot[parity][s][V][2] u64, V = F + 8: vector of sender s for exchanges of that parity
+// Exchange k (k = 0: doubled counts + insert counters, k >= 1: increments of iteration k) uses parity k & 1 and tag
+// epoch + k.  A sender overwrites slot[k & 1] only after it received exchange k-1 from every peer, which a peer sends
+// after all of its threads finished reading exchange k-2 (grid barriers in between).  The purged message (tag
+// epoch + 24) closes a call the same way, so the next call may start writing at once.  Vectors of up to EM_XCHG_CTA0
+// values are exchanged by CTA 0 alone (the other CTAs wait at the next grid barrier), longer ones by the whole grid.
+struct PeerTable { unsigned char *base[16]; };
+constexpr uint32_t EM_XCHG_CTA0 = 8192;
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+__device__ __forceinline__ void ll_store(unsigned long long *p, unsigned long long w0, unsigned long long w1)
 {
-    uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+__device__ __forceinline__ void ll_load(const unsigned long long *p, unsigned long long &w0, unsigned long long &w1)
 {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long *ll_slot(const PeerTable &pt, int dst, uint32_t parity, int src, int n_ranks, uint32_t V)
+{
+    return reinterpret_cast<unsigned long long *>(pt.base[dst] + 128) + (((size_t)parity * (size_t)n_ranks + (size_t)src) * V) * 2;
 }
 
 template <bool SMEM>
 __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
-                                                            const double *U, double *a, double *inc, double *partial, uint32_t F,
-                                                            double *delta_out, int32_t *result,
+                                                            const uint32_t *ui, const uint32_t *counters, uint32_t nl_lo, uint32_t nl_hi,
+                                                            double *U, double *a, double *inc, double *partial, uint32_t F,
+                                                            double *delta_out, int32_t *result, uint32_t *hc_out,
                                                             PeerTable peers, int n_ranks, int rank, uint32_t epoch)
 {
     namespace cg = cooperative_groups;
@@ -611,8 +627,47 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
     const uint32_t ncopy = SMEM ? em_copies(F) : 1u;
     double *sa = s_em, *si = s_em + F;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    unsigned char *mine = const_cast<unsigned char *>(peers.base[rank]);
-    int k = 1, conv = 0, timeout = 0;
+    const uint32_t V = F + 8;
+    // who takes part in the exchanges
+    const bool cta0 = V <= EM_XCHG_CTA0;
+    const bool part = !cta0 || blockIdx.x == 0;
+    const uint32_t ptid = cta0 ? threadIdx.x : gtid, pn = cta0 ? blockDim.x : gsz, nparts = cta0 ? 1u : gridDim.x;
+    int timeout = 0;
+    // push my vector (getv) to every rank, then wait for everyone's vector and hand the rank-ordered total of every
+    // element to put().  Called by the participants only; needs no barrier of its own.
+    auto exchange = [&](uint32_t tag, uint32_t parity, auto getv, auto put) {
+        const unsigned long long want = (unsigned long long)(epoch + tag), t = want << 32;
+        for (uint32_t i = ptid; i < V; i += pn) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(getv(i));
+            const unsigned long long w0 = t | (bits & 0xffffffffull), w1 = t | (bits >> 32);
+            for (int r = 0; r < n_ranks; r++) ll_store(ll_slot(peers, r, parity, rank, n_ranks, V) + 2 * (size_t)i, w0, w1);
+        }
+        for (uint32_t i = ptid; i < V; i += pn) {
+            double tot = 0;
+            for (int r = 0; r < n_ranks; r++) {
+                const unsigned long long *src = ll_slot(peers, rank, parity, r, n_ranks, V) + 2 * (size_t)i;
+                unsigned long long w0, w1, spins = 0;
+                for (;;) {
+                    ll_load(src, w0, w1);
+                    if ((w0 >> 32) == want && (w1 >> 32) == want) break;
+                    if (++spins > (1ull << 26)) { timeout = 1; break; }
+                }
+                tot += __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+            }
+            put(i, tot);
+        }
+        if (timeout) result[2] = 1;
+    };
+    // ---- exchange 0: U = a = (sum over ranks of the doubled counts) / 2 (:286); insert counters and list totals for the host.
+    //      Small integers are exact in f64, so the totals equal the integer sums.
+    if (gtid < 20) delta_out[gtid] = 0.0;
+    if (gtid < 4) result[gtid] = 0;
+    if (part)
+        exchange(0u, 0u,
+                 [&](uint32_t i) -> double { return i < F ? (double)ui[i] : i < F + 4 ? (double)counters[i - F] : i == F + 4 ? (double)nl_lo : i == F + 5 ? (double)nl_hi : 0.0; },
+                 [&](uint32_t i, double tot) { if (i < F) { const double u = tot / 2; U[i] = u; a[i] = u; inc[i] = 0.0; } else hc_out[i - F] = (uint32_t)tot; });
+    grid.sync();
+    int k = 1, conv = 0;
     for (; k < 20; k++) {
         if (SMEM) {
             for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) sa[i] = a[i];
@@ -631,37 +686,28 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
             }
         }
         grid.sync();
-        // publish my increments, then tell the peers
-        double *pub = reinterpret_cast<double *>(mine + 128) + (size_t)(k & 1) * F;
-        for (uint32_t i = gtid; i < F; i += gsz) { pub[i] = inc[i]; inc[i] = 0.0; }
-        __threadfence_system();
-        grid.sync();
-        if (gtid == 0) st_release_sys(reinterpret_cast<uint32_t *>(mine), epoch + (uint32_t)k);
-        if (blockIdx.x == 0 && threadIdx.x < (uint32_t)n_ranks) {
-            const uint32_t *pf = reinterpret_cast<const uint32_t *>(peers.base[threadIdx.x]);
-            unsigned long long spins = 0;
-            while ((int32_t)(ld_acquire_sys(pf) - (epoch + (uint32_t)k)) < 0) { if (++spins > (1ull << 28)) { timeout = 1; break; } __nanosleep(64); }
-            if (timeout) result[2] = 1;
+        // exchange the increments; a = U + total, flush < 1e-20, per-CTA partial of sum diff^2   (:369-379)
+        if (part) {
+            double dd = 0;
+            exchange((uint32_t)k, (uint32_t)k & 1u,
+                     [&](uint32_t i) -> double { if (i >= F) return 0.0; const double v = inc[i]; inc[i] = 0.0; return v; },
+                     [&](uint32_t i, double tot) {
+                         if (i >= F) return;
+                         double an = U[i] + tot;
+                         if (an < 1e-20) an = 0;
+                         const double diff = an - a[i];
+                         dd += diff * diff;
+                         a[i] = an;
+                     });
+            s_red[threadIdx.x] = dd;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+            if (threadIdx.x == 0) partial[blockIdx.x] = s_red[0];
         }
         grid.sync();
-        // a = U + sum over ranks (rank order) ; per-CTA partial of sum diff^2
-        double dd = 0;
-        for (uint32_t i = gtid; i < F; i += gsz) {
-            double tot = 0;
-            for (int r = 0; r < n_ranks; r++) tot += (reinterpret_cast<const double *>(peers.base[r] + 128) + (size_t)(k & 1) * F)[i];
-            double an = U[i] + tot;
-            if (an < 1e-20) an = 0;
-            const double diff = an - a[i];
-            dd += diff * diff;
-            a[i] = an;
-        }
-        s_red[threadIdx.x] = dd;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
-        if (threadIdx.x == 0) partial[blockIdx.x] = s_red[0];
-        grid.sync();
+        // delta (every CTA, same order)                                   (:380-383)
         double acc = 0;
-        for (uint32_t b = threadIdx.x; b < gridDim.x; b += 256) acc += partial[b];
+        for (uint32_t b = threadIdx.x; b < nparts; b += 256) acc += __ldcg(partial + b);
         s_red[threadIdx.x] = acc;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
@@ -670,37 +716,38 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
         if (gtid == 0) delta_out[k - 1] = delta;
         if (delta < 1e-10) { conv = 1; break; }
     }
-    // purged = #lists whose final abundances sum to exactly 0 (:394-404), summed over ranks through the same regions
+    // ---- purged = #lists whose final abundances sum to exactly 0 (:394-404), summed over ranks through the same regions
     {
-        __shared__ uint32_t s_z;
-        if (threadIdx.x == 0) s_z = 0;
-        __syncthreads();
         uint32_t z = 0;
         for (uint32_t l = gtid; l < nlists; l += gsz) {
+            const uint32_t b = mm_off[l], e = b + mm_len[l];
             double sum = 0;
-            for (uint32_t q = mm_off[l]; q < mm_off[l] + mm_len[l]; q++) sum += a[mm_fid[q]];
+            for (uint32_t q = b; q < e; q++) sum += a[mm_fid[q]];
             z += (sum == 0);
         }
         z = __reduce_add_sync(0xffffffffu, z);
-        if ((threadIdx.x & 31u) == 0 && z) atomicAdd(&s_z, z);
-        __syncthreads();
-        uint32_t *mycount = reinterpret_cast<uint32_t *>(mine + 64);
-        if (threadIdx.x == 0 && s_z) atomicAdd(mycount, s_z);      // region word 16 was zeroed by the host before the launch
-        __threadfence_system();
+        if ((threadIdx.x & 31u) == 0 && z) atomicAdd(reinterpret_cast<uint32_t *>(result + 3), z);
         grid.sync();
-        if (gtid == 0) st_release_sys(reinterpret_cast<uint32_t *>(mine), epoch + 24u);
-        if (gtid == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long want = (unsigned long long)(epoch + 24u);
+            const unsigned long long msg = (want << 32) | (unsigned long long)__ldcg(reinterpret_cast<const uint32_t *>(result + 3));
+            for (int r = 0; r < n_ranks; r++)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(reinterpret_cast<unsigned long long *>(peers.base[r]) + rank), "l"(msg) : "memory");
             uint32_t tot = 0;
             for (int r = 0; r < n_ranks; r++) {
-                const uint32_t *pf = reinterpret_cast<const uint32_t *>(peers.base[r]);
-                unsigned long long spins = 0;
-                while ((int32_t)(ld_acquire_sys(pf) - (epoch + 24u)) < 0) { if (++spins > (1ull << 28)) { result[2] = 1; break; } __nanosleep(64); }
-                tot += ld_acquire_sys(pf + 16);
+                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(peers.base[rank]) + r;
+                unsigned long long w, spins = 0;
+                for (;;) {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                    if ((w >> 32) == want) break;
+                    if (++spins > (1ull << 26)) { result[2] = 1; break; }
+                }
+                tot += (uint32_t)w;
             }
             result[3] = (int32_t)tot;
+            result[0] = k < 20 ? k : 19; result[1] = conv;
         }
     }
-    if (gtid == 0) { result[0] = k < 20 ? k : 19; result[1] = conv; }
 }
 
 // purged = #lists whose final abundances sum to exactly 0  (:394-404)
