@@ -397,7 +397,10 @@ def run_ours(args):
                          "full_scan_gbs": full_scan, "kernel_share_of_step": dec_ms / step_ms},
             "e2e": {"value": e2e_value, "unit": "M alignments/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(tim2["h2d_bytes"] // e2e_steps), "d2h_bytes_per_step": int(tim2["d2h_bytes"] // e2e_steps),
-                    "host_ingest_gbs": (tim2["h2d_bytes"] / e2e_steps) / (e2e_ms * 1e-3) / 1e9},
+                    "host_ingest_gbs": (tim2["h2d_bytes"] / e2e_steps) / (e2e_ms * 1e-3) / 1e9,
+                    "bam_gbs": raw.nbytes / (e2e_ms * 1e-3) / 1e9,
+                    "h2d_mode": ("zero-copy: decode windows pulled from the pinned host batch over PCIe (h2d bytes = window chunks requested"
+                                 " + offset index DMA; SEQ/QUAL never leave the host)") if tim2.get("zero_copy_chunks", 0) else "staged: whole batch DMA"},
             "gpu_launches": int(tim["kernel_launches"]),
             "clocks": clocks,
         }

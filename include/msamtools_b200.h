@@ -204,6 +204,7 @@ typedef struct msg_timing {
     uint64_t slow_records;   /* records parsed by the global-memory slow path                    */
     uint64_t fused_chunks;   /* chunks that went through the fused besthit->profile pass          */
     uint64_t fused_fallbacks;/* ... of which the guard sent to the general pipeline               */
+    uint64_t zero_copy_chunks;/* msg_push chunks decoded straight from pinned host memory (no bulk H2D) */
 } msg_timing;
 int  msg_get_timing(msg_ctx *ctx, msg_timing *t, int reset);
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of this

@@ -5,6 +5,6 @@ in include/msamtools_b200.h; importing this package does not touch the GPU, but 
 Context does and fails loudly when the library or a device is missing (no CPU fallback).
 """
 from . import _lib
-from .api import Context, MsgError, index_records, split_point, nccl_unique_id, parse_multi
+from .api import Context, MsgError, PinnedBuffer, index_records, split_point, nccl_unique_id, parse_multi
 
-__all__ = ["Context", "MsgError", "index_records", "split_point", "nccl_unique_id", "parse_multi", "_lib"]
+__all__ = ["Context", "MsgError", "PinnedBuffer", "index_records", "split_point", "nccl_unique_id", "parse_multi", "_lib"]

@@ -45,6 +45,7 @@ class MsgTiming(C.Structure):
         ("decode_ms", C.c_double), ("decode_launches", C.c_uint64), ("total_ms", C.c_double),
         ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("alg_bytes", C.c_uint64), ("slow_records", C.c_uint64), ("fused_chunks", C.c_uint64), ("fused_fallbacks", C.c_uint64),
+        ("zero_copy_chunks", C.c_uint64),
     ]
 
 

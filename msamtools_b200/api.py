@@ -195,6 +195,31 @@ class Context:
         return {k: getattr(t, k) for k, _ in L.MsgTiming._fields_}
 
 
+class PinnedBuffer:
+    """Page-locked host memory from msg_host_alloc as a numpy uint8 array (`.array`).  msg_push decodes such buffers in
+    place (zero-copy over PCIe) when the fused filter->profile pass applies; free with close() or a `with` block."""
+
+    def __init__(self, nbytes, device=0):
+        self.lib = L.load()
+        self.ptr = C.c_void_p()
+        rc = self.lib.msg_host_alloc(int(device), int(nbytes), C.byref(self.ptr))
+        if rc != 0:
+            raise RuntimeError(f"msg_host_alloc failed ({rc}): {self.lib.msg_last_error(None).decode()}")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(max(int(nbytes), 1),))[:int(nbytes)]
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.lib.msg_host_free(self.ptr)
+            self.ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 def index_records(raw):
     """Host offset index over an uncompressed BAM record stream (msg_index_records)."""
     lib = L.load()

@@ -87,6 +87,7 @@ struct msg_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     bool has_filter = false, need_stats = false, cov_fused = false;
+    uint64_t zc_chunks = 0;                           // chunks decoded straight from pinned host memory
     uint32_t lay_lpr = 0, lay_hc = 0, lay_tc = 0;     // decode window layout (probe_layout)
     uint32_t decode_mode = 0;
 
@@ -418,8 +419,11 @@ int probe_layout(msg_ctx *c, const uint8_t *h_raw, const uint64_t *h_off, const 
     return MSG_OK;
 }
 
+// zero_copy: d_raw is a device view of the caller's pinned HOST buffer h_raw (msg_push); the decode kernel then pulls
+// only the 16-byte chunks of its windows over PCIe.  If the chunk has to go through the general pipeline after all, it
+// is staged into device memory first.
 int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readable, const uint64_t *d_off, uint64_t n,
-              const uint8_t *h_raw = nullptr, const uint64_t *h_off = nullptr)
+              const uint8_t *h_raw = nullptr, const uint64_t *h_off = nullptr, bool zero_copy = false)
 {
     const msg_config &g = c->cfg;
     if (n >= 0xffffffffull) return fail(c, MSG_EINVAL, "a chunk may hold at most 2^32-2 records");
@@ -474,6 +478,13 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
             c->ev_total.push_back({t0, t1});
             return MSG_OK;
         }
+    }
+    if (zero_copy) {                                 // fused pass declined the chunk: the kernels below re-read records, stage them
+        CU(c->raw.reserve(nbytes + 64));
+        CU(cudaMemcpyAsync(c->raw.p, h_raw, nbytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync((uint8_t *)c->raw.p + nbytes, 0, 64, c->stream));
+        c->h2d_bytes += nbytes;
+        c->cur_raw = d_raw = c->raw.as<uint8_t>();
     }
     // ---- filter stage -> stream of kept records in reference output order
     const uint32_t *stream = nullptr; uint64_t m = n;
@@ -795,7 +806,26 @@ int msg_push(msg_ctx *c, const uint8_t *raw, size_t nbytes, const uint64_t *rec_
     if (!c || (nrec && (!raw || !rec_off))) return MSG_EINVAL;
     CU(cudaSetDevice(c->cfg.device));
     if (nrec == 0) { c->cur_n = 0; c->n_kept = 0; c->out_bytes = 0; return MSG_OK; }
-    CU(c->raw.reserve(nbytes + 64)); CU(c->off.reserve((nrec + 1) * 8));
+    CU(c->off.reserve((nrec + 1) * 8));
+    // Pinned (mapped) host buffer + fused filter->profile pass: do not copy the chunk at all.  The decode kernel reads
+    // its head / tail windows straight from host memory, so only ~55 % of the BAM bytes cross PCIe (64-byte granules
+    // around the windows; SEQ/QUAL stay on the host).  MSG_ZERO_COPY=0 forces the staged copy.
+    static const bool zc_allowed = !(getenv("MSG_ZERO_COPY") && atoi(getenv("MSG_ZERO_COPY")) == 0);
+    if (zc_allowed && c->fused_enabled && c->cfg.want_profile && !((uintptr_t)raw & 15u)) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, raw) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            CU(cudaMemcpyAsync(c->off.p, rec_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+            c->h2d_bytes += (nrec + 1) * 8;
+            c->zc_chunks++;
+            const uint64_t before = c->h2d_bytes;
+            int rc = run_chunk(c, static_cast<const uint8_t *>(at.devicePointer), nbytes, (nbytes + 15) & ~(size_t)15, c->off.as<uint64_t>(), nrec, raw, rec_off, true);
+            // bytes the decode kernel asked for (window chunks); a staged fallback has already counted the whole chunk
+            if (c->h2d_bytes == before) c->h2d_bytes += (uint64_t)nrec * (c->lay_hc + c->lay_tc) * 16;
+            return rc;
+        }
+        cudaGetLastError();
+    }
+    CU(c->raw.reserve(nbytes + 64));
     CU(cudaMemcpyAsync(c->raw.p, raw, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync((uint8_t *)c->raw.p + nbytes, 0, 64, c->stream));
     CU(cudaMemcpyAsync(c->off.p, rec_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1106,10 +1136,10 @@ int msg_get_timing(msg_ctx *c, msg_timing *t, int reset)
     t->decode_ms = c->decode_ms; t->decode_launches = c->decode_launches; t->total_ms = c->total_ms;
     t->kernel_launches = c->kernel_launches; t->h2d_bytes = c->h2d_bytes; t->d2h_bytes = c->d2h_bytes;
     t->alg_bytes = acct[0]; t->slow_records = acct[1];
-    t->fused_chunks = c->fused_chunks; t->fused_fallbacks = c->fused_fallbacks;
+    t->fused_chunks = c->fused_chunks; t->fused_fallbacks = c->fused_fallbacks; t->zero_copy_chunks = c->zc_chunks;
     if (reset) {
         c->decode_ms = c->total_ms = 0; c->decode_launches = c->kernel_launches = 0; c->h2d_bytes = c->d2h_bytes = 0;
-        c->fused_chunks = c->fused_fallbacks = 0;
+        c->fused_chunks = c->fused_fallbacks = 0; c->zc_chunks = 0;
         CU(cudaMemset(c->d_acct, 0, 16));
     }
     return MSG_OK;

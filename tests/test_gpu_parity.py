@@ -373,6 +373,58 @@ def test_fused_guard_fallback(m, oracle):
         assert (st["mapped_inserts"], st["uniq"], st["multi"], st["purged"]) == (est["mapped_inserts"], est["uniq"], est["multi"], est["purged"])
 
 
+@pytest.mark.parametrize("mode", ["proportional", "equal"])
+def test_zero_copy_push(m, oracle, mixed, mode):
+    """msg_push on a pinned host buffer: the decode kernel reads its windows straight from host memory (no bulk H2D);
+    same results as the staged copy and the oracle.  Unaligned sub-chunks silently take the staged path."""
+    raw, off, tlen, p = mixed
+    n = len(off) - 1
+    opts = dict(l=80, p=95, z=80, besthit=True)
+    idx = oracle.filter_stream(raw, off, oracle.filter_cfg(**opts))
+    eab, est, eui, ed = oracle.profile(raw, off, idx, len(tlen), SHARE[mode])
+    with m.PinnedBuffer(raw.nbytes) as pb, m.Context(profile=True, multi=mode, kept=False, n_targets=len(tlen), **opts) as ctx:
+        pb.array[:] = raw
+        ctx.push(pb.array, off)
+        assert ctx.kept_count() == len(idx)
+        ui, d = ctx.pull_counts()
+        ab, st = ctx.finish_profile()
+        t = ctx.timing(reset=True)
+        assert (t["zero_copy_chunks"], t["fused_chunks"], t["fused_fallbacks"]) == (1, 1, 0)
+        assert t["h2d_bytes"] < raw.nbytes                     # windows + offsets only
+        assert np.array_equal(ui, eui) and close(d, ed) and close(ab, eab)
+        for k in ("mapped_inserts", "uniq", "multi", "purged", "iterations", "converged", "n_lists", "n_entries"):
+            assert st[k] == est[k], k
+        # chunked: sub-chunks start wherever a QNAME group starts, so most are not 16-byte aligned
+        ctx.reset()
+        cuts = [0, m.split_point(raw, off, n // 3), m.split_point(raw, off, 2 * n // 3), n]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            ctx.push(pb.array[int(off[a]):int(off[b])], off[a:b + 1] - off[a])
+        ab2, st2 = ctx.finish_profile()
+        ui2, _ = ctx.pull_counts()
+        assert np.array_equal(ui2, eui) and close(ab2, eab) and st2["n_lists"] == est["n_lists"]
+
+
+def test_zero_copy_guard_fallback(m, oracle):
+    """zero-copy chunk that the fused pass declines (equal QNAME hashes around a dropped record): it is staged into
+    device memory and rerun on the general pipeline."""
+    a = "\t0\t%s\t10\t60\t%dM\t*\t0\t0\t%s\t%s\tNM:i:0\tAS:i:%d"
+    rec = lambda n, ref, ln, sc: n + a % (ref, ln, "A" * ln, "I" * ln, sc)
+    text = HDR + "\n".join([rec("u", "C", 20, 9), rec("x", "A", 20, 10), rec("y", "A", 5, 5), rec("x", "B", 20, 20), rec("z", "C", 20, 7)]) + "\n"
+    s = _sam(text)
+    opts = dict(l=8, besthit=True)
+    idx = oracle.filter_stream(s.raw, s.off, oracle.filter_cfg(**opts))
+    eab, est, eui, ed = oracle.profile(s.raw, s.off, idx, 3, SHARE["proportional"])
+    with m.PinnedBuffer(len(s.raw)) as pb, m.Context(profile=True, multi="proportional", kept=False, n_targets=3, **opts) as ctx:
+        pb.array[:] = s.raw
+        ctx.push(pb.array, s.off)
+        ui, d = ctx.pull_counts()
+        ab, st = ctx.finish_profile()
+        t = ctx.timing()
+    assert (t["zero_copy_chunks"], t["fused_chunks"], t["fused_fallbacks"]) == (1, 1, 1)
+    assert ui.tolist() == eui.tolist() and close(ab, eab)
+    assert (st["mapped_inserts"], st["uniq"], st["multi"], st["purged"]) == (est["mapped_inserts"], est["uniq"], est["multi"], est["purged"])
+
+
 def test_huge_group(m, oracle):
     # one QNAME with 5000 alignments over 40 references: exercises the oversized-group serial kernel
     rng = np.random.default_rng(7)
