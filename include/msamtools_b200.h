@@ -147,7 +147,10 @@ int  msg_index_records(const uint8_t *raw, size_t nbytes, uint64_t *rec_off, siz
 size_t msg_split_point(const uint8_t *raw, const uint64_t *rec_off, size_t nrec, size_t want);
 
 /* ------------------------------------------------------------------ data path */
-/* Host buffers (pinned or pageable).  H2D copy + all kernels for this chunk. */
+/* Host buffers (pinned or pageable).  H2D copy + all kernels for this chunk.  A pinned, mapped, 16-byte
+ * aligned buffer (msg_host_alloc) is not copied when the fused filter->profile pass applies
+ * (do_filter, hit_mode, want_profile and no kept/records/coverage): the decode kernel reads its
+ * windows of each record in place over PCIe (msg_timing.zero_copy_chunks; MSG_ZERO_COPY=0 disables). */
 int  msg_push(msg_ctx *ctx, const uint8_t *raw, size_t nbytes,
               const uint64_t *rec_off, size_t nrec);
 /* Same, but the chunk already lives in device memory (device pointers).      */
@@ -184,8 +187,9 @@ int  msg_pull_stats(msg_ctx *ctx, size_t nrec, int32_t *alen, int32_t *qlen, int
 /* raw counters before the abundance step: ui_insert_count (doubled, u32) and
  * d_insert_count; either may be NULL.  Local to this rank (no allreduce).    */
 int  msg_pull_counts(msg_ctx *ctx, uint32_t *ui, double *d);
-/* mInsertCountToAbundanceMatrix: U = ui/2 (+ d | proportional loop).  With
- * n_ranks > 1 this performs the NCCL allreduce(s); every rank gets the result. */
+/* mInsertCountToAbundanceMatrix: U = ui/2 (+ d | proportional loop).  With n_ranks > 1 every rank
+ * must call it and gets the same result: proportional mode combines the ranks inside one
+ * cooperative kernel over CUDA-IPC peer memory, the other modes (or MSG_NO_P2P=1) through NCCL.  */
 int  msg_finish_profile(msg_ctx *ctx, double *abundance /*[n_features]*/, msg_profile_stats *st);
 /* per target: covered flag, #positions with depth != 0, sum of depths
  * (msam_coverage.c:189-219).  With n_ranks > 1: allreduce first.             */
