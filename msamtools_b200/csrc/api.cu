@@ -617,7 +617,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     } else if (g.want_profile && g.n_features != g.n_targets) { int rc = fail(nullptr, MSG_EINVAL, "identity fmap needs n_features == n_targets"); msg_destroy(ctx); return rc; }
     if (g.want_profile) {
         CUC(cudaMalloc(&ctx->d_ui, F * 4)); CUC(cudaMalloc(&ctx->d_d, F * 8)); CUC(cudaMalloc(&ctx->d_counters, 32));
-        CUC(cudaMalloc(&ctx->d_U, F * 8)); CUC(cudaMalloc(&ctx->d_a, F * 8)); CUC(cudaMalloc(&ctx->d_inc, F * 8));
+        CUC(cudaMalloc(&ctx->d_U, F * 8)); CUC(cudaMalloc(&ctx->d_a, F * 8)); CUC(cudaMalloc(&ctx->d_inc, 3 * F * 8));
         CUC(cudaHostAlloc((void **)&ctx->h_ab, F * 8, cudaHostAllocPortable));
         CUC(cudaMalloc(&ctx->d_partial, ((F + 255) / 256) * 8)); CUC(cudaMalloc(&ctx->d_delta, 8 * 20)); CUC(cudaMalloc(&ctx->d_purged, 4));
         CUC(cudaMalloc(&ctx->d_ui_tmp, F * 4)); CUC(cudaMalloc(&ctx->d_d_tmp, F * 8)); CUC(cudaMalloc(&ctx->d_fcnt, 32)); CUC(cudaMalloc(&ctx->d_cursor, 8));
@@ -975,7 +975,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_multi_kernel<true>, 256, shm));
                 else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_multi_kernel<false>, 256, shm));
             } else {
-                if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<true>, 256, shm));
+                if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_smem_kernel, 256, shm));
                 else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<false>, 256, shm));
             }
             if (per_sm < 1 && coop_multi) return fail(c, MSG_ECUDA, "cannot launch the cooperative PropSharing kernel (F = %u needs too much shared memory?)", F);
@@ -1004,7 +1004,8 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                     c->em_epoch += 32;
                     CU(cudaMemcpyAsync(hc, hc_dev, 24, cudaMemcpyDeviceToHost, c->stream));
                 } else {
-                    if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<true>, dim3(grid), dim3(256), args, shm, c->stream));
+                    void *sargs[] = {&a0, &a1, &a2, &nl_arg, &U, &av, &inc, &F_arg, &dout, &d_res};
+                    if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_smem_kernel, dim3(grid), dim3(256), sargs, shm, c->stream));
                     else    CU(cudaLaunchCooperativeKernel((void *)em_loop_kernel<false>, dim3(grid), dim3(256), args, shm, c->stream));
                 }
                 LAUNCHED(c);

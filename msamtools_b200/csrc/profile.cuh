@@ -416,7 +416,7 @@ __global__ void em_init_kernel(const uint32_t *ui, const double *d, int use_d, d
     double u = 1.0 * ui[i] / 2;                                         // :286
     if (use_d) u += d[i];                                               // :305
     U[i] = u; a[i] = u;
-    if (inc) inc[i] = 0.0;
+    if (inc) { inc[i] = 0.0; inc[(size_t)n + i] = 0.0; inc[2 * (size_t)n + i] = 0.0; }      // three buffers (em_loop_smem_kernel)
 }
 __global__ void em_init_from_U_kernel(const double *U, double *a, uint32_t n)
 {
@@ -476,6 +476,32 @@ __device__ __forceinline__ void em_share_list(const int32_t *mm_fid, uint32_t b,
     for (uint32_t q = 4; q < n; q++) { const int32_t f = mm_fid[b + q]; atomicAdd(iv + f, av[f] * inv); }
 }
 
+// Two lists at once: the gather is latency bound (offsets -> features -> shared a[] -> divide -> atomics), so a
+// thread keeps the loads of two independent lists in flight.  Same arithmetic per list as em_share_list.
+__device__ __forceinline__ void em_share_list_pair(const int32_t *mm_fid, uint32_t b0, uint32_t n0, uint32_t b1, uint32_t n1,
+                                                   const double *av, double *iv)
+{
+    int32_t f0[4], f1[4]; double a0[4], a1[4];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) { f0[j] = j < n0 ? mm_fid[b0 + j] : 0; f1[j] = j < n1 ? mm_fid[b1 + j] : 0; }
+    double s0 = 0, s1 = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) { if (j < n0) { a0[j] = av[f0[j]]; s0 += a0[j]; } if (j < n1) { a1[j] = av[f1[j]]; s1 += a1[j]; } }
+    for (uint32_t q = 4; q < n0; q++) s0 += av[mm_fid[b0 + q]];
+    for (uint32_t q = 4; q < n1; q++) s1 += av[mm_fid[b1 + q]];
+    const double i0 = s0 > 0 ? 1.0 / s0 : 0.0, i1 = s1 > 0 ? 1.0 / s1 : 0.0;
+    if (s0 > 0) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) if (j < n0) atomicAdd(iv + f0[j], a0[j] * i0);
+        for (uint32_t q = 4; q < n0; q++) { const int32_t f = mm_fid[b0 + q]; atomicAdd(iv + f, av[f] * i0); }
+    }
+    if (s1 > 0) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) if (j < n1) atomicAdd(iv + f1[j], a1[j] * i1);
+        for (uint32_t q = 4; q < n1; q++) { const int32_t f = mm_fid[b1 + q]; atomicAdd(iv + f, av[f] * i1); }
+    }
+}
+
 // a_new = U + inc; flush < 1e-20; per-block partial of sum (a_new - a_old)^2 in a fixed order  (:369-379)
 __global__ void __launch_bounds__(256) em_update_kernel(const double *U, const double *inc, double *a, double *partial, uint32_t n)
 {
@@ -532,7 +558,11 @@ __global__ void __launch_bounds__(256) em_loop_kernel(const uint32_t *mm_off, co
         }
         const double *av = SMEM ? sa : a;
         double *iv = SMEM ? si + (size_t)((threadIdx.x >> 5) % ncopy) * F : inc;
-        for (uint32_t l = gtid; l < nlists; l += gsz) em_share_list(mm_fid, mm_off[l], mm_len[l], av, iv);
+        {
+            uint32_t l = gtid;
+            for (; l + gsz < nlists; l += 2 * gsz) em_share_list_pair(mm_fid, mm_off[l], mm_len[l], mm_off[l + gsz], mm_len[l + gsz], av, iv);
+            if (l < nlists) em_share_list(mm_fid, mm_off[l], mm_len[l], av, iv);
+        }
         if (SMEM) {
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) {
@@ -574,6 +604,73 @@ __global__ void __launch_bounds__(256) em_loop_kernel(const uint32_t *mm_off, co
         const uint32_t b = mm_off[l], e = b + mm_len[l];
         double sum = 0;
         for (uint32_t q = b; q < e; q++) sum += a[mm_fid[q]];
+        z += (sum == 0);
+    }
+    z = warp_sum_u32(z);
+    if ((threadIdx.x & 31) == 0 && z) atomicAdd(reinterpret_cast<uint32_t *>(result + 3), z);
+}
+
+// Single GPU, F <= EM_SMEM_F: the loop with ONE grid barrier per iteration.  Every CTA keeps the whole abundance vector
+// in shared memory and, after the barrier that completes inc[], redoes the (tiny) update a = U + inc and the delta
+// reduction for ALL features itself -- same data, same order, so every CTA holds bit-identical a[] and takes the same
+// stop decision without a second barrier or a partial-sum array.  inc[] is triple buffered: CTA 0 clears buffer
+// (k+2) % 3 after barrier k; its last readers (update k-1) are before barrier k, its next writers (gather k+2) after
+// barrier k+1.  inc3 must arrive zeroed (3 * F doubles).
+__global__ void __launch_bounds__(256) em_loop_smem_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
+                                                           const double *U, double *a, double *inc3, uint32_t F,
+                                                           double *delta_out, int32_t *result)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double s_em[];
+    __shared__ double s_red[256];
+    const uint32_t ncopy = em_copies(F);
+    double *sa = s_em, *si = s_em + F;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) sa[i] = a[i];
+    int k = 1, conv = 0;
+    for (; k < 20; k++) {
+        for (uint32_t i = threadIdx.x; i < F * ncopy; i += blockDim.x) si[i] = 0.0;
+        __syncthreads();
+        // gather: s = sum a[f] in list order; inc[f] += a[f]/s            (:341-365)
+        double *iv = si + (size_t)((threadIdx.x >> 5) % ncopy) * F;
+        uint32_t l = gtid;
+        for (; l + gsz < nlists; l += 2 * gsz) em_share_list_pair(mm_fid, mm_off[l], mm_len[l], mm_off[l + gsz], mm_len[l + gsz], sa, iv);
+        if (l < nlists) em_share_list(mm_fid, mm_off[l], mm_len[l], sa, iv);
+        __syncthreads();
+        double *inc = inc3 + (size_t)(k % 3) * F;
+        for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) {
+            double v = 0.0;
+            for (uint32_t cp = 0; cp < ncopy; cp++) v += si[(size_t)cp * F + i];
+            if (v != 0.0) atomicAdd(inc + i, v);
+        }
+        grid.sync();
+        if (blockIdx.x == 0) { double *nxt = inc3 + (size_t)((k + 2) % 3) * F; for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) nxt[i] = 0.0; }
+        // update (every CTA, all features): a = U + inc, flush < 1e-20, delta = sum diff^2 / F   (:369-383)
+        double dd = 0;
+        for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) {
+            double an = U[i] + __ldcg(inc + i);
+            if (an < 1e-20) an = 0;
+            const double diff = an - sa[i];
+            dd += diff * diff;
+            sa[i] = an;
+        }
+        s_red[threadIdx.x] = dd;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+        const double delta = s_red[0] / F;
+        __syncthreads();
+        if (gtid == 0) delta_out[k - 1] = delta;
+        if (delta < 1e-10) { conv = 1; break; }
+    }
+    if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) a[i] = sa[i];
+    if (gtid == 0) { result[0] = k < 20 ? k : 19; result[1] = conv; }
+    // purged = #lists whose final abundances sum to exactly 0  (:394-404), from this CTA's own (identical) copy of a[]
+    uint32_t z = 0;
+    for (uint32_t l = gtid; l < nlists; l += gsz) {
+        const uint32_t b = mm_off[l], e = b + mm_len[l];
+        double sum = 0;
+        for (uint32_t q = b; q < e; q++) sum += sa[mm_fid[q]];
         z += (sum == 0);
     }
     z = warp_sum_u32(z);
@@ -676,7 +773,11 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
         }
         const double *av = SMEM ? sa : a;
         double *iv = SMEM ? si + (size_t)((threadIdx.x >> 5) % ncopy) * F : inc;
-        for (uint32_t l = gtid; l < nlists; l += gsz) em_share_list(mm_fid, mm_off[l], mm_len[l], av, iv);
+        {
+            uint32_t l = gtid;
+            for (; l + gsz < nlists; l += 2 * gsz) em_share_list_pair(mm_fid, mm_off[l], mm_len[l], mm_off[l + gsz], mm_len[l + gsz], av, iv);
+            if (l < nlists) em_share_list(mm_fid, mm_off[l], mm_len[l], av, iv);
+        }
         if (SMEM) {
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) {
