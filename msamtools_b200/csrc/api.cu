@@ -818,7 +818,7 @@ int msg_push(msg_ctx *c, const uint8_t *raw, size_t nbytes, const uint64_t *rec_
             c->h2d_bytes += (nrec + 1) * 8;
             c->zc_chunks++;
             const uint64_t before = c->h2d_bytes;
-            int rc = run_chunk(c, static_cast<const uint8_t *>(at.devicePointer), nbytes, (nbytes + 15) & ~(size_t)15, c->off.as<uint64_t>(), nrec, raw, rec_off, true);
+            int rc = run_chunk(c, static_cast<const uint8_t *>(at.devicePointer), nbytes, nbytes & ~(size_t)15, c->off.as<uint64_t>(), nrec, raw, rec_off, true);
             // bytes the decode kernel asked for (window chunks); a staged fallback has already counted the whole chunk
             if (c->h2d_bytes == before) c->h2d_bytes += (uint64_t)nrec * (c->lay_hc + c->lay_tc) * 16;
             return rc;
@@ -838,7 +838,7 @@ int msg_push_device(msg_ctx *c, const uint8_t *d_raw, size_t nbytes, const uint6
     if (!c || (nrec && (!d_raw || !d_rec_off))) return MSG_EINVAL;
     if ((uintptr_t)d_raw & 15u) return fail(c, MSG_EINVAL, "device chunk must be 16-byte aligned");
     CU(cudaSetDevice(c->cfg.device));
-    return run_chunk(c, d_raw, nbytes, (nbytes + 15) & ~(size_t)15, d_rec_off, nrec);
+    return run_chunk(c, d_raw, nbytes, nbytes & ~(size_t)15, d_rec_off, nrec);       // never read past the caller's nbytes
 }
 
 int msg_kept_count(msg_ctx *c, size_t *n_kept) { if (!c || !n_kept) return MSG_EINVAL; *n_kept = c->n_kept; return MSG_OK; }

@@ -32,7 +32,7 @@ struct DecodeParams {
     const uint8_t  *raw;
     const uint64_t *off;
     uint64_t n;
-    uint64_t nbytes_readable;       // bytes that may be touched (>= round_up(nbytes,16))
+    uint64_t nbytes_readable;       // bytes the 16-byte window loads may touch (multiple of 16; may be < nbytes for caller-owned buffers)
     // outputs (any may be null)
     int32_t  *tid;
     uint32_t *fb;
@@ -405,11 +405,14 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
     const uint64_t o = s_off[t], len = s_off[t + 1] - o;
     const uint32_t rel = (uint32_t)(o & 15u);
     uint32_t arel = 0;
-    bool slow = force_slow;
-    RecCore c = force_slow ? parse_core(GlAcc{p.raw + o}, len) : parse_core(SmAcc{slot, rel}, len);
+    bool slow = force_slow || o + 36 > p.nbytes_readable;            // (fixed header not fully staged: chunk's last, tiny record)
+    RecCore c = slow ? parse_core(GlAcc{p.raw + o}, len) : parse_core(SmAcc{slot, rel}, len);
     // does the record fit its windows?
     const uint32_t need_head = 36 + c.lq + ((mode & DM_NEED_CIGAR) ? 4 * c.nc : 0);
     if (rel + need_head > 16 * hc) slow = true;
+    // window chunks at or beyond nbytes_readable were not loaded (caller-owned buffers are only read up to the last whole
+    // 16-byte chunk): the chunk's final record(s) then take the byte-wise path
+    if (o + need_head > p.nbytes_readable || ((mode & DM_NEED_AUX) && c.aux_len && o + c.rec_len > p.nbytes_readable)) slow = true;
     if ((mode & DM_NEED_AUX) && c.aux_len) {
         const uint64_t wend = (o + c.rec_len + 15ull) & ~15ull;           // end of the tail window
         const uint64_t astart = o + c.aux_off;
