@@ -462,8 +462,11 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
     { int prc = probe_layout(c, h_raw, h_off, d_raw, d_off, nbytes, n, (mode & DM_NEED_CIGAR) != 0, (mode & DM_NEED_AUX) != 0); if (prc) return prc; }
     p.head_chunks = c->lay_hc; p.tail_chunks = c->lay_tc;
     CU(cudaEventRecord(k0, c->stream));
-    if (c->lay_lpr == 8) decode_kernel<8><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p);
-    else                 decode_kernel<16><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p);
+    // L2 fill granularity of the window loads: 64-byte granules (.L2::64B) or whole 128-byte lines.  MSG_L2_GRANULE=64|128 overrides.
+    static const int g_env = getenv("MSG_L2_GRANULE") ? atoi(getenv("MSG_L2_GRANULE")) : 0;
+    const bool g64 = g_env ? g_env == 64 : true;
+    if (c->lay_lpr == 8) { if (g64) decode_kernel<8, true><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); else decode_kernel<8, false><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); }
+    else                 { if (g64) decode_kernel<16, true><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); else decode_kernel<16, false><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); }
     LAUNCHED(c);
     CU(cudaEventRecord(k1, c->stream));
     c->ev_decode.push_back({k0, k1});

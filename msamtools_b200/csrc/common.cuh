@@ -46,6 +46,14 @@ __device__ __forceinline__ uint4 ldg_stream128(const uint4 *p)
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// same without the qualifier (L2 fills whole 128-byte lines)
+__device__ __forceinline__ uint4 ldg_stream128_line(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 
 __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
 {

@@ -477,7 +477,7 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
 // dependent DRAM latencies (offsets -> windows) and keeps the issue slots of the (low-ILP) parser
 // busy.  A persistent, register-staged software pipeline was measured and lost (profiles/r01_notes.md):
 // at the 4 CTAs/SM its 123 registers allow, the parser alone cannot fill the schedulers.
-template <int LPR>
+template <int LPR, bool G64>
 __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ DecodeParams p)
 {
     constexpr int SLOT_WORDS = LPR * 4 + 1;            // odd stride: thread-per-slot reads are conflict-free
@@ -518,7 +518,8 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
             v[it] = make_uint4(0, 0, 0, 0);
             if (go && r < nrec) {
                 const uint32_t cidx = (head ? s_hb[r] : s_tb[r]) + sub;     // a tail window that starts before the buffer wraps to a huge index
-                if (cidx < nchunks) v[it] = ldg_stream128(reinterpret_cast<const uint4 *>(p.raw) + cidx);
+                if (cidx < nchunks) v[it] = G64 ? ldg_stream128(reinterpret_cast<const uint4 *>(p.raw) + cidx)
+                                                : ldg_stream128_line(reinterpret_cast<const uint4 *>(p.raw) + cidx);
             }
         }
 #pragma unroll

@@ -33,11 +33,11 @@ for name, preset, opts in CASES:
             if opts.get("profile"):
                 return ctx.finish_profile()[1]
             return ctx.finish_coverage()[0].sum()
-        for _ in range(2):
+        for _ in range(30):           # also brings the SM clocks up: short loops right after the (CPU-side) data generation run at idle clocks
             res = step()
         ctx.timing(reset=True)
         ctx.sync(); ctx.mark(0)
-        K = 5
+        K = 40
         for _ in range(K):
             res = step()
         ctx.mark(1); ms = ctx.elapsed_ms(0, 1) / K
