@@ -96,7 +96,10 @@ def dist_env():
 def make_batch(records, rank, pinned=True):
     """configs[1]-shaped shard for this rank, generated straight into pinned host memory."""
     from msamtools_b200 import synth
-    p = synth.make_params("community", n_records=records, seed=13579, qname_base=rank * 1_000_000_000)
+    # disjoint insert numbers per rank; the stride keeps "sim%08llu" at 8 digits on every rank (up to 9 ranks at the default
+    # size), so that per-GPU work really is the same -- a 1e9 stride gave ranks >= 1 two more QNAME bytes per record
+    stride = 10_000_000 if records <= 20_000_000 else 1_000_000_000
+    p = synth.make_params("community", n_records=records, seed=13579, qname_base=rank * stride)
     cap_b, cap_r = (records + 64) * 330, records + 66
     raw = off = None
     if pinned:

@@ -122,6 +122,7 @@ struct msg_ctx {
     uint32_t *d_stamp = nullptr; uint32_t stamp_next = 0;
     double *d_U = nullptr, *d_a = nullptr, *d_inc = nullptr, *d_partial = nullptr, *d_delta = nullptr;
     uint32_t *d_purged = nullptr;
+    uint32_t *d_bflag = nullptr;               // broadcast flag of em_loop_multi_kernel (monotonic epochs)
 
     // coverage accumulators
     int32_t *d_diff = nullptr, *d_depth = nullptr; uint8_t *d_covered = nullptr;
@@ -622,7 +623,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
         CUC(cudaMalloc(&ctx->d_ui, F * 4)); CUC(cudaMalloc(&ctx->d_d, F * 8)); CUC(cudaMalloc(&ctx->d_counters, 32));
         CUC(cudaMalloc(&ctx->d_U, F * 8)); CUC(cudaMalloc(&ctx->d_a, F * 8)); CUC(cudaMalloc(&ctx->d_inc, 3 * F * 8));
         CUC(cudaHostAlloc((void **)&ctx->h_ab, F * 8, cudaHostAllocPortable));
-        CUC(cudaMalloc(&ctx->d_partial, ((F + 255) / 256) * 8)); CUC(cudaMalloc(&ctx->d_delta, 8 * 20)); CUC(cudaMalloc(&ctx->d_purged, 4));
+        CUC(cudaMalloc(&ctx->d_partial, ((F + 255) / 256) * 8)); CUC(cudaMalloc(&ctx->d_delta, 8 * 20)); CUC(cudaMalloc(&ctx->d_purged, 4)); CUC(cudaMalloc(&ctx->d_bflag, 8)); CUC(cudaMemset(ctx->d_bflag, 0, 8));
         CUC(cudaMalloc(&ctx->d_ui_tmp, F * 4)); CUC(cudaMalloc(&ctx->d_d_tmp, F * 8)); CUC(cudaMalloc(&ctx->d_fcnt, 32)); CUC(cudaMalloc(&ctx->d_cursor, 8));
         CUC(cudaMemset(ctx->d_ui_tmp, 0, F * 4)); CUC(cudaMemset(ctx->d_d_tmp, 0, F * 8));
         // the fused pass applies when the profile is the filter stage's only consumer (MSG_NO_FUSED=1 forces the general pipeline)
@@ -695,7 +696,7 @@ void msg_destroy(msg_ctx *c)
                       &c->csr_off, &c->csr_len, &c->csr_fid, &c->win, &c->t_ui, &c->t_d, &c->t_cnt, &c->t_cov};
     for (DevBuf *b : bufs) b->release();
     void *ptrs[] = {c->d_fmap, c->d_tlen, c->d_covbase, c->d_err, c->d_acct, c->d_total, c->d_ui, c->d_d, c->d_counters, c->d_stamp, c->d_U, c->d_a,
-                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_wl, c->d_ui_tmp, c->d_d_tmp, c->d_fcnt, c->d_cursor, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
+                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_bflag, c->d_wl, c->d_ui_tmp, c->d_d_tmp, c->d_fcnt, c->d_cursor, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_ab) cudaFreeHost(c->h_ab);
@@ -998,7 +999,10 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 uint32_t nl_lo = (uint32_t)(c->csr_lists & 0xffffu), nl_hi = (uint32_t)(c->csr_lists >> 16);   // two 16-bit halves, as in the NCCL path
                 uint32_t *hc_dev = nullptr;
                 if (g.n_ranks > 1) { CU(c->t_cnt.reserve(64)); hc_dev = c->t_cnt.as<uint32_t>(); }
-                void *margs[] = {&a0, &a1, &a2, &nl_arg, &ui_arg, &cnt_arg, &nl_lo, &nl_hi, &Uw, &av, &inc, &partial, &F_arg, &dout, &d_res, &hc_dev, &pt, &nr, &rk, &epoch};
+                double *totbuf = nullptr; uint32_t *bflag = c->d_bflag;
+                if (g.n_ranks > 1) { CU(c->t_d.reserve((size_t)F * 16)); totbuf = c->t_d.as<double>(); }
+                void *margs[] = {&a0, &a1, &a2, &nl_arg, &ui_arg, &cnt_arg, &nl_lo, &nl_hi, &Uw, &av, &inc, &partial, &F_arg, &dout, &d_res, &hc_dev,
+                                 &totbuf, &bflag, &pt, &nr, &rk, &epoch};
                 // inc, delta, d_res and the peer region's purged word were cleared by em_init_kernel
                 if (g.n_ranks > 1) {
                     // compute + collective in one kernel: increments are exchanged through peer memory inside the loop

@@ -715,6 +715,7 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
                                                             const uint32_t *ui, const uint32_t *counters, uint32_t nl_lo, uint32_t nl_hi,
                                                             double *U, double *a, double *inc, double *partial, uint32_t F,
                                                             double *delta_out, int32_t *result, uint32_t *hc_out,
+                                                            double *totbuf, uint32_t *bflag,
                                                             PeerTable peers, int n_ranks, int rank, uint32_t epoch)
 {
     namespace cg = cooperative_groups;
@@ -765,6 +766,59 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
                  [&](uint32_t i, double tot) { if (i < F) { const double u = tot / 2; U[i] = u; a[i] = u; inc[i] = 0.0; } else hc_out[i - F] = (uint32_t)tot; });
     grid.sync();
     int k = 1, conv = 0;
+    if (SMEM) {
+        // F <= EM_SMEM_F: ONE grid barrier per iteration.  After the barrier that completes inc[], CTA 0 exchanges the
+        // increments with the peers and broadcasts the rank-ordered totals through totbuf[k & 1] + a release flag; every
+        // CTA then redoes the F-sized update and the delta reduction from its own shared-memory a[] (same data, same order:
+        // bit-identical everywhere, no second barrier).  CTA 0 clears inc[] before it raises the flag, so the other CTAs'
+        // next gather (which starts only after they have seen the flag) adds into zeros.
+        for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) sa[i] = __ldcg(a + i);
+        for (; k < 20; k++) {
+            for (uint32_t i = threadIdx.x; i < F * ncopy; i += blockDim.x) si[i] = 0.0;
+            __syncthreads();
+            double *iv = si + (size_t)((threadIdx.x >> 5) % ncopy) * F;
+            uint32_t l = gtid;
+            for (; l + gsz < nlists; l += 2 * gsz) em_share_list_pair(mm_fid, mm_off[l], mm_len[l], mm_off[l + gsz], mm_len[l + gsz], sa, iv);
+            if (l < nlists) em_share_list(mm_fid, mm_off[l], mm_len[l], sa, iv);
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) {
+                double v = 0.0;
+                for (uint32_t cp = 0; cp < ncopy; cp++) v += si[(size_t)cp * F + i];
+                if (v != 0.0) atomicAdd(inc + i, v);
+            }
+            grid.sync();
+            double *tb = totbuf + (size_t)(k & 1) * F;
+            if (blockIdx.x == 0) {
+                exchange((uint32_t)k, (uint32_t)k & 1u,
+                         [&](uint32_t i) -> double { if (i >= F) return 0.0; const double v = __ldcg(inc + i); inc[i] = 0.0; return v; },
+                         [&](uint32_t i, double tot) { if (i < F) tb[i] = tot; });
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bflag), "r"(epoch + (uint32_t)k) : "memory");
+            }
+            if (threadIdx.x == 0) {
+                uint32_t seen;
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bflag) : "memory"); } while ((int32_t)(seen - (epoch + (uint32_t)k)) < 0);
+            }
+            __syncthreads();
+            double dd = 0;
+            for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) {
+                double an = U[i] + __ldcg(tb + i);
+                if (an < 1e-20) an = 0;
+                const double diff = an - sa[i];
+                dd += diff * diff;
+                sa[i] = an;
+            }
+            s_red[threadIdx.x] = dd;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+            const double delta = s_red[0] / F;
+            __syncthreads();
+            if (gtid == 0) delta_out[k - 1] = delta;
+            if (delta < 1e-10) { conv = 1; break; }
+        }
+        if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) a[i] = sa[i];
+    } else
     for (; k < 20; k++) {
         if (SMEM) {
             for (uint32_t i = threadIdx.x; i < F; i += blockDim.x) sa[i] = a[i];
@@ -823,7 +877,7 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
         for (uint32_t l = gtid; l < nlists; l += gsz) {
             const uint32_t b = mm_off[l], e = b + mm_len[l];
             double sum = 0;
-            for (uint32_t q = b; q < e; q++) sum += a[mm_fid[q]];
+            for (uint32_t q = b; q < e; q++) sum += SMEM ? sa[mm_fid[q]] : a[mm_fid[q]];
             z += (sum == 0);
         }
         z = __reduce_add_sync(0xffffffffu, z);
