@@ -26,11 +26,32 @@ def test_exports_match_header():
     assert lib.msg_abi_version() == m._lib.MSG_ABI_VERSION
 
 
-def test_struct_layout_matches_header():
-    # sizes computed from the C header by the compiler would be ideal; here: the fields the ABI documents
+def test_struct_layout_matches_header(tmp_path):
     assert C.sizeof(m._lib.MsgConfig) == 80
     assert C.sizeof(m._lib.MsgProfileStats) == 4 * 6 + 8 * 20 + 16
     assert C.sizeof(m._lib.MsgTiming) == 88
+    # field by field against the compiler's view of include/msamtools_b200.h (same names, offsets and sizes)
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    structs = {"msg_config": m._lib.MsgConfig, "msg_profile_stats": m._lib.MsgProfileStats, "msg_timing": m._lib.MsgTiming}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "msamtools_b200.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu %zu\\n", offsetof({cname}, {fname}), sizeof((({cname} *)0)->{fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict((l.split()[0], [int(x) for x in l.split()[1:]]) for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert got[cname] == [C.sizeof(ct)]
+        for fname, _ in ct._fields_:
+            f = getattr(ct, fname)
+            assert got[f"{cname}.{fname}"] == [f.offset, f.size], f"{cname}.{fname}"
 
 
 @pytest.mark.skipif(have_gpu(), reason="a GPU is present")
