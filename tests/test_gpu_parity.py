@@ -402,6 +402,18 @@ def test_zero_copy_push(m, oracle, mixed, mode):
         ab2, st2 = ctx.finish_profile()
         ui2, _ = ctx.pull_counts()
         assert np.array_equal(ui2, eui) and close(ab2, eab) and st2["n_lists"] == est["n_lists"]
+        # chunked, every chunk in its own pinned buffer (what a double-buffering host does): all of them zero-copy
+        ctx.reset(); ctx.timing(reset=True)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            lo, hi = int(off[a]), int(off[b])
+            with m.PinnedBuffer(hi - lo) as pc:
+                pc.array[:] = raw[lo:hi]
+                ctx.push(pc.array, off[a:b + 1] - off[a])
+        ab3, st3 = ctx.finish_profile()
+        ui3, _ = ctx.pull_counts()
+        t3 = ctx.timing()
+        assert (t3["zero_copy_chunks"], t3["fused_chunks"], t3["fused_fallbacks"]) == (3, 3, 0)
+        assert np.array_equal(ui3, eui) and close(ab3, eab) and st3["n_lists"] == est["n_lists"] and st3["purged"] == est["purged"]
 
 
 def test_zero_copy_guard_fallback(m, oracle):
