@@ -748,7 +748,8 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
                 for (;;) {
                     ll_load(src, w0, w1);
                     if ((w0 >> 32) == want && (w1 >> 32) == want) break;
-                    if (++spins > (1ull << 26)) { timeout = 1; break; }
+                    // a peer that never shows up costs ONE time limit (~40 s), not one per exchange: the flag is sticky
+                    if (timeout || ++spins > (1ull << 26)) { timeout = 1; break; }
                 }
                 tot += __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
             }
@@ -895,7 +896,7 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
                 for (;;) {
                     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
                     if ((w >> 32) == want) break;
-                    if (++spins > (1ull << 26)) { result[2] = 1; break; }
+                    if (*reinterpret_cast<volatile int32_t *>(result + 2) || ++spins > (1ull << 26)) { result[2] = 1; break; }
                 }
                 tot += (uint32_t)w;
             }
