@@ -970,7 +970,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
         const uint32_t nb = nblocks(F, 256);
         bool looped = false;
         if ((g.n_ranks <= 1 || c->p2p_ok) && F > 0 && !getenv("MSG_EM_HOST_LOOP")) {
-            // single GPU: the whole loop is one cooperative launch (grid-wide barriers, no host round trips)
+            // the whole loop is one cooperative launch (grid-wide barriers, no host round trips; with n_ranks > 1 the exchange is inside)
             const bool sm = F <= EM_SMEM_F;
             const size_t shm = sm ? (size_t)F * 8 * (1 + em_copies(F)) : 0;
             int per_sm = 0, nsm = 0;
@@ -1003,7 +1003,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 if (g.n_ranks > 1) { CU(c->t_d.reserve((size_t)F * 16)); totbuf = c->t_d.as<double>(); }
                 void *margs[] = {&a0, &a1, &a2, &nl_arg, &ui_arg, &cnt_arg, &nl_lo, &nl_hi, &Uw, &av, &inc, &partial, &F_arg, &dout, &d_res, &hc_dev,
                                  &totbuf, &bflag, &pt, &nr, &rk, &epoch};
-                // inc, delta, d_res and the peer region's purged word were cleared by em_init_kernel
+                // single GPU: inc[3F], delta and d_res were cleared by em_init_kernel; the multi-GPU kernel clears its own state
                 if (g.n_ranks > 1) {
                     // compute + collective in one kernel: increments are exchanged through peer memory inside the loop
                     if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<true>, dim3(grid), dim3(256), margs, shm, c->stream));
