@@ -33,10 +33,17 @@ def test_reference_suite_passes_on_ref_binary(ref_bin, suite, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.fixture(scope="module")
-def synth_bam(tmp_path_factory):
+STREAMS = {"mixed": ("mixed", 40_000, 424242, {}),
+           # second stream: few references, heavy clipping / indels, unmapped pairs, up to 12 occurrences per insert
+           "clippy": ("community", 30_000, 7, dict(n_refs=12, ref_len_min=3_000, ref_len_max=9_000, clip_fraction=0.35, indel_fraction=0.25,
+                                                  unmapped_fraction=0.06, shared_fraction=0.45, single_fraction=0.15, max_occ=12))}
+
+
+@pytest.fixture(scope="module", params=list(STREAMS))
+def synth_bam(request, tmp_path_factory):
     from msamtools_b200 import synth
-    p = synth.make_params("mixed", n_records=40_000, seed=424242)
+    preset, nrec, seed, over = STREAMS[request.param]
+    p = synth.make_params(preset, n_records=nrec, seed=seed, **over)
     raw, off, _ = synth.generate(p)
     tlen = synth.target_lengths(p)
     names = [f"ref{i:04d}" for i in range(len(tlen))]
