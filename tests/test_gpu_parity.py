@@ -93,10 +93,16 @@ FILTER_OPTS = [
 ]
 
 
-@pytest.fixture(scope="module")
-def mixed():
+@pytest.fixture(scope="module", params=["mixed", "clippy"])
+def mixed(request):
+    """two seeded synthetic streams: the `mixed` preset, and a 12-reference one with heavy clipping / indels, unmapped
+    pairs and up to 12 occurrences per insert (same shape as tests/test_ref_binary.py pins the oracle on)"""
     from msamtools_b200 import synth
-    p = synth.make_params("mixed", n_records=60_000, seed=24680)
+    if request.param == "mixed":
+        p = synth.make_params("mixed", n_records=60_000, seed=24680)
+    else:
+        p = synth.make_params("community", n_records=50_000, seed=7, n_refs=12, ref_len_min=3_000, ref_len_max=9_000, clip_fraction=0.35,
+                              indel_fraction=0.25, unmapped_fraction=0.06, shared_fraction=0.45, single_fraction=0.15, max_occ=12)
     raw, off, st = synth.generate(p)
     return raw, off, synth.target_lengths(p), p
 
