@@ -8,7 +8,7 @@ LIB     := msamtools_b200/libmsamtools_b200.so
 SYNTH   := msamtools_b200/libmsamsynth.so
 
 CLI     := msamtools_b200/bin/msamtools
-HOSTSRC := $(CSRC)/host/bamio.c $(CSRC)/host/margs.c $(CSRC)/host/keyorder.c
+HOSTSRC := $(CSRC)/host/bamio.c $(CSRC)/host/finflate.c $(CSRC)/host/margs.c $(CSRC)/host/keyorder.c
 
 all: $(LIB) $(SYNTH) $(CLI) oracle
 

@@ -1,5 +1,6 @@
 /* bamio.c -- SAM / BAM / BGZF I/O over zlib.  See bamio.h. */
 #include "bamio.h"
+#include "finflate.h"
 #include <ctype.h>
 #include <errno.h>
 #include <stdio.h>
@@ -25,6 +26,7 @@ struct bio_file {
     int threads, bgzf;
     uint8_t *cin; size_t cin_len, cin_cap;
     uint64_t ingest_bytes; double ingest_sec;
+    uint64_t blocks_fast, blocks_zlib;   /* parallel path: blocks inflated by finflate.c / handed to zlib */
     /* name -> tid hash for SAM parsing */
     int32_t *ht; size_t ht_size; const bio_hdr *ht_hdr;
     /* writer */
@@ -58,10 +60,11 @@ static double now_sec(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC,
 
 void bio_set_threads(bio_file *f, int n) { if (f && !f->writing) f->threads = n < 1 ? 1 : (n > 64 ? 64 : n); }
 void bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds) { if (bytes) *bytes = f->ingest_bytes; if (seconds) *seconds = f->ingest_sec; }
+void bio_inflate_stats(const bio_file *f, uint64_t *fast_blocks, uint64_t *zlib_blocks) { if (fast_blocks) *fast_blocks = f->blocks_fast; if (zlib_blocks) *zlib_blocks = f->blocks_zlib; }
 
 /* ---- BGZF blocks are independent gzip members: inflate a batch of them on worker threads */
 typedef struct { size_t in_off, in_len, out_off; uint32_t isize, crc; } bgzf_blk;
-typedef struct { const uint8_t *in; uint8_t *out; const bgzf_blk *blk; size_t nblk; int id, nthr; int err; } bgzf_job;
+typedef struct { const uint8_t *in; uint8_t *out; const bgzf_blk *blk; size_t nblk; int id, nthr; int err; uint64_t n_fast, n_zlib; } bgzf_job;
 
 static void *bgzf_worker(void *arg)
 {
@@ -71,6 +74,10 @@ static void *bgzf_worker(void *arg)
     for (size_t k = (size_t)j->id; k < j->nblk; k += (size_t)j->nthr) {
         const bgzf_blk *b = &j->blk[k];
         if (b->isize == 0) continue;
+        /* fast one-shot decoder first (finflate.c); anything it declines, or whose CRC does not match, goes through zlib */
+        if (fi_inflate(j->in + b->in_off, b->in_len, j->out + b->out_off, b->isize) == 0 &&
+            (uint32_t)crc32(crc32(0L, NULL, 0), j->out + b->out_off, b->isize) == b->crc) { j->n_fast++; continue; }
+        j->n_zlib++;
         inflateReset(&zs);
         zs.next_in = (Bytef *)(j->in + b->in_off); zs.avail_in = (uInt)b->in_len;
         zs.next_out = j->out + b->out_off; zs.avail_out = b->isize;
@@ -122,12 +129,13 @@ static int rd_fill_bgzf(bio_file *f)
         int nthr = f->threads; if ((size_t)nthr > nblk) nthr = (int)nblk;
         pthread_t th[64]; bgzf_job job[64];
         for (int i = 0; i < nthr; i++) {
-            job[i] = (bgzf_job){ f->cin, f->dec, blk, nblk, i, nthr, 0 };
+            job[i] = (bgzf_job){ f->cin, f->dec, blk, nblk, i, nthr, 0, 0, 0 };
             if (i && pthread_create(&th[i], NULL, bgzf_worker, &job[i])) { job[i].err = 2; }
         }
         bgzf_worker(&job[0]);
         int err = job[0].err;
         for (int i = 1; i < nthr; i++) { if (job[i].err == 2) { job[i].err = 0; bgzf_worker(&job[i]); } else pthread_join(th[i], NULL); err |= job[i].err; }
+        for (int i = 0; i < nthr; i++) { f->blocks_fast += job[i].n_fast; f->blocks_zlib += job[i].n_zlib; }
         free(blk);
         if (err) { set_err(f, "corrupt BGZF block (inflate/CRC)"); return -1; }
         memmove(f->cin, f->cin + p, f->cin_len - p); f->cin_len -= p;

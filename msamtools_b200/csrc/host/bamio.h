@@ -34,6 +34,8 @@ const char *bio_error(const bio_file *f);
 void      bio_set_threads(bio_file *f, int n);
 /* bytes of decompressed input produced so far / seconds spent producing them (read + inflate)  */
 void      bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds);
+/* parallel path only: blocks inflated by the fast one-shot decoder (finflate.c) / blocks that went through zlib         */
+void      bio_inflate_stats(const bio_file *f, uint64_t *fast_blocks, uint64_t *zlib_blocks);
 
 /* ---- writing: mode "w" SAM, "wh" SAM+header, "wb" BAM, "wbu" BAM in level-0 BGZF (msam_filter.c:464-470) */
 bio_file *bio_open_write(const char *path, const char *mode);

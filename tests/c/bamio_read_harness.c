@@ -1,6 +1,7 @@
 /* Reads a BAM through msamtools_b200/csrc/host/bamio.c with N inflate threads and writes the raw record stream to stdout
  * (tests/test_bamio_threads.py compares it with the stream the file was written from).  usage: harness file.bam threads */
 #include <stdio.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include "bamio.h"
 
@@ -17,6 +18,7 @@ int main(int argc, char **argv)
         if (len > (1u << 22)) { fwrite(buf, 1, len, stdout); len = 0; }
     if (rc < 0) { fprintf(stderr, "read: %s\n", bio_error(f)); return 1; }
     fwrite(buf, 1, len, stdout);
+    { uint64_t a = 0, b = 0; bio_inflate_stats(f, &a, &b); fprintf(stderr, "fast %llu zlib %llu\n", (unsigned long long)a, (unsigned long long)b); }
     free(buf); bio_hdr_free(h); bio_close(f);
     return 0;
 }

@@ -48,6 +48,11 @@ def test_parallel_inflate_equals_streaming(harness, stream, level):
         r = subprocess.run([exe, path, str(thr)], capture_output=True)
         assert r.returncode == 0, r.stderr.decode()
         outs[thr] = r.stdout
+        fast, zl = (int(x) for x in r.stderr.decode().split()[1::2])
+        if thr == 1:
+            assert (fast, zl) == (0, 0)                 # streaming zlib path
+        else:
+            assert fast > 0 and zl == 0                 # every block of a zlib-written file is taken by the fast decoder
     assert outs[1] == raw and outs[2] == raw and outs[5] == raw
 
 
