@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- `M alignments/s filter+besthit+profile` on B200 (BASELINE.json metric).
 
-A step = one pass of the hot path (decode + filter statistics, best-hit, proportional profile
-incl. the EM loop and, at N>1, the NCCL allreduce) over one batch of synthetic name-sorted
-PE150 alignments of BASELINE.json configs[1] shape (per-GPU batch = --records, default 10 M;
-weak scaling: every rank owns its own QNAME-group shard).
+Default workload = BASELINE.json configs[4], the configuration the metric is quoted on: alignments to a
+1 M-gene catalogue, sharded on QNAME-group boundaries over the ranks (weak scaling: --records per GPU per step,
+default 100 M = 10 chunks of 10 M name-sorted PE150 records, 29.5 GB resident per GPU), through
+`filter -l 80 -p 95 -z 80 --besthit | profile --multi=proportional`.  A step = msg_reset, one push per chunk
+(decode + filter statistics, best-hit, insert counting), msg_finish_profile (PropSharing loop; at N > 1 the
+cross-GPU exchange is inside it).
 
-  value      whole-job throughput, batch resident in HBM when the timed region starts
-  e2e        same metric through msg_push with HOST (pinned) buffers: H2D of the batch and D2H of
-             the abundance vector inside the timed region
-  roofline   decode/filter kernel: algorithmic bytes per launch / CUDA-event launch time vs the
-             measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline  the CPU oracle (restated reference algorithm) on a bounded sample, host cores
+  value      whole-job throughput, chunks resident in HBM when the timed region starts (CUDA events, max over ranks)
+  e2e        same metric through the public host API: pinned HOST chunks pushed with msg_push_async (two in flight),
+             the abundance vector read back, all inside the timed region
+  roofline   dominant kernel (decode + fused filter statistics): algorithmic bytes per launch / its CUDA-event
+             launch time vs the measured HBM peak; `step` = the same arithmetic for the whole step
+  cpu_baseline  the reference's own object code (oracle/_ref) on a bounded sample, on the box's host cores
+  parity     every run checks its own results before printing: a >= 1 M-record subsample of this very workload goes
+             through the same (multi-GPU) path and is compared with the CPU oracle; abundance vectors must be
+             bit-identical on all ranks
 
-`--impl reference` times the reference's CPU algorithm (oracle/_ref when built, else the oracle
-port) on the box's host cores for the same config/metric.
+`--config 1|3|4` select the other BASELINE.json configs (single GPU); `--impl reference` times the reference's CPU
+implementation of the selected config on the box's host cores.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -30,9 +36,31 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FILTER_OPTS = dict(l=80, p=95, z=80, besthit=True)
-MULTI = "proportional"
 METRIC = "M alignments/s filter+besthit+profile"
+FILTER = dict(l=80, p=95, z=80)
+SEED = 13579
+QNAME_ORIGIN = 100_000_000          # every QNAME is "sim" + 9 digits on every rank and chunk (same bytes per record everywhere)
+
+CONFIGS = {
+    5: dict(preset="genes1m", records=100_000_000, chunk=10_000_000,
+            workload="configs[4]: alignments to a 1M-gene catalogue, QNAME-group sharded over the GPUs: "
+                     "filter -l 80 -p 95 -z 80 --besthit | profile --multi=proportional",
+            ctx=dict(besthit=True, profile=True, multi="proportional", kept=False, **FILTER),
+            ref_filter=["filter", "-b", "-u", "-l", "80", "-p", "95", "-z", "80", "--besthit"],
+            ref_second=["profile", "--label", "S", "--multi=proportional"]),
+    1: dict(preset="community", records=20_000_000, chunk=20_000_000,
+            workload="configs[1]: synthetic community PE150, 100 genomes: filter -l 80 -p 95 -z 80 with record output",
+            ctx=dict(records=True, kept=False, **FILTER),
+            ref_filter=["filter", "-b", "-u", "-l", "80", "-p", "95", "-z", "80"], ref_second=None),
+    3: dict(preset="catalog10k", records=20_000_000, chunk=20_000_000,
+            workload="configs[2]: name-sorted alignments, 10k references, 30% multi-mappers: profile --multi=proportional",
+            ctx=dict(profile=True, multi="proportional", do_filter=False),
+            ref_filter=["profile", "--label", "S", "--multi=proportional"], ref_second=None),
+    4: dict(preset="community", records=20_000_000, chunk=20_000_000,
+            workload="configs[3]: filter -l 80 -p 95 -z 80 fused with coverage --summary, 100 genomes, 1 GPU",
+            ctx=dict(coverage=True, kept=False, **FILTER),
+            ref_filter=["filter", "-b", "-u", "-l", "80", "-p", "95", "-z", "80"], ref_second=["coverage", "--summary"]),
+}
 
 
 def peaks():
@@ -41,6 +69,14 @@ def peaks():
         with open(path) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def source_stamp(files):
+    h = hashlib.sha1()
+    for f in files:
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -73,17 +109,19 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        # median over the samples taken under load (power above the idle floor), else over all of them
+        hot = [s for s, p in zip(sm, pw) if p > 300.0]
+        return {"sm_mhz": statistics.median(hot or sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(hot), "power_w_max": max(pw) if pw else None}
 
 
 def dist_env():
@@ -93,59 +131,52 @@ def dist_env():
     return rank, world, local
 
 
-def make_batch(records, rank, pinned=True):
-    """configs[1]-shaped shard for this rank, generated straight into pinned host memory."""
+# ------------------------------------------------------------------------------------------------ synthetic workload
+def chunk_plan(cfg, records, chunk_records, world):
+    nchunks = max(1, (records + chunk_records - 1) // chunk_records)
+    per = records // nchunks
+    stride = (int(per / 2.4) // 100_000 + 1) * 100_000            # > inserts per chunk (>= 2.9 records per insert in every preset)
+    if QNAME_ORIGIN + world * nchunks * stride >= 1_000_000_000:
+        sys.exit("bench.py: records x ranks too large for 9-digit QNAMEs")
+    return nchunks, per, stride
+
+
+def chunk_params(cfg, rank, k, nchunks, per, stride, n_records=None):
     from msamtools_b200 import synth
-    # disjoint insert numbers per rank; the stride keeps "sim%08llu" at 8 digits on every rank (up to 9 ranks at the default
-    # size), so that per-GPU work really is the same -- a 1e9 stride gave ranks >= 1 two more QNAME bytes per record
-    stride = 10_000_000 if records <= 20_000_000 else 1_000_000_000
-    p = synth.make_params("community", n_records=records, seed=13579, qname_base=rank * stride)
-    cap_b, cap_r = (records + 64) * 330, records + 66
-    raw = off = None
-    if pinned:
-        try:
-            import torch
-            raw = torch.empty(cap_b, dtype=torch.uint8, pin_memory=True).numpy()
-            off = torch.empty(cap_r, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
-        except Exception:
-            raw = off = None
+    return synth.make_params(cfg["preset"], n_records=per if n_records is None else n_records, seed=SEED,
+                             qname_base=QNAME_ORIGIN + (rank * nchunks + k) * stride)
+
+
+def gen_chunk(cfg, rank, k, plan, raw=None, off=None, n_records=None):
+    from msamtools_b200 import synth
+    p = chunk_params(cfg, rank, k, *plan, n_records=n_records)
+    n = p.n_records
     if raw is None:
-        raw, off = np.empty(cap_b, dtype=np.uint8), np.empty(cap_r, dtype=np.uint64)
-    raw, off, st = synth.generate(p, raw, off)
-    return raw, off, synth.target_lengths(p), st
+        raw = np.empty((n + 64) * 330, dtype=np.uint8)
+    if off is None:
+        off = np.empty(n + 66, dtype=np.uint64)
+    raw, off, _ = synth.generate(p, raw, off)
+    return raw, off
 
 
-def cpu_reference_run(raw, off, tlen, sample_records, threads):
-    """The reference algorithm on host cores: `threads` independent QNAME-boundary shards of the first
-    `sample_records` records, one orc_pipeline (filter -> besthit -> proportional profile) per shard.
-    Returns (alignments processed, seconds)."""
-    from concurrent.futures import ThreadPoolExecutor
-    import msamtools_b200 as m
-    from oracle import oracle as orc
-    orc.load()
-    n = min(sample_records, len(off) - 1)
-    cuts = [0]
-    for t in range(1, threads):
-        k = m.split_point(raw, off, n * t // threads)
-        cuts.append(max(k, cuts[-1]))
-    cuts.append(m.split_point(raw, off, n) or n)
-    cfg = orc.filter_cfg(**FILTER_OPTS)
-    shards = []
-    for a, b in zip(cuts[:-1], cuts[1:]):
-        if b > a:
-            lo, hi = int(off[a]), int(off[b])
-            shards.append((raw[lo:hi], (off[a:b + 1] - off[a]).copy()))
-
-    def work(sh):
-        return orc.pipeline(sh[0], sh[1], cfg, len(tlen), 3)[1]["n_kept"]
-
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:      # ctypes releases the GIL inside the C call
-        list(ex.map(work, shards))
-    dt = time.perf_counter() - t0
-    return cuts[-1], dt, len(shards)
+def target_lengths(cfg):
+    from msamtools_b200 import synth
+    return synth.target_lengths(synth.make_params(cfg["preset"], n_records=1, seed=SEED))
 
 
+def gen_threads(world, nchunks):
+    cores = os.cpu_count() or 1
+    t = max(1, min(nchunks, cores // max(world, 1)))
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        t = max(1, min(t, int(avail * 0.45 / (3.6e9 * world))))      # every in-flight chunk holds ~3.3 GB of host memory
+    except Exception:
+        pass
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "msamtools")
 
 
@@ -153,21 +184,43 @@ def have_ref_binary():
     return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
 
 
-class RefPipelines:
-    """The reference's own object code (oracle/_ref/msamtools: msamtools v1.1.3 sources compiled against the
-    I/O shim) run as its documented pipe `filter -b -u -l 80 -p 95 -z 80 --besthit in.bam | profile
-    --multi=proportional -o out.gz -`, one pipe (two processes) per QNAME-boundary shard, shards on tmpfs as
-    level-0 BGZF BAM so that inflate cost is negligible."""
+def bam_header_blob(names, tlen):
+    import struct
+    text = ("@HD\tVN:1.6\tSO:queryname\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (n, int(l)) for n, l in zip(names, tlen))).encode()
+    parts = [b"BAM\1", struct.pack("<i", len(text)), text, struct.pack("<i", len(names))]
+    for n, l in zip(names, tlen):
+        nb = n.encode() + b"\0"
+        parts.append(struct.pack("<i", len(nb)) + nb + struct.pack("<i", int(l)))
+    return b"".join(parts)
 
-    def __init__(self, raw, off, tlen, n_pipes, per_pipe):
+
+def write_bgzf0(path, blobs):
+    """level-0 ("stored") BGZF, so that the reference arm pays (almost) nothing for inflate"""
+    import struct
+    import zlib
+    data = b"".join(bytes(b) for b in blobs)
+    with open(path, "wb") as fh:
+        for o in range(0, len(data), 0xff00):
+            blk = data[o:o + 0xff00]
+            co = zlib.compressobj(0, zlib.DEFLATED, -15)
+            comp = co.compress(blk) + co.flush()
+            fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25))
+            fh.write(comp + struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))
+        fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+class RefPipelines:
+    """The reference's own object code (oracle/_ref/msamtools: msamtools v1.1.3 sources compiled against the I/O shim)
+    run as its documented pipe, one pipe per QNAME-boundary shard (the reference is single-threaded), shards on
+    tmpfs as level-0 BGZF BAM so that inflate cost is negligible."""
+
+    def __init__(self, cfg, raw, off, tlen, n_pipes, per_pipe):
         import tempfile
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import samutil
         import msamtools_b200 as m
         base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        self.cfg = cfg
         self.dir = tempfile.mkdtemp(prefix="msb200_ref_", dir=base)
-        names = [f"g{i:06d}" for i in range(len(tlen))]
-        hdr = samutil.synth_header(names, tlen)
+        hdr = bam_header_blob([f"g{i:07d}" for i in range(len(tlen))], tlen)
         n = len(off) - 1
         self.paths, self.n = [], 0
         a = 0
@@ -177,7 +230,7 @@ class RefPipelines:
             if b <= a:
                 break
             path = os.path.join(self.dir, f"shard{k}.bam")
-            samutil.write_bam(path, hdr, names, tlen, raw[int(off[a]):int(off[b])], level=0)
+            write_bgzf0(path, [hdr, raw[int(off[a]):int(off[b])]])
             self.paths.append(path)
             self.n += b - a
             a = b
@@ -186,124 +239,208 @@ class RefPipelines:
         t0 = time.perf_counter()
         procs = []
         for i, path in enumerate(self.paths):
-            f = subprocess.Popen([REF_BIN, "filter", "-b", "-u", "-l", "80", "-p", "95", "-z", "80", "--besthit", path],
-                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
-            g = subprocess.Popen([REF_BIN, "profile", "--label", "S", "--multi=proportional", "-o", os.path.join(self.dir, f"out{i}.gz"), "-"],
-                                 stdin=f.stdout, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            f.stdout.close()
-            procs.append((f, g))
-        for f, g in procs:
-            if g.wait() != 0 or f.wait() != 0:
-                raise RuntimeError("reference pipeline failed")
+            out = os.path.join(self.dir, f"out{i}.gz")
+            first = [REF_BIN] + self.cfg["ref_filter"]
+            if self.cfg["ref_second"] is None:
+                if first[1] == "profile":
+                    first += ["-o", out]
+                f = subprocess.Popen(first + [path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                procs.append((f,))
+            else:
+                f = subprocess.Popen(first + [path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+                g = subprocess.Popen([REF_BIN] + self.cfg["ref_second"] + ["-o", out, "-"], stdin=f.stdout, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                f.stdout.close()
+                procs.append((g, f))
+        for ps in procs:
+            for p in ps:
+                if p.wait() != 0:
+                    raise RuntimeError("reference pipeline failed")
         return time.perf_counter() - t0
+
+    def procs_per_pipe(self):
+        return 1 if self.cfg["ref_second"] is None else 2
+
+    def describe(self):
+        cmd = "msamtools " + " ".join(self.cfg["ref_filter"])
+        if self.cfg["ref_second"] is not None:
+            cmd += " | msamtools " + " ".join(self.cfg["ref_second"])
+        return (f"{self.n} alignments per step as {len(self.paths)} QNAME-boundary shards (level-0 BGZF BAM on tmpfs), one `{cmd}` pipe "
+                f"per shard ({self.procs_per_pipe()} process(es) each; the reference is single-threaded); reference arithmetic "
+                f"(oracle/_ref = the reference's unmodified C sources), shim I/O (not htslib 1.24)")
 
     def close(self):
         import shutil
         shutil.rmtree(self.dir, ignore_errors=True)
 
 
-def cpu_baseline_entry(raw, off, tlen, args, n):
-    """cpu_baseline object for the JSON line: the reference's own object code when oracle/_ref exists
-    (kind "reference"), else the oracle port (kind "port")."""
-    cores = os.cpu_count() or 1
-    if have_ref_binary() and not args.cpu_port:
-        pipes = args.cpu_threads // 2 if args.cpu_threads else max(1, min(cores // 2, 16))
-        per = args.cpu_sample // pipes if args.cpu_sample else 500_000
-        rp = RefPipelines(raw, off, tlen, pipes, min(per, n))
-        try:
-            rp.run()                                   # page-cache / exec warm-up
-            dt = min(rp.run() for _ in range(2))
-        finally:
-            rp.close()
-        return {"value": rp.n / dt / 1e6, "unit": "M alignments/s", "cores": 2 * len(rp.paths), "kind": "reference",
-                "host_cores_available": cores,
-                "sample": f"{rp.n} alignments of the same batch as {len(rp.paths)} QNAME-boundary shards (level-0 BGZF BAM on tmpfs), one "
-                          f"`msamtools filter -b -u -l 80 -p 95 -z 80 --besthit | msamtools profile --multi=proportional` pipe per shard "
-                          f"(2 processes each; the reference is single-threaded); reference arithmetic, shim I/O (not htslib 1.24); best of 2"}, rp.n / dt / 1e6
-    threads = args.cpu_threads or min(cores, 32)
-    sample = args.cpu_sample or 2_000_000 * threads
-    nn, dt, nsh = cpu_reference_run(raw, off, tlen, min(sample, n), threads)
-    return {"value": nn / dt / 1e6, "unit": "M alignments/s", "cores": threads, "kind": "port", "host_cores_available": cores,
-            "sample": f"first {nn} alignments of the same batch in {nsh} QNAME-boundary shards, one in-memory oracle pipeline "
-                      f"(filter+besthit+proportional profile, no file I/O) per thread; the reference is single-threaded"}, nn / dt / 1e6
+def oracle_port_run(cfg, raw, off, tlen, sample_records, threads):
+    """Fallback when oracle/_ref is absent: the oracle port, one in-memory pipeline per thread (config 5 only)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import msamtools_b200 as m
+    from oracle import oracle as orc
+    orc.load()
+    n = min(sample_records, len(off) - 1)
+    cuts = [0]
+    for t in range(1, threads):
+        cuts.append(max(m.split_point(raw, off, n * t // threads), cuts[-1]))
+    cuts.append(m.split_point(raw, off, n) or n)
+    ocfg = orc.filter_cfg(besthit=True, **FILTER)
+    shards = [(raw[int(off[a]):int(off[b])], (off[a:b + 1] - off[a]).copy()) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:      # ctypes releases the GIL inside the C call
+        list(ex.map(lambda sh: orc.pipeline(sh[0], sh[1], ocfg, len(tlen), 3)[1]["n_kept"], shards))
+    return cuts[-1], time.perf_counter() - t0, len(shards)
+
+
+def ref_sample(cfg, args, plan, cores):
+    """host-side sample of the workload for the CPU arm: chunk 0 of rank 0, `pipes x per` records"""
+    procs = 2 if cfg["ref_second"] is not None else 1
+    pipes = args.cpu_threads // procs if args.cpu_threads else max(1, min(cores // procs, 16))
+    per = args.cpu_sample // pipes if args.cpu_sample else 1_000_000
+    raw, off = gen_chunk(cfg, 0, 0, plan, n_records=min(plan[1], pipes * per + 1000))
+    return raw, off, pipes, per
+
+
+def config_json(cfg, key, plan, records, n_refs):
+    """identical in both arms (the driver compares them): only what defines the workload, nothing measured"""
+    return {"workload": cfg["workload"], "config_index": key, "preset": cfg["preset"], "records_per_gpu_per_step": int(records),
+            "chunks_per_step": int(plan[0]), "n_references": int(n_refs), "seed": SEED,
+            "l2": "inputs larger than L2 (every chunk is ~%.1f GB of records vs 126 MB)" % (plan[1] * 295 / 1e9)}
 
 
 def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    use_ref = have_ref_binary() and not args.cpu_port
-    if use_ref:
-        pipes = args.cpu_threads // 2 if args.cpu_threads else max(1, min(cores // 2, 16))
-        per = args.cpu_sample // pipes if args.cpu_sample else 500_000
-        raw, off, tlen, _ = make_batch(min(args.records, pipes * per + 1000), 0, pinned=False)
-        rp = RefPipelines(raw, off, tlen, pipes, per)
+    records = args.records or cfg["records"]
+    plan = chunk_plan(cfg, records, args.chunk_records or cfg["chunk"], world)
+    tlen = target_lengths(cfg)
+    raw, off, pipes, per = ref_sample(cfg, args, plan, cores)
+    if have_ref_binary() and not args.cpu_port:
+        rp = RefPipelines(cfg, raw, off, tlen, pipes, per)
         try:
             for _ in range(max(1, min(args.warmup, 2))):
                 rp.run()
             tot_t = sum(rp.run() for _ in range(args.steps))
         finally:
             rp.close()
-        n, nsh, used = rp.n, len(rp.paths), 2 * len(rp.paths)
-        tot_n = n * args.steps
-        kind = "reference"
-        sample = (f"{n} alignments per step as {nsh} QNAME-boundary shards (level-0 BGZF BAM on tmpfs), one `msamtools filter -b -u -l 80 -p 95 "
-                  f"-z 80 --besthit | msamtools profile --multi=proportional` pipe per shard (2 processes each; the reference is "
-                  f"single-threaded); reference arithmetic (oracle/_ref), shim I/O (not htslib 1.24)")
+        n, used, kind, sample = rp.n, rp.procs_per_pipe() * len(rp.paths), "reference", rp.describe()
     else:
         threads = args.cpu_threads or min(cores, 32)
-        sample_n = args.cpu_sample or 2_000_000 * threads
-        raw, off, tlen, _ = make_batch(min(args.records, sample_n + 1000), 0, pinned=False)
-        for _ in range(args.warmup):
-            cpu_reference_run(raw, off, tlen, min(sample_n, 200_000), threads)
-        tot_n, tot_t = 0, 0.0
+        tot_t = 0.0
         for _ in range(args.steps):
-            n, dt, nsh = cpu_reference_run(raw, off, tlen, sample_n, threads)
-            tot_n += n; tot_t += dt
+            n, dt, nsh = oracle_port_run(cfg, raw, off, tlen, pipes * per, threads)
+            tot_t += dt
         used, kind = threads, "port"
-        sample = (f"{n} alignments per step in {nsh} QNAME-boundary shards, one in-memory oracle pipeline per thread "
-                  f"(reference arithmetic restated in oracle/msam_oracle.c; the reference itself is single-threaded)")
-    v = tot_n / tot_t / 1e6
+        sample = f"{n} alignments per step in {nsh} QNAME-boundary shards, one in-memory oracle pipeline per thread (oracle/msam_oracle.c)"
+    v = n * args.steps / tot_t / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "M alignments/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic community PE150, 100 genomes, filter -l 80 -p 95 -z 80 --besthit | profile --multi=proportional",
-                       "records_per_step": n},
+            "config": config_json(cfg, args.config, plan, records, len(tlen)),
             "cpu_baseline": {"value": v, "unit": "M alignments/s", "cores": used, "kind": kind, "host_cores_available": cores, "sample": sample},
             "e2e": {"value": v, "unit": "M alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+def cpu_baseline_entry(cfg, args, plan, tlen):
+    cores = os.cpu_count() or 1
+    raw, off, pipes, per = ref_sample(cfg, args, plan, cores)
+    if have_ref_binary() and not args.cpu_port:
+        rp = RefPipelines(cfg, raw, off, tlen, pipes, per)
+        try:
+            rp.run()                                   # page-cache / exec warm-up
+            dt = min(rp.run() for _ in range(2))
+        finally:
+            rp.close()
+        out = {"value": rp.n / dt / 1e6, "unit": "M alignments/s", "cores": rp.procs_per_pipe() * len(rp.paths), "kind": "reference",
+               "host_cores_available": cores, "sample": rp.describe() + "; best of 2"}
+    else:
+        threads = args.cpu_threads or min(cores, 32)
+        nn, dt, nsh = oracle_port_run(cfg, raw, off, tlen, pipes * per, threads)
+        out = {"value": nn / dt / 1e6, "unit": "M alignments/s", "cores": threads, "kind": "port", "host_cores_available": cores,
+               "sample": f"first {nn} alignments of chunk 0 in {nsh} QNAME-boundary shards, one in-memory oracle pipeline per thread"}
+    if args.config == 5:
+        one_n, one_dt, _ = oracle_port_run(cfg, raw, off, tlen, min(1_000_000, len(off) - 1), 1)
+        out["oracle_port_single_thread_value"] = one_n / one_dt / 1e6
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ parity inside the bench
+def close_rel(a, b, rel=1e-9):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return bool(np.all(np.abs(a - b) <= rel * np.maximum(np.abs(a), np.abs(b))))
+
+
+def parity_check(m, cfg, plan, tlen, rank, world, local, dist, bcast):
+    """A subsample of this workload (the first `v` records of every rank's chunk 0, >= 1 M records in total) through the
+    same contexts' code path (same options, same n_ranks: fused pass + the in-kernel cross-GPU exchange) vs the CPU
+    oracle run over the concatenation of all ranks' subsamples.  Integers exact, abundances within 1e-9 relative."""
+    from oracle import oracle as orc
+    v = 1_000_000 if world == 1 else 500_000
+    raw, off = gen_chunk(cfg, rank, 0, plan, n_records=v)
+    uid = bcast(m.nccl_unique_id() if (world > 1 and rank == 0) else None)
+    with m.Context(n_targets=len(tlen), device=local, n_ranks=world, rank=rank, nccl_unique_id=uid, **cfg["ctx"]) as ctx:
+        ctx.push(raw, off)
+        kept = ctx.kept_count()
+        ab, st = ctx.finish_profile()
+    res = {"subsample_records_per_rank": int(len(off) - 1)}
+    digest = hashlib.sha1(ab.tobytes()).hexdigest()
+    if dist is not None:
+        import torch
+        box = [None] * world
+        dist.all_gather_object(box, (digest, int(kept)))
+        digests, kepts = [b[0] for b in box], [b[1] for b in box]
+    else:
+        digests, kepts = [digest], [int(kept)]
+    res["ranks_bit_identical"] = len(set(digests)) == 1
+    ok = res["ranks_bit_identical"]
+    if rank == 0:
+        orc.load()
+        raws, offs, base = [raw], [off], int(off[-1])
+        for r in range(1, world):
+            rr, ro = gen_chunk(cfg, r, 0, plan, n_records=v)
+            raws.append(rr); offs.append(ro[1:] + np.uint64(base)); base += int(ro[-1])
+        raw_all, off_all = np.concatenate(raws), np.concatenate(offs)
+        eab, est = orc.pipeline(raw_all, off_all, orc.filter_cfg(besthit=True, **FILTER), len(tlen), 3)
+        ints = {k: (int(st[k]), int(est[k])) for k in ("mapped_inserts", "uniq", "multi", "purged", "iterations", "converged", "n_lists")}
+        ints["kept_records"] = (int(sum(kepts)), int(est["n_kept"]))
+        res.update(records=int(len(off_all) - 1), integers_exact=all(a == b for a, b in ints.values()),
+                   abundance_within_1e9=close_rel(ab, eab), em_iterations=int(est["iterations"]), multi_lists=int(est["n_lists"]),
+                   max_rel_err=float(np.max(np.abs(ab - eab) / np.maximum(np.maximum(np.abs(ab), np.abs(eab)), 1e-300))))
+        if not res["integers_exact"]:
+            res["integer_mismatches"] = {k: v2 for k, v2 in ints.items() if v2[0] != v2[1]}
+        ok = ok and res["integers_exact"] and res["abundance_within_1e9"]
+    ok = bool(bcast(ok if rank == 0 else None))
+    return ok, res
+
+
+# ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import msamtools_b200 as m
+    from concurrent.futures import ThreadPoolExecutor, as_completed
     rank, world, local = dist_env()
-    if args.gpus != world:
-        if world == 1 and args.gpus > 1:
-            sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    key = args.config
+    cfg = CONFIGS[key]
+    if key != 5 and world > 1:
+        sys.exit("bench.py: --config 1|3|4 are single-GPU lines")
     dist = None
-    uid = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        box = [m.nccl_unique_id() if rank == 0 else None]
+
+    def bcast(x):
+        if dist is None:
+            return x
+        box = [x]
         dist.broadcast_object_list(box, src=0)
-        uid = box[0]
-
-    raw, off, tlen, gen = make_batch(args.records, rank)
-    n = len(off) - 1
-    # kept=False: the profile is the filter stage's only consumer (the reference pipe's output is the profile, not the records)
-    ctx = m.Context(profile=True, multi=MULTI, kept=False, n_targets=len(tlen), device=local, n_ranks=world, rank=rank,
-                    nccl_unique_id=uid, **FILTER_OPTS)
-
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
+        return box[0]
 
     def max_over_ranks(x):
         if dist is None:
@@ -313,19 +450,87 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- resident: batch uploaded once, steps run from HBM
-    d_raw = ctx.device_alloc(raw.nbytes)
-    d_off = ctx.device_alloc(off.nbytes)
-    ctx.device_upload(d_raw, raw)
-    ctx.device_upload(d_off, off)
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t.item())
+
+    records = args.records or cfg["records"]
+    plan = chunk_plan(cfg, records, args.chunk_records or cfg["chunk"], world)
+    nchunks = plan[0]
+    tlen = target_lengths(cfg)
+    has_profile = bool(cfg["ctx"].get("profile"))
+    has_cov = bool(cfg["ctx"].get("coverage"))
+    has_rec = bool(cfg["ctx"].get("records"))
+
+    # ---- parity first (also warms every code path up)
+    parity_ok, parity = (True, {"skipped": "profile configs only"})
+    if has_profile and key == 5 and not args.no_parity:
+        parity_ok, parity = parity_check(m, cfg, plan, tlen, rank, world, local, dist, bcast)
+        if not parity_ok:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "parity_checked": False, "parity": parity}))
+            sys.exit("bench.py: parity check against the oracle FAILED")
+
+    uid = bcast(m.nccl_unique_id() if (world > 1 and rank == 0) else None)
+    kw = dict(n_targets=len(tlen), device=local, n_ranks=world, rank=rank, nccl_unique_id=uid)
+    if has_cov:
+        kw["target_len"] = tlen
+    ctx = m.Context(**kw, **cfg["ctx"])
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- the rank's shard: nchunks chunks, generated on the host cores, uploaded to HBM; the first e2e_chunks stay in pinned memory
+    n_e2e = max(1, min(nchunks, args.e2e_chunks))
+    per = plan[1]
+    pinned, host_chunks, dev_chunks = [], {}, {}
+    for k in range(n_e2e):
+        pinned.append((m.PinnedBuffer((per + 64) * 330, device=local), m.PinnedBuffer((per + 66) * 8, device=local)))
+
+    def job(k):
+        if k < n_e2e:
+            return k, gen_chunk(cfg, rank, k, plan, pinned[k][0].array, pinned[k][1].array.view(np.uint64))
+        return k, gen_chunk(cfg, rank, k, plan)
+
+    t_gen = time.perf_counter()
+    n_local = raw_bytes = 0
+    with ThreadPoolExecutor(max_workers=gen_threads(world, nchunks)) as ex:
+        for fut in as_completed([ex.submit(job, k) for k in range(nchunks)]):
+            k, (raw, off) = fut.result()
+            d_raw, d_off = ctx.device_alloc(raw.nbytes), ctx.device_alloc(off.nbytes)
+            ctx.device_upload(d_raw, raw); ctx.device_upload(d_off, off)
+            dev_chunks[k] = (d_raw, raw.nbytes, d_off, len(off) - 1)
+            n_local += len(off) - 1; raw_bytes += raw.nbytes
+            if k < n_e2e:
+                host_chunks[k] = (raw, off)
+            del raw, off
+    t_gen = time.perf_counter() - t_gen
+    order = sorted(dev_chunks)
+
+    def finish():
+        if has_profile:
+            return ctx.finish_profile()
+        if has_cov:
+            return ctx.finish_coverage()
+        ctx.sync()
+        return None
 
     def step_resident():
         ctx.reset()
-        ctx.push_device(d_raw, raw.nbytes, d_off, n)
-        return ctx.finish_profile()
+        for k in order:
+            ctx.push_device(*dev_chunks[k])
+        return finish()
 
     for _ in range(args.warmup):
-        ab, st = step_resident()
+        out = step_resident()
     ctx.timing(reset=True)
     sampler = ClockSampler(local)
     barrier()
@@ -334,87 +539,121 @@ def run_ours(args):
     ctx.mark(0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ab, st = step_resident()
+        out = step_resident()
     ctx.mark(1)
     dev_ms = ctx.elapsed_ms(0, 1)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     tim = ctx.timing(reset=True)
+    kept_last = int(ctx.kept_count())
     step_ms = max_over_ranks(max(dev_ms, 0.0) / args.steps)
     wall_step_ms = max_over_ranks(wall_ms / args.steps)
-    n_total = n * world if dist is None else int(max_over_ranks(0) or 0) or n * world
-    if dist is not None:
-        import torch
-        t = torch.tensor([n], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t)
-        n_total = int(t.item())
+    n_total = sum_over_ranks(n_local)
     value = n_total / (step_ms * 1e-3) / 1e6
 
-    # ---- end to end: host buffers through msg_push, H2D + D2H inside the timed region
+    # the job's own result must be the same bits on every rank, and obey the conservation laws of the profile
+    job_check = {}
+    if has_profile:
+        ab, st = out
+        digest = hashlib.sha1(ab.tobytes()).hexdigest()
+        if dist is not None:
+            box = [None] * world
+            dist.all_gather_object(box, digest)
+        else:
+            box = [digest]
+        job_check = {"ranks_bit_identical": len(set(box)) == 1,
+                     "uniq_plus_multi_eq_inserts": int(st["uniq"]) + int(st["multi"]) == int(st["mapped_inserts"]),
+                     "abundance_sum_eq_inserts_minus_purged": bool(abs(ab.sum() - (st["mapped_inserts"] - st["purged"])) <= 1e-6 * max(st["mapped_inserts"], 1)),
+                     "inserts": int(st["mapped_inserts"]), "multi_lists": int(st["n_lists"]), "purged": int(st["purged"]),
+                     "em_iterations": int(st["iterations"]), "em_converged": int(st["converged"])}
+        parity_ok = parity_ok and all(v for k2, v in job_check.items() if isinstance(v, bool))
+
+    # ---- end to end: pinned HOST chunks through the public push API, H2D + D2H inside the timed region
+    e2e_order = sorted(host_chunks)
+
     def step_e2e():
         ctx.reset()
-        ctx.push(raw, off)
-        return ctx.finish_profile()
+        for k in e2e_order:
+            ctx.push_async(*host_chunks[k])
+        ctx.wait()
+        res = finish()
+        if has_rec:
+            ctx.pull_records()
+        return res
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    ctx.timing(reset=True)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(e2e_steps):
-        ab2, st2 = step_e2e()
-    barrier()
-    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / e2e_steps)
+    n_e2e_local = sum(len(host_chunks[k][1]) - 1 for k in e2e_order)
+    e2e = None
+    if args.e2e_steps > 0:
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        ctx.timing(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / e2e_steps)
+        tim2 = ctx.timing(reset=True)
+        n_e2e_total = sum_over_ranks(n_e2e_local)
+        e2e_bytes = sum(host_chunks[k][0].nbytes for k in e2e_order)
+        e2e = {"value": n_e2e_total / (e2e_ms * 1e-3) / 1e6, "unit": "M alignments/s", "ms_per_step": e2e_ms,
+               "records_per_gpu_per_step": int(n_e2e_local), "chunks_per_step": len(e2e_order),
+               "h2d_bytes_per_step": int(tim2["h2d_bytes"] // e2e_steps), "d2h_bytes_per_step": int(tim2["d2h_bytes"] // e2e_steps),
+               "h2d_gbs": (tim2["h2d_bytes"] / e2e_steps) / (e2e_ms * 1e-3) / 1e9,
+               "bam_gbs_per_gpu": e2e_bytes / (e2e_ms * 1e-3) / 1e9,
+               "api": "msg_push_async x chunks (pinned host buffers, two chunks in flight) + msg_wait + msg_finish_*",
+               "h2d_mode": ("zero-copy: decode windows pulled from the pinned host chunks over PCIe (h2d bytes = window chunks requested + offset "
+                            "index DMA; SEQ/QUAL never leave the host)") if tim2.get("zero_copy_chunks", 0) else "staged: whole chunks DMA'd into two device slots"}
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (resident + e2e)
-    tim2 = ctx.timing(reset=True)
-    e2e_value = n_total / (e2e_ms * 1e-3) / 1e6
 
-    ctx.device_free(d_raw); ctx.device_free(d_off)
+    for k in order:
+        ctx.device_free(dev_chunks[k][0]); ctx.device_free(dev_chunks[k][2])
 
     if rank == 0:
         peak, peak_src = peaks()
-        dec_ms = tim["decode_ms"] / max(tim["decode_launches"], 1)
-        alg_per_launch = tim["alg_bytes"] / max(tim["decode_launches"], 1)
+        launches = max(tim["decode_launches"], 1)
+        dec_ms = tim["decode_ms"] / launches
+        alg_per_launch = tim["alg_bytes"] / launches
         achieved = alg_per_launch / (dec_ms * 1e-3) / 1e9
-        full_scan = (raw.nbytes + off.nbytes) / (dec_ms * 1e-3) / 1e9
+        alg_step = tim["alg_bytes"] / args.steps
+        if has_rec:       # A_out(rec) = 8 + B_rec + keep * B_rec: the records are read once and the survivors written once
+            alg_step = raw_bytes + 8 * n_local + raw_bytes * kept_last / max(n_local, 1)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "decode_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 tj = json.load(fh)
-            if tj.get("records") == n:
+            if tj.get("source_stamp") == source_stamp(["msamtools_b200/csrc/decode.cuh", "msamtools_b200/csrc/common.cuh"]) \
+                    and tj.get("config_index") == key and abs(tj.get("records_per_launch", 0) - n_local / nchunks) < 1000:
                 traffic = tj.get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": "M alignments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic community PE150, 100 genomes, filter -l 80 -p 95 -z 80 --besthit | profile --multi=proportional",
-                       "records_per_gpu": n, "raw_bytes_per_gpu": int(raw.nbytes), "n_references": int(len(tlen)),
-                       "l2": "inputs larger than L2 (%.1f GB batch vs 126 MB)" % (raw.nbytes / 1e9),
-                       "kept_records": int(ctx.kept_count()), "inserts": int(st["mapped_inserts"]), "em_iterations": int(st["iterations"]),
-                       "wall_ms_per_step": wall_step_ms},
+            "config": config_json(cfg, key, plan, records, len(tlen)),
+            "run": {"records_per_gpu": int(n_local), "raw_bytes_per_gpu": int(raw_bytes), "kept_records_last_chunk": kept_last,
+                    "wall_ms_per_step": wall_step_ms, "generation_s": round(t_gen, 1), "job": job_check},
+            "parity_checked": bool(parity_ok), "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "decode_kernel (record decode + fused filter statistics)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": traffic, "alg_bytes_per_launch": alg_per_launch, "launch_ms": dec_ms,
-                         "full_scan_gbs": full_scan, "kernel_share_of_step": dec_ms / step_ms},
-            "e2e": {"value": e2e_value, "unit": "M alignments/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(tim2["h2d_bytes"] // e2e_steps), "d2h_bytes_per_step": int(tim2["d2h_bytes"] // e2e_steps),
-                    "host_ingest_gbs": (tim2["h2d_bytes"] / e2e_steps) / (e2e_ms * 1e-3) / 1e9,
-                    "bam_gbs": raw.nbytes / (e2e_ms * 1e-3) / 1e9,
-                    "h2d_mode": ("zero-copy: decode windows pulled from the pinned host batch over PCIe (h2d bytes = window chunks requested"
-                                 " + offset index DMA; SEQ/QUAL never leave the host)") if tim2.get("zero_copy_chunks", 0) else "staged: whole batch DMA"},
+                         "traffic": traffic, "alg_bytes_per_launch": alg_per_launch, "launch_ms": dec_ms, "launches_per_step": launches / args.steps,
+                         "full_scan_gbs": (raw_bytes + 8 * n_local) / nchunks / (dec_ms * 1e-3) / 1e9, "kernel_share_of_step": dec_ms * launches / args.steps / step_ms,
+                         "step": {"alg_bytes": alg_step, "achieved": alg_step / (step_ms * 1e-3) / 1e9, "frac": alg_step / (step_ms * 1e-3) / 1e9 / peak}},
+            "e2e": e2e,
             "gpu_launches": int(tim["kernel_launches"]),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_baseline_entry(raw, off, tlen, args, n)
-            one_n, one_dt, _ = cpu_reference_run(raw, off, tlen, min(1_000_000, n), 1)
-            line["cpu_baseline"]["oracle_port_single_thread_value"] = one_n / one_dt / 1e6
+            line["cpu_baseline"] = cpu_baseline_entry(cfg, args, plan, tlen)
         print(json.dumps(line))
     ctx.close()
+    for a, b in pinned:
+        a.close(); b.close()
     if dist is not None:
         dist.destroy_process_group()
+    if not parity_ok:
+        sys.exit("bench.py: result checks FAILED")
 
 
 def main():
@@ -423,11 +662,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--records", type=int, default=10_000_000, help="alignments per GPU per step")
+    ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS), help="BASELINE.json config (1-based: 5 = the 1M-gene catalogue job the metric is quoted on)")
+    ap.add_argument("--records", type=int, default=0, help="alignments per GPU per step (default: the config's)")
+    ap.add_argument("--chunk-records", type=int, default=0, help="alignments per pushed chunk")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunks", type=int, default=3, help="chunks kept in pinned host memory for the end-to-end leg")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-port", action="store_true", help="time the in-memory oracle port even when oracle/_ref exists")
     args = ap.parse_args()
     if args.impl == "reference":

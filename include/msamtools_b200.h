@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MSG_ABI_VERSION 1
+#define MSG_ABI_VERSION 2
 
 /* error codes */
 #define MSG_OK         0
@@ -156,6 +156,26 @@ int  msg_push(msg_ctx *ctx, const uint8_t *raw, size_t nbytes,
 /* Same, but the chunk already lives in device memory (device pointers).      */
 int  msg_push_device(msg_ctx *ctx, const uint8_t *d_raw, size_t nbytes,
                      const uint64_t *d_rec_off, size_t nrec);
+/*
+ * Asynchronous, double-buffered push -- the streaming loop of the reference (one record at a time through mSamRead,
+ * msam_filter.c:116-125, msam_helper.c:246-268) becomes a pipeline of chunks: the call queues the chunk's transfers
+ * and kernels and returns without waiting for them, so that the host can inflate / index the next chunk meanwhile.
+ *   - at most TWO chunks are in flight.  The call first completes the chunk pushed two calls earlier; its buffers
+ *     (raw, rec_off) may be recycled once this call returns.  A host that rotates three buffers never waits for the
+ *     GPU; with two it calls msg_wait before refilling.  msg_wait (and every result / finish / reset call)
+ *     completes everything in flight.
+ *   - staged chunks are copied on a second stream into one of two device slots while the previous chunk's kernels
+ *     run; pinned 16-byte aligned buffers (msg_host_alloc) are decoded in place over PCIe instead.
+ *   - errors of a chunk (MSG_ENOTAG, MSG_ENOAS, MSG_EFORMAT) are reported by the call that completes it.
+ *   - contexts that need host decisions per chunk (record output, kept list, coverage, stats, profile without
+ *     best-hit) complete the chunk before returning: for them msg_push_async == msg_push.
+ *   - "results of the LAST pushed chunk" below refer to the last COMPLETED chunk.
+ */
+int  msg_push_async(msg_ctx *ctx, const uint8_t *raw, size_t nbytes,
+                    const uint64_t *rec_off, size_t nrec);
+int  msg_push_device_async(msg_ctx *ctx, const uint8_t *d_raw, size_t nbytes,
+                           const uint64_t *d_rec_off, size_t nrec);
+int  msg_wait(msg_ctx *ctx);
 /* Device staging owned by the library, for callers that want to fill HBM once
  * and push the same resident chunk repeatedly (benchmarks).                   */
 int  msg_device_alloc(msg_ctx *ctx, size_t nbytes, void **d_ptr);

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmsamtools_b200.so")
 
-MSG_ABI_VERSION = 1
+MSG_ABI_VERSION = 2
 MSG_OK, MSG_EINVAL, MSG_ENODEV, MSG_ECUDA, MSG_ENOMEM = 0, -1, -2, -3, -4
 MSG_ENOTAG, MSG_ENOAS, MSG_EFORMAT, MSG_ERANGE, MSG_ENCCL, MSG_ESTATE = -5, -6, -7, -8, -9, -10
 HIT_NONE, HIT_BEST, HIT_UNIQUE = 0, 1, 2
@@ -53,7 +53,7 @@ class MsgTiming(C.Structure):
 EXPORTS = [
     "msg_create", "msg_destroy", "msg_last_error", "msg_abi_version", "msg_device_count",
     "msg_index_records", "msg_split_point",
-    "msg_push", "msg_push_device", "msg_device_alloc", "msg_device_free", "msg_device_upload", "msg_sync", "msg_reset",
+    "msg_push", "msg_push_device", "msg_push_async", "msg_push_device_async", "msg_wait", "msg_device_alloc", "msg_device_free", "msg_device_upload", "msg_sync", "msg_reset",
     "msg_kept_count", "msg_pull_kept", "msg_pull_records", "msg_pull_stats", "msg_pull_counts",
     "msg_finish_profile", "msg_finish_coverage", "msg_pull_coverage", "msg_get_timing", "msg_nccl_unique_id",
     "msg_mark", "msg_elapsed_ms", "msg_host_alloc", "msg_host_free",
@@ -82,6 +82,9 @@ def load():
     lib.msg_split_point.argtypes = [u8p, u64p, sz, sz]; lib.msg_split_point.restype = sz
     lib.msg_push.argtypes = [vp, u8p, sz, u64p, sz]
     lib.msg_push_device.argtypes = [vp, vp, sz, vp, sz]
+    lib.msg_push_async.argtypes = [vp, u8p, sz, u64p, sz]
+    lib.msg_push_device_async.argtypes = [vp, vp, sz, vp, sz]
+    lib.msg_wait.argtypes = [vp]
     lib.msg_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     lib.msg_device_free.argtypes = [vp, vp]
     lib.msg_device_upload.argtypes = [vp, vp, vp, sz]

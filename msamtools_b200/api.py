@@ -103,6 +103,21 @@ class Context:
         self._last_n = n
         self._check(self.lib.msg_push(self.h, _ptr(raw), raw.nbytes, _ptr(rec_off), n))
 
+    def push_async(self, raw, rec_off):
+        """msg_push_async: queue the chunk and return; raw / rec_off must stay alive and unmodified until wait() or two
+        further push_async calls have returned (the caller keeps the references)."""
+        assert raw.dtype == np.uint8 and raw.flags.c_contiguous and rec_off.dtype == np.uint64 and rec_off.flags.c_contiguous
+        n = len(rec_off) - 1 if len(rec_off) else 0
+        self._last_n = n
+        self._check(self.lib.msg_push_async(self.h, _ptr(raw), raw.nbytes, _ptr(rec_off), n))
+
+    def push_device_async(self, d_raw, nbytes, d_off, nrec):
+        self._last_n = nrec
+        self._check(self.lib.msg_push_device_async(self.h, d_raw, nbytes, d_off, nrec))
+
+    def wait(self):
+        self._check(self.lib.msg_wait(self.h))
+
     def device_alloc(self, nbytes):
         p = C.c_void_p()
         self._check(self.lib.msg_device_alloc(self.h, nbytes, C.byref(p)))

@@ -82,10 +82,25 @@ NcclApi g_nccl;
 
 } // namespace
 
+// One chunk in flight on the fused filter->profile pass (msg_push_async): where its bytes are, the pinned block its
+// small results land in, and what is needed to rerun it on the general pipeline should the guard decline it.
+struct Slot {
+    DevBuf raw, off;                          // staged copies of host chunks
+    uint32_t *h_res = nullptr;                // pinned: [0..4] inserts, uniq, multi, guard flag, kept; [5..6] list cursors; [8..9] error word
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool pending = false;
+    const uint8_t *d_raw = nullptr, *h_raw = nullptr; const uint64_t *d_off = nullptr, *h_off = nullptr;
+    uint64_t nbytes = 0, readable = 0, n = 0; bool zero_copy = false;
+    uint64_t ub_lists = 0, ub_ent = 0;        // list space reserved for it (worst case) until its real counts are known
+};
+
 struct msg_ctx {
     msg_config cfg;
     std::string err;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    Slot slot[2]; int next_slot = 0;          // slot[next_slot] is the older of the two
+    bool cursor_dirty = true;                 // host csr_lists / csr_ent must be uploaded before the next fused pass
+    uint64_t inflight_lists = 0, inflight_ent = 0;
     bool has_filter = false, need_stats = false, cov_fused = false;
     uint64_t zc_chunks = 0;                           // chunks decoded straight from pinned host memory
     uint32_t lay_lpr = 0, lay_hc = 0, lay_tc = 0;     // decode window layout (probe_layout)
@@ -96,7 +111,7 @@ struct msg_ctx {
     uint64_t cov_cells = 0;
 
     // chunk staging (msg_push) and per-chunk columns
-    DevBuf raw, off, tid, fb, score, hash, nid, st_alen, st_qlen, st_qclip, st_edit;
+    DevBuf tid, fb, score, hash, nid, st_alen, st_qlen, st_qclip, st_edit;
     DevBuf kbase, worklist, gmeta, out_idx, tile_sums, pcount, scanv, biglist;
     uint32_t *d_wl = nullptr;                  // [0] best-hit worklist length [1] profile worklist length
     // fused filter+besthit -> profile path (fused.cuh): chunk-local accumulators, list cursors, window summaries
@@ -132,7 +147,7 @@ struct msg_ctx {
     // multi-GPU
     ncclComm_t comm = nullptr;
     // peer-memory exchange for the fused EM loop (profile.cuh em_loop_multi_kernel): CUDA IPC mappings of every rank's region
-    unsigned char *peer_region = nullptr; PeerTable peer_tab; std::vector<void *> ipc_opened; bool p2p_ok = false; uint32_t em_epoch = 32;
+    unsigned char *peer_region = nullptr; size_t peer_region_bytes = 0; PeerTable peer_tab; std::vector<void *> ipc_opened; bool p2p_ok = false; uint32_t em_epoch = 32;
 
     // timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_decode, ev_total;
@@ -209,6 +224,10 @@ int check_device_errors(msg_ctx *c)
 
 int report_device_errors(msg_ctx *c, const uint32_t *h)
 {
+    if (h[0]) {                   // reported once: the next chunk starts with a clean error word
+        cudaMemsetAsync(c->d_err, 0, 4, c->stream);
+        cudaMemsetAsync(c->d_err + 1, 0xff, 4, c->stream);
+    }
     if (h[0] & DERR_FORMAT) return fail(c, MSG_EFORMAT, "malformed BAM record or reference id out of range (first near record %u)", h[1]);
     if (h[0] & DERR_NOTAG)  return fail(c, MSG_ENOTAG, "Either NM or MD must be present in SAM/BAM input for 'filter' command. Type 'msamtools filter -h' for details.");
     if (h[0] & DERR_NOAS)   return fail(c, MSG_ENOAS, "Required field AS not found in SAM/BAM input. Type 'msamtools -h' for details.");
@@ -316,25 +335,41 @@ int records_stage(msg_ctx *c, const uint32_t *stream, uint64_t m)
     return MSG_OK;
 }
 
-// filter+besthit -> profile without materialising the kept stream (fused.cuh).  Returns MSG_OK with
-// *done = true when the chunk was fully handled, *done = false when the guard asked for the general
-// pipeline (accumulators untouched in that case).
-int fused_stage(msg_ctx *c, const DecodeParams &dp, uint64_t n, bool *done)
+int wait_all(msg_ctx *c);
+
+// filter+besthit -> profile without materialising the kept stream (fused.cuh), enqueued WITHOUT a host round trip:
+// the guard flag, counters, list cursors and the error word of the chunk are copied into the slot's pinned block and
+// read when the slot is completed (complete_slot).  The list cursors live on the device between chunks; if the guard
+// trips, fused_commit_kernel drops the chunk's partial sums and puts the cursors back, and the host later reruns the
+// chunk on the general pipeline.  *queued = false: the chunk cannot take this path (list space would pass 2^32).
+int fused_enqueue(msg_ctx *c, const DecodeParams &dp, uint64_t n, Slot &sl, bool *queued)
 {
     const msg_config &g = c->cfg;
-    *done = false;
+    *queued = false;
     const bool prop = g.share_type == MSG_MULTI_PROPORTIONAL;
     const uint32_t nwin = nblocks(n, 32);
     CU(c->worklist.reserve(((size_t)nwin + 2) * 4));
     CU(c->win.reserve((size_t)nwin * sizeof(WinInfo)));
+    sl.ub_lists = sl.ub_ent = 0;
     if (prop) {
-        if (c->csr_lists + n / 2 + 2 >= 0xffffffffull || c->csr_ent + n + 2 >= 0xffffffffull) return MSG_OK;       // general path reports the overflow
-        CU(c->csr_off.reserve_keep((c->csr_lists + n / 2 + 2) * 4, c->csr_lists * 4, c->stream));
-        CU(c->csr_len.reserve_keep((c->csr_lists + n / 2 + 2) * 4, c->csr_lists * 4, c->stream));
-        CU(c->csr_fid.reserve_keep((c->csr_ent + n + 2) * 4, c->csr_ent * 4, c->stream));
+        const uint64_t ul = n / 2 + 2, ue = n + 2;
+        if (c->csr_lists + c->inflight_lists + ul >= 0xffffffffull || c->csr_ent + c->inflight_ent + ue >= 0xffffffffull) return MSG_OK;   // general path reports the overflow
+        if ((c->csr_lists + c->inflight_lists + ul) * 4 > c->csr_off.cap || (c->csr_ent + c->inflight_ent + ue) * 4 > c->csr_fid.cap || !c->csr_off.p) {
+            // growing the list storage copies the lists written so far: the counts of the chunks in flight must be known first
+            int rc = wait_all(c); if (rc) return rc;
+            CU(c->csr_off.reserve_keep((c->csr_lists + ul) * 4, c->csr_lists * 4, c->stream));
+            CU(c->csr_len.reserve_keep((c->csr_lists + ul) * 4, c->csr_lists * 4, c->stream));
+            CU(c->csr_fid.reserve_keep((c->csr_ent + ue) * 4, c->csr_ent * 4, c->stream));
+        }
+        sl.ub_lists = ul; sl.ub_ent = ue;
     }
-    const uint32_t cur[2] = {(uint32_t)c->csr_lists, (uint32_t)c->csr_ent};
-    CU(cudaMemcpyAsync(c->d_cursor, cur, 8, cudaMemcpyHostToDevice, c->stream));
+    if (c->cursor_dirty) {
+        const uint32_t cur[2] = {(uint32_t)c->csr_lists, (uint32_t)c->csr_ent};
+        memcpy(c->h_pin + 80, cur, 8);                                           // pinned: the async copy reads it later
+        CU(cudaMemcpyAsync(c->d_cursor, c->h_pin + 80, 8, cudaMemcpyHostToDevice, c->stream));
+        c->cursor_dirty = false;
+    }
+    CU(cudaMemcpyAsync(c->d_cursor + 2, c->d_cursor, 8, cudaMemcpyDeviceToDevice, c->stream));   // where the cursors go back to if the guard trips
     CU(cudaMemsetAsync(c->d_fcnt, 0, 32, c->stream));
     CU(cudaMemsetAsync(c->d_wl, 0, 4, c->stream));
     FusedParams p;
@@ -352,23 +387,13 @@ int fused_stage(msg_ctx *c, const DecodeParams &dp, uint64_t n, bool *done)
     fused_guard_kernel<<<nblocks(nwin, 256), 256, 0, c->stream>>>(p.win, nwin, c->d_fcnt + 3); LAUNCHED(c);
     const size_t F = (size_t)(g.n_features > 0 ? g.n_features : 1);
     fused_commit_kernel<<<nblocks(F < 3 ? 3 : F, 256), 256, 0, c->stream>>>(c->d_ui, c->d_d, c->d_ui_tmp, c->d_d_tmp, (uint32_t)g.n_features,
-                                                                           g.share_type == MSG_MULTI_EQUAL, c->d_counters, c->d_fcnt); LAUNCHED(c);
-    // the chunk's only host round trip: guard flag, counters, list cursors and the error word, into pinned memory
-    uint32_t *h = c->h_pin;
+                                                                           g.share_type == MSG_MULTI_EQUAL, c->d_counters, c->d_fcnt, c->d_cursor); LAUNCHED(c);
+    uint32_t *h = sl.h_res;
     CU(cudaMemcpyAsync(h, c->d_fcnt, 20, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(h + 5, c->d_cursor, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(h + 8, c->d_err, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    c->d2h_bytes += 36;
-    { int erc = report_device_errors(c, h + 8); if (erc) return erc; }
-    c->fused_chunks++;
-    if (h[3]) {            // guard tripped: the commit kernel dropped this chunk's partial sums; keep the list cursors where they were
-        c->fused_fallbacks++;
-        return MSG_OK;
-    }
-    c->csr_lists = h[5]; c->csr_ent = h[6];
-    c->n_kept = h[4]; c->have_stream = false;
-    *done = true;
+    c->inflight_lists += sl.ub_lists; c->inflight_ent += sl.ub_ent;
+    *queued = true;
     return MSG_OK;
 }
 
@@ -420,21 +445,11 @@ int probe_layout(msg_ctx *c, const uint8_t *h_raw, const uint64_t *h_off, const 
     return MSG_OK;
 }
 
-// zero_copy: d_raw is a device view of the caller's pinned HOST buffer h_raw (msg_push); the decode kernel then pulls
-// only the 16-byte chunks of its windows over PCIe.  If the chunk has to go through the general pipeline after all, it
-// is staged into device memory first.
-int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readable, const uint64_t *d_off, uint64_t n,
-              const uint8_t *h_raw = nullptr, const uint64_t *h_off = nullptr, bool zero_copy = false)
+// Decode + filter statistics of one chunk: reserves the SoA columns, picks the window layout, launches decode_kernel.
+int launch_decode(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readable, const uint64_t *d_off, uint64_t n,
+                  const uint8_t *h_raw, const uint64_t *h_off, DecodeParams *out)
 {
     const msg_config &g = c->cfg;
-    if (n >= 0xffffffffull) return fail(c, MSG_EINVAL, "a chunk may hold at most 2^32-2 records");
-    c->cur_raw = d_raw; c->cur_off = d_off; c->cur_n = n; c->cur_nbytes = nbytes;
-    c->n_kept = 0; c->have_stream = false; c->out_bytes = 0;
-    if (n == 0) return MSG_OK;
-
-    cudaEvent_t t0 = get_event(c), t1 = get_event(c), k0 = get_event(c), k1 = get_event(c);
-    CU(cudaEventRecord(t0, c->stream));
-
     const bool hit = g.do_filter && g.hit_mode != MSG_HIT_NONE;
     const bool need_score = hit || g.want_stats || (g.do_filter && g.rescore && g.want_records);
     CU(c->tid.reserve(n * 4)); CU(c->fb.reserve(n * 4));
@@ -444,7 +459,7 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
 
     DecodeParams p;
     memset(&p, 0, sizeof p);
-    p.raw = d_raw; p.off = d_off; p.n = n; p.nbytes_readable = readable;
+    p.raw = d_raw; p.off = d_off; p.n = n; p.nbytes = nbytes; p.nbytes_readable = readable;
     p.tid = c->tid.as<int32_t>(); p.fb = c->fb.as<uint32_t>();
     p.score = need_score ? c->score.as<int32_t>() : nullptr;
     p.hash = g.want_profile ? c->hash.as<uint32_t>() : nullptr;
@@ -462,6 +477,7 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
 
     { int prc = probe_layout(c, h_raw, h_off, d_raw, d_off, nbytes, n, (mode & DM_NEED_CIGAR) != 0, (mode & DM_NEED_AUX) != 0); if (prc) return prc; }
     p.head_chunks = c->lay_hc; p.tail_chunks = c->lay_tc;
+    cudaEvent_t k0 = get_event(c), k1 = get_event(c);
     CU(cudaEventRecord(k0, c->stream));
     // L2 fill granularity of the window loads: 64-byte granules (.L2::64B) or whole 128-byte lines.  MSG_L2_GRANULE=64|128 overrides.
     static const int g_env = getenv("MSG_L2_GRANULE") ? atoi(getenv("MSG_L2_GRANULE")) : 0;
@@ -471,25 +487,39 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
     LAUNCHED(c);
     CU(cudaEventRecord(k1, c->stream));
     c->ev_decode.push_back({k0, k1});
+    *out = p;
+    return MSG_OK;
+}
 
-    int rc = MSG_OK;
-    if (c->fused_enabled && g.want_profile) {
-        bool done = false;
-        rc = fused_stage(c, p, n, &done);
-        if (rc) return rc;
-        if (done) {                                  // device errors were already checked with the guard readback
-            CU(cudaEventRecord(t1, c->stream));
-            c->ev_total.push_back({t0, t1});
-            return MSG_OK;
-        }
-    }
-    if (zero_copy) {                                 // fused pass declined the chunk: the kernels below re-read records, stage them
-        CU(c->raw.reserve(nbytes + 64));
-        CU(cudaMemcpyAsync(c->raw.p, h_raw, nbytes, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemsetAsync((uint8_t *)c->raw.p + nbytes, 0, 64, c->stream));
-        c->h2d_bytes += nbytes;
-        c->cur_raw = d_raw = c->raw.as<uint8_t>();
-    }
+int chunk_args_ok(msg_ctx *c, uint64_t nbytes, uint64_t n)
+{
+    if (n >= 0xffffffffull) return fail(c, MSG_EINVAL, "a chunk may hold at most 2^32-2 records");
+    if (nbytes >= (1ull << 36)) return fail(c, MSG_EINVAL, "a chunk may hold at most 64 GiB of records");
+    return MSG_OK;
+}
+
+// The general pipeline, synchronous: decode -> stream of kept records in reference output order -> profile / coverage /
+// record output.  d_raw must be device memory (later kernels read whole records).  Every configuration can take it; the
+// fused pass (fused_enqueue) is the fast path for filter --besthit|--uniqhit | profile.
+int run_chunk_general(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readable, const uint64_t *d_off, uint64_t n,
+                      const uint8_t *h_raw = nullptr, const uint64_t *h_off = nullptr)
+{
+    const msg_config &g = c->cfg;
+    { int rc0 = chunk_args_ok(c, nbytes, n); if (rc0) return rc0; }
+    c->cur_raw = d_raw; c->cur_off = d_off; c->cur_n = n; c->cur_nbytes = nbytes;
+    c->n_kept = 0; c->have_stream = false; c->out_bytes = 0;
+    if (n == 0) return MSG_OK;
+
+    cudaEvent_t t0 = get_event(c), t1 = get_event(c);
+    CU(cudaEventRecord(t0, c->stream));
+    DecodeParams p;
+    int rc = launch_decode(c, d_raw, nbytes, readable, d_off, n, h_raw, h_off, &p);
+    if (rc) return rc;
+    // the kernels below follow rec_off[] into the record bytes: a malformed index must be reported before they run
+    rc = check_device_errors(c);
+    if (rc) return rc;
+
+    const bool hit = g.do_filter && g.hit_mode != MSG_HIT_NONE;
     // ---- filter stage -> stream of kept records in reference output order
     const uint32_t *stream = nullptr; uint64_t m = n;
     if (g.do_filter) {
@@ -515,7 +545,7 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
     }
     c->n_kept = m;
 
-    if (g.want_profile) { rc = profile_stage(c, stream, m); if (rc) return rc; }
+    if (g.want_profile) { rc = profile_stage(c, stream, m); if (rc) return rc; c->cursor_dirty = true; }
     if (g.want_coverage && !c->cov_fused && m) {
         coverage_stream_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(d_raw, d_off, stream, m, g.n_targets, c->d_diff, c->d_covbase,
                                                                       c->d_tlen, c->d_covered, c->d_err); LAUNCHED(c);
@@ -527,6 +557,131 @@ int run_chunk(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readab
     CU(cudaEventRecord(t1, c->stream));
     c->ev_total.push_back({t0, t1});
     return check_device_errors(c);
+}
+
+// Finish the chunk in flight in slot s: wait for its kernels, read its results out of the pinned block, report its
+// errors; if the fused guard declined it, rerun it on the general pipeline (after the other chunk in flight, so that
+// the host's list cursors are current).
+int complete_slot(msg_ctx *c, int s)
+{
+    Slot &sl = c->slot[s];
+    if (!sl.pending) return MSG_OK;
+    CU(cudaEventSynchronize(sl.done));
+    sl.pending = false;
+    c->inflight_lists -= sl.ub_lists; c->inflight_ent -= sl.ub_ent;
+    const uint32_t *h = sl.h_res;
+    c->d2h_bytes += 36;
+    c->fused_chunks++;
+    c->cur_raw = sl.d_raw; c->cur_off = sl.d_off; c->cur_n = sl.n; c->cur_nbytes = sl.nbytes;
+    c->out_bytes = 0;
+    { int erc = report_device_errors(c, h + 8); if (erc) return erc; }
+    if (!h[3]) {
+        c->csr_lists = h[5]; c->csr_ent = h[6];
+        c->n_kept = h[4]; c->have_stream = false;
+        return MSG_OK;
+    }
+    // guard tripped: fused_commit_kernel dropped this chunk's partial sums and put the list cursors back
+    c->fused_fallbacks++;
+    int rc = complete_slot(c, s ^ 1);
+    if (rc) return rc;
+    const uint8_t *d_raw = sl.d_raw; uint64_t readable = sl.readable;
+    if (sl.zero_copy) {                              // the kernels of the general pipeline re-read whole records: stage them
+        CU(sl.raw.reserve(sl.nbytes + 64));
+        CU(cudaMemcpyAsync(sl.raw.p, sl.h_raw, sl.nbytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync((uint8_t *)sl.raw.p + sl.nbytes, 0, 64, c->stream));
+        c->h2d_bytes += sl.nbytes;
+        d_raw = sl.raw.as<uint8_t>(); readable = sl.nbytes + 64;
+    }
+    return run_chunk_general(c, d_raw, sl.nbytes, readable, sl.d_off, sl.n, sl.h_raw, sl.h_off);
+}
+
+int wait_all(msg_ctx *c)
+{
+    int rc = complete_slot(c, c->next_slot);         // older chunk first
+    int rc2 = complete_slot(c, c->next_slot ^ 1);
+    return rc ? rc : rc2;
+}
+
+// Queue one chunk.  Host chunks (h_raw != NULL) are staged into the slot's device buffers on the copy stream, or -- pinned,
+// mapped, 16-byte aligned buffers -- decoded in place over PCIe (zero-copy windows); device chunks are used where they are.
+// Configurations outside the fused pass complete the chunk before returning.
+int push_chunk(msg_ctx *c, const uint8_t *h_raw, const uint8_t *dev_raw, size_t nbytes, const uint64_t *h_off, const uint64_t *dev_off, size_t nrec)
+{
+    const msg_config &g = c->cfg;
+    { int rc0 = chunk_args_ok(c, nbytes, nrec); if (rc0) return rc0; }
+    if (nrec == 0) { int rc = wait_all(c); c->cur_n = 0; c->n_kept = 0; c->out_bytes = 0; return rc; }
+    const bool fused = c->fused_enabled && g.want_profile;
+    const int s = c->next_slot;
+    int rc = fused ? complete_slot(c, s) : wait_all(c);          // the chunk pushed two calls ago / everything
+    if (rc) return rc;
+    Slot &sl = c->slot[fused ? s : 0];
+    sl.h_raw = h_raw; sl.h_off = h_off; sl.nbytes = nbytes; sl.n = nrec; sl.zero_copy = false;
+
+    cudaEvent_t t0 = get_event(c), t1 = get_event(c);
+    if (dev_raw) {
+        sl.d_raw = dev_raw; sl.d_off = dev_off; sl.readable = nbytes & ~(size_t)15;          // never read past the caller's nbytes
+        CU(cudaEventRecord(t0, c->stream));
+    } else {
+        CU(sl.off.reserve((nrec + 1) * 8));
+        sl.d_off = sl.off.as<uint64_t>();
+        // Pinned (mapped) host buffer + fused pass: do not copy the chunk at all.  The decode kernel reads its head / tail
+        // windows straight from host memory, so only ~55 % of the BAM bytes cross PCIe (64-byte granules around the
+        // windows; SEQ/QUAL stay on the host).  MSG_ZERO_COPY=0 forces the staged copy.
+        static const bool zc_allowed = !(getenv("MSG_ZERO_COPY") && atoi(getenv("MSG_ZERO_COPY")) == 0);
+        cudaPointerAttributes at;
+        if (zc_allowed && fused && !((uintptr_t)h_raw & 15u) && cudaPointerGetAttributes(&at, h_raw) == cudaSuccess &&
+            at.type == cudaMemoryTypeHost && at.devicePointer) {
+            sl.zero_copy = true;
+            sl.d_raw = static_cast<const uint8_t *>(at.devicePointer); sl.readable = nbytes & ~(size_t)15;
+            CU(cudaEventRecord(t0, c->stream));
+            CU(cudaMemcpyAsync(sl.off.p, h_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+            c->h2d_bytes += (nrec + 1) * 8;
+            c->zc_chunks++;
+        } else {
+            cudaGetLastError();
+            CU(sl.raw.reserve(nbytes + 64));
+            sl.d_raw = sl.raw.as<uint8_t>(); sl.readable = nbytes + 64;
+            // the copy stream fills this slot while the previous chunk's kernels run on the main stream
+            cudaStream_t cs = fused ? c->copy_stream : c->stream;
+            CU(cudaEventRecord(t0, cs));
+            CU(cudaMemcpyAsync(sl.raw.p, h_raw, nbytes, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemsetAsync((uint8_t *)sl.raw.p + nbytes, 0, 64, cs));
+            CU(cudaMemcpyAsync(sl.off.p, h_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, cs));
+            if (fused) { CU(cudaEventRecord(sl.copied, cs)); CU(cudaStreamWaitEvent(c->stream, sl.copied, 0)); }
+            c->h2d_bytes += nbytes + (nrec + 1) * 8;
+        }
+    }
+    if (fused) {
+        DecodeParams p;
+        const uint64_t before = c->h2d_bytes;
+        rc = launch_decode(c, sl.d_raw, nbytes, sl.readable, sl.d_off, nrec, h_raw, h_off, &p);
+        if (rc) return rc;
+        // bytes the decode kernel asks for over PCIe (window chunks)
+        if (sl.zero_copy && c->h2d_bytes == before) c->h2d_bytes += (uint64_t)nrec * (c->lay_hc + c->lay_tc) * 16;
+        bool queued = false;
+        rc = fused_enqueue(c, p, nrec, sl, &queued);
+        if (rc) return rc;
+        if (queued) {
+            CU(cudaEventRecord(t1, c->stream));
+            CU(cudaEventRecord(sl.done, c->stream));
+            c->ev_total.push_back({t0, t1});
+            sl.pending = true;
+            c->next_slot = s ^ 1;
+            return MSG_OK;
+        }
+        rc = wait_all(c);
+        if (rc) return rc;
+    }
+    c->ev_free.push_back(t0); c->ev_free.push_back(t1);
+    const uint8_t *d_raw = sl.d_raw; uint64_t readable = sl.readable;
+    if (sl.zero_copy) {
+        CU(sl.raw.reserve(nbytes + 64));
+        CU(cudaMemcpyAsync(sl.raw.p, h_raw, nbytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync((uint8_t *)sl.raw.p + nbytes, 0, 64, c->stream));
+        c->h2d_bytes += nbytes;
+        d_raw = sl.raw.as<uint8_t>(); readable = nbytes + 64;
+    }
+    return run_chunk_general(c, d_raw, nbytes, readable, sl.d_off, nrec, h_raw, h_off);
 }
 
 int allreduce(msg_ctx *c, void *buf, size_t count, ncclDataType_t dt, ncclRedOp_t op)
@@ -593,6 +748,12 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     const msg_config &g = ctx->cfg;
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { int rc__ = fail(nullptr, e__ == cudaErrorMemoryAllocation ? MSG_ENOMEM : MSG_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); msg_destroy(ctx); return rc__; } } while (0)
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (Slot &sl : ctx->slot) {
+        CUC(cudaHostAlloc((void **)&sl.h_res, 64, cudaHostAllocPortable)); memset(sl.h_res, 0, 64);
+        CUC(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
     ctx->has_filter = g.do_filter && (g.min_length > 0 || g.ppt != 0 || g.max_clip < 100);        // msam_filter.c:79-81
     ctx->need_stats = g.do_filter && (ctx->has_filter || g.rescore);                             // :104
     ctx->cov_fused = g.want_coverage && !(g.do_filter && g.hit_mode != MSG_HIT_NONE);
@@ -624,7 +785,7 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
         CUC(cudaMalloc(&ctx->d_U, F * 8)); CUC(cudaMalloc(&ctx->d_a, F * 8)); CUC(cudaMalloc(&ctx->d_inc, 3 * F * 8));
         CUC(cudaHostAlloc((void **)&ctx->h_ab, F * 8, cudaHostAllocPortable));
         CUC(cudaMalloc(&ctx->d_partial, ((F + 255) / 256) * 8)); CUC(cudaMalloc(&ctx->d_delta, 8 * 20)); CUC(cudaMalloc(&ctx->d_purged, 4)); CUC(cudaMalloc(&ctx->d_bflag, 8)); CUC(cudaMemset(ctx->d_bflag, 0, 8));
-        CUC(cudaMalloc(&ctx->d_ui_tmp, F * 4)); CUC(cudaMalloc(&ctx->d_d_tmp, F * 8)); CUC(cudaMalloc(&ctx->d_fcnt, 32)); CUC(cudaMalloc(&ctx->d_cursor, 8));
+        CUC(cudaMalloc(&ctx->d_ui_tmp, F * 4)); CUC(cudaMalloc(&ctx->d_d_tmp, F * 8)); CUC(cudaMalloc(&ctx->d_fcnt, 32)); CUC(cudaMalloc(&ctx->d_cursor, 16));
         CUC(cudaMemset(ctx->d_ui_tmp, 0, F * 4)); CUC(cudaMemset(ctx->d_d_tmp, 0, F * 8));
         // the fused pass applies when the profile is the filter stage's only consumer (MSG_NO_FUSED=1 forces the general pipeline)
         ctx->fused_enabled = g.do_filter && g.hit_mode != MSG_HIT_NONE && !g.want_records && !g.want_kept && !g.want_coverage && !getenv("MSG_NO_FUSED");
@@ -650,7 +811,10 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
         if (g.want_profile && g.n_ranks <= 16 && g_nccl.AllGather) {
             // Map every rank's publish region into this process (CUDA IPC over NVLink).  If any rank cannot, all ranks
             // agree (allreduce-min) to keep the NCCL-per-iteration loop instead.
-            const size_t region = 128 + 2 * (size_t)g.n_ranks * (F + 8) * 16;    // profile.cuh: purged[16] u64, slot[2][n_ranks][F + 8][2] u64
+            // profile.cuh: small vectors travel as flagged words, all to all (purged[16] u64, slot[2][n_ranks][F + 8][2] u64);
+            // gene catalogues use the reduce-scatter / all-gather layout (RsagLayout, ~4 * F * 8 bytes)
+            const size_t region = F + 8 <= EM_XCHG_CTA0 ? 128 + 2 * (size_t)g.n_ranks * (F + 8) * 16 : rsag_layout((uint32_t)F, g.n_ranks).total();
+            ctx->peer_region_bytes = region;
             int ok = 1;
             cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof mine);
             unsigned char *d_hs = nullptr; int *d_ok = nullptr;
@@ -687,11 +851,19 @@ void msg_destroy(msg_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (Slot &sl : c->slot) {
+        sl.raw.release(); sl.off.release();
+        if (sl.h_res) cudaFreeHost(sl.h_res);
+        if (sl.copied) cudaEventDestroy(sl.copied);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (void *pp : c->ipc_opened) cudaIpcCloseMemHandle(pp);
     if (c->peer_region) cudaFree(c->peer_region);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    DevBuf *bufs[] = {&c->raw, &c->off, &c->tid, &c->fb, &c->score, &c->hash, &c->nid, &c->st_alen, &c->st_qlen, &c->st_qclip, &c->st_edit,
+    DevBuf *bufs[] = {&c->tid, &c->fb, &c->score, &c->hash, &c->nid, &c->st_alen, &c->st_qlen, &c->st_qclip, &c->st_edit,
                       &c->kbase, &c->worklist, &c->gmeta, &c->out_idx, &c->tile_sums, &c->pcount, &c->scanv, &c->biglist, &c->out_len, &c->out_off, &c->plan, &c->out_rec,
                       &c->csr_off, &c->csr_len, &c->csr_fid, &c->win, &c->t_ui, &c->t_d, &c->t_cnt, &c->t_cov};
     for (DevBuf *b : bufs) b->release();
@@ -712,6 +884,9 @@ int msg_reset(msg_ctx *c)
 {
     if (!c) return MSG_EINVAL;
     CU(cudaSetDevice(c->cfg.device));
+    for (int k = 0; k < 2; k++)                       // results of chunks still in flight are dropped with the rest of the state
+        if (c->slot[k].pending) { cudaEventSynchronize(c->slot[k].done); c->slot[k].pending = false; }
+    c->inflight_lists = c->inflight_ent = 0; c->cursor_dirty = true; c->next_slot = 0;
     const msg_config &g = c->cfg;
     const size_t T = (size_t)(g.n_targets > 0 ? g.n_targets : 1), F = (size_t)(g.n_features > 0 ? g.n_features : 1);
     CU(cudaMemsetAsync(c->d_err, 0, 4, c->stream));
@@ -800,57 +975,60 @@ int msg_sync(msg_ctx *c)
 {
     if (!c) return MSG_EINVAL;
     CU(cudaSetDevice(c->cfg.device));
+    int wrc = wait_all(c);
     CU(cudaStreamSynchronize(c->stream));
     harvest_events(c);
-    return MSG_OK;
+    return wrc;
 }
 
-int msg_push(msg_ctx *c, const uint8_t *raw, size_t nbytes, const uint64_t *rec_off, size_t nrec)
+int msg_push_async(msg_ctx *c, const uint8_t *raw, size_t nbytes, const uint64_t *rec_off, size_t nrec)
 {
     if (!c || (nrec && (!raw || !rec_off))) return MSG_EINVAL;
     CU(cudaSetDevice(c->cfg.device));
-    if (nrec == 0) { c->cur_n = 0; c->n_kept = 0; c->out_bytes = 0; return MSG_OK; }
-    CU(c->off.reserve((nrec + 1) * 8));
-    // Pinned (mapped) host buffer + fused filter->profile pass: do not copy the chunk at all.  The decode kernel reads
-    // its head / tail windows straight from host memory, so only ~55 % of the BAM bytes cross PCIe (64-byte granules
-    // around the windows; SEQ/QUAL stay on the host).  MSG_ZERO_COPY=0 forces the staged copy.
-    static const bool zc_allowed = !(getenv("MSG_ZERO_COPY") && atoi(getenv("MSG_ZERO_COPY")) == 0);
-    if (zc_allowed && c->fused_enabled && c->cfg.want_profile && !((uintptr_t)raw & 15u)) {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, raw) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-            CU(cudaMemcpyAsync(c->off.p, rec_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-            c->h2d_bytes += (nrec + 1) * 8;
-            c->zc_chunks++;
-            const uint64_t before = c->h2d_bytes;
-            int rc = run_chunk(c, static_cast<const uint8_t *>(at.devicePointer), nbytes, nbytes & ~(size_t)15, c->off.as<uint64_t>(), nrec, raw, rec_off, true);
-            // bytes the decode kernel asked for (window chunks); a staged fallback has already counted the whole chunk
-            if (c->h2d_bytes == before) c->h2d_bytes += (uint64_t)nrec * (c->lay_hc + c->lay_tc) * 16;
-            return rc;
-        }
-        cudaGetLastError();
-    }
-    CU(c->raw.reserve(nbytes + 64));
-    CU(cudaMemcpyAsync(c->raw.p, raw, nbytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemsetAsync((uint8_t *)c->raw.p + nbytes, 0, 64, c->stream));
-    CU(cudaMemcpyAsync(c->off.p, rec_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    c->h2d_bytes += nbytes + (nrec + 1) * 8;
-    return run_chunk(c, c->raw.as<uint8_t>(), nbytes, nbytes + 64, c->off.as<uint64_t>(), nrec, raw, rec_off);
+    return push_chunk(c, raw, nullptr, nbytes, rec_off, nullptr, nrec);
 }
 
-int msg_push_device(msg_ctx *c, const uint8_t *d_raw, size_t nbytes, const uint64_t *d_rec_off, size_t nrec)
+int msg_push_device_async(msg_ctx *c, const uint8_t *d_raw, size_t nbytes, const uint64_t *d_rec_off, size_t nrec)
 {
     if (!c || (nrec && (!d_raw || !d_rec_off))) return MSG_EINVAL;
     if ((uintptr_t)d_raw & 15u) return fail(c, MSG_EINVAL, "device chunk must be 16-byte aligned");
     CU(cudaSetDevice(c->cfg.device));
-    return run_chunk(c, d_raw, nbytes, nbytes & ~(size_t)15, d_rec_off, nrec);       // never read past the caller's nbytes
+    return push_chunk(c, nullptr, d_raw, nbytes, nullptr, d_rec_off, nrec);
 }
 
-int msg_kept_count(msg_ctx *c, size_t *n_kept) { if (!c || !n_kept) return MSG_EINVAL; *n_kept = c->n_kept; return MSG_OK; }
+int msg_wait(msg_ctx *c)
+{
+    if (!c) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    return wait_all(c);
+}
+
+int msg_push(msg_ctx *c, const uint8_t *raw, size_t nbytes, const uint64_t *rec_off, size_t nrec)
+{
+    int rc = msg_push_async(c, raw, nbytes, rec_off, nrec);
+    return rc ? rc : wait_all(c);
+}
+
+int msg_push_device(msg_ctx *c, const uint8_t *d_raw, size_t nbytes, const uint64_t *d_rec_off, size_t nrec)
+{
+    int rc = msg_push_device_async(c, d_raw, nbytes, d_rec_off, nrec);
+    return rc ? rc : wait_all(c);
+}
+
+int msg_kept_count(msg_ctx *c, size_t *n_kept)
+{
+    if (!c || !n_kept) return MSG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    { int wrc = wait_all(c); if (wrc) return wrc; }
+    *n_kept = c->n_kept;
+    return MSG_OK;
+}
 
 int msg_pull_kept(msg_ctx *c, uint32_t *idx, size_t cap, size_t *n_kept)
 {
     if (!c) return MSG_EINVAL;
     CU(cudaSetDevice(c->cfg.device));
+    { int wrc = wait_all(c); if (wrc) return wrc; }
     if (n_kept) *n_kept = c->n_kept;
     if (!idx) return MSG_OK;
     if (c->cfg.do_filter && !c->cfg.want_kept) return fail(c, MSG_ESTATE, "context was created without want_kept");
@@ -868,6 +1046,7 @@ int msg_pull_records(msg_ctx *c, uint8_t *out, size_t cap, size_t *nbytes, size_
     if (!c) return MSG_EINVAL;
     if (!c->cfg.want_records) return fail(c, MSG_ESTATE, "context was created without want_records");
     CU(cudaSetDevice(c->cfg.device));
+    { int wrc = wait_all(c); if (wrc) return wrc; }
     if (nbytes) *nbytes = c->out_bytes;
     if (nrec) *nrec = c->n_kept;
     if (!out) return MSG_OK;
@@ -884,6 +1063,7 @@ int msg_pull_stats(msg_ctx *c, size_t nrec, int32_t *alen, int32_t *qlen, int32_
 {
     if (!c) return MSG_EINVAL;
     if (!c->cfg.want_stats) return fail(c, MSG_ESTATE, "context was created without want_stats");
+    { int wrc = wait_all(c); if (wrc) return wrc; }
     if (nrec != c->cur_n) return fail(c, MSG_EINVAL, "nrec does not match the last chunk");
     CU(cudaSetDevice(c->cfg.device));
     if (nrec == 0) return MSG_OK;
@@ -905,6 +1085,7 @@ int msg_pull_counts(msg_ctx *c, uint32_t *ui, double *d)
     if (!c) return MSG_EINVAL;
     if (!c->cfg.want_profile) return fail(c, MSG_ESTATE, "context was created without want_profile");
     CU(cudaSetDevice(c->cfg.device));
+    { int wrc = wait_all(c); if (wrc) return wrc; }
     const size_t F = (size_t)c->cfg.n_features;
     if (ui && F) CU(cudaMemcpyAsync(ui, c->d_ui, F * 4, cudaMemcpyDeviceToHost, c->stream));
     if (d && F)  CU(cudaMemcpyAsync(d, c->d_d, F * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -917,6 +1098,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
     if (!c) return MSG_EINVAL;
     if (!c->cfg.want_profile) return fail(c, MSG_ESTATE, "context was created without want_profile");
     CU(cudaSetDevice(c->cfg.device));
+    { int wrc = wait_all(c); if (wrc) return wrc; }
     const msg_config &g = c->cfg;
     const uint32_t F = (uint32_t)g.n_features;
     msg_profile_stats s; memset(&s, 0, sizeof s);
@@ -975,7 +1157,9 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
             const size_t shm = sm ? (size_t)F * 8 * (1 + em_copies(F)) : 0;
             int per_sm = 0, nsm = 0;
             CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, g.device));
-            if (g.n_ranks > 1) {
+            const bool rsag = g.n_ranks > 1 && F + 8 > EM_XCHG_CTA0;       // gene catalogues: reduce-scatter / all-gather exchange
+            if (rsag) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_rsag_kernel, 256, 0));
+            else if (g.n_ranks > 1) {
                 if (sm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_multi_kernel<true>, 256, shm));
                 else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_multi_kernel<false>, 256, shm));
             } else {
@@ -1001,13 +1185,28 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 if (g.n_ranks > 1) { CU(c->t_cnt.reserve(64)); hc_dev = c->t_cnt.as<uint32_t>(); }
                 double *totbuf = nullptr; uint32_t *bflag = c->d_bflag;
                 if (g.n_ranks > 1) { CU(c->t_d.reserve((size_t)F * 16)); totbuf = c->t_d.as<double>(); }
+                static const double peer_timeout_s = getenv("MSG_PEER_TIMEOUT_S") ? atof(getenv("MSG_PEER_TIMEOUT_S")) : 120.0;
+                unsigned long long timeout_ns = (unsigned long long)(peer_timeout_s * 1e9);
                 void *margs[] = {&a0, &a1, &a2, &nl_arg, &ui_arg, &cnt_arg, &nl_lo, &nl_hi, &Uw, &av, &inc, &partial, &F_arg, &dout, &d_res, &hc_dev,
-                                 &totbuf, &bflag, &pt, &nr, &rk, &epoch};
+                                 &totbuf, &bflag, &pt, &nr, &rk, &epoch, &timeout_ns};
+                void *rargs[] = {&a0, &a1, &a2, &nl_arg, &ui_arg, &cnt_arg, &nl_lo, &nl_hi, &Uw, &av, &inc, &F_arg, &dout, &d_res, &hc_dev,
+                                 &pt, &nr, &rk, &epoch, &timeout_ns};
                 // single GPU: inc[3F], delta and d_res were cleared by em_init_kernel; the multi-GPU kernel clears its own state
                 if (g.n_ranks > 1) {
+                    // The kernels of all ranks wait for one another inside the loop: line the ranks up first (a 4-byte NCCL
+                    // allreduce on the same stream; it waits, on the device, for however long the slowest rank's ingest takes),
+                    // so that the wall-clock limit inside the kernel (MSG_PEER_TIMEOUT_S, default 120 s) only ever measures a
+                    // peer that died, not one that is merely late.
+                    CU(cudaMemsetAsync(d_res, 0, 16, c->stream));
+                    CU(c->t_cnt.reserve(64));
+                    if ((rc = allreduce(c, c->t_cnt.as<uint32_t>() + 8, 1, ncclUint32, ncclSum))) return rc;
+                    if (rsag) {
+                        CU(cudaMemsetAsync(c->d_inc, 0, (size_t)F * 8, c->stream));
+                        CU(cudaLaunchCooperativeKernel((void *)em_loop_rsag_kernel, dim3(grid), dim3(256), rargs, 0, c->stream));
+                    }
                     // compute + collective in one kernel: increments are exchanged through peer memory inside the loop
-                    if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<true>, dim3(grid), dim3(256), margs, shm, c->stream));
-                    else    CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<false>, dim3(grid), dim3(256), margs, shm, c->stream));
+                    else if (sm) CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<true>, dim3(grid), dim3(256), margs, shm, c->stream));
+                    else         CU(cudaLaunchCooperativeKernel((void *)em_loop_multi_kernel<false>, dim3(grid), dim3(256), margs, shm, c->stream));
                     c->em_epoch += 32;
                     CU(cudaMemcpyAsync(hc, hc_dev, 24, cudaMemcpyDeviceToHost, c->stream));
                 } else {
@@ -1092,6 +1291,7 @@ int msg_finish_coverage(msg_ctx *c, uint8_t *covered, int64_t *touched, int64_t 
     if (!c) return MSG_EINVAL;
     if (!c->cfg.want_coverage) return fail(c, MSG_ESTATE, "context was created without want_coverage");
     CU(cudaSetDevice(c->cfg.device));
+    { int wrc = wait_all(c); if (wrc) return wrc; }
     const msg_config &g = c->cfg;
     const size_t T = (size_t)g.n_targets;
     int rc;
@@ -1137,6 +1337,7 @@ int msg_get_timing(msg_ctx *c, msg_timing *t, int reset)
 {
     if (!c || !t) return MSG_EINVAL;
     CU(cudaSetDevice(c->cfg.device));
+    { int wrc = wait_all(c); if (wrc) return wrc; }
     CU(cudaStreamSynchronize(c->stream));
     harvest_events(c);
     unsigned long long acct[2];

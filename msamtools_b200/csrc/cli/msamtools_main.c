@@ -21,6 +21,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -83,36 +85,59 @@ static char *command_line(int argc, char *argv[])
 
 /* ============================================================ record chunks */
 typedef struct {
-    uint8_t *raw; size_t len, cap;
-    uint64_t *off; size_t n, offcap;
+    uint8_t *raw; size_t len, cap;        /* record stream; len may include a partial trailing record (bulk reader) */
+    uint64_t *off; size_t n, offcap;      /* off[0..n]: whole records indexed so far, off[n] = end of the last one */
+    int fixed;                            /* 1: raw is a fixed-capacity (possibly pinned) buffer, never realloc'ed */
+    int pinned;
+    size_t k;                             /* records handed to the GPU (a QNAME boundary) */
 } chunk_t;
+
+static void input_die(bio_file *in)
+{   /* the reference ends the stream silently on sam_read1 < -1 and htslib prints the reason; a drop-in that keeps going
+       after a corrupt block would write a partial result with exit status 0, so this one stops */
+    mDie("Cannot read input: %s", bio_error(in));
+}
 
 static void chunk_reserve_off(chunk_t *c, size_t n)
 {
     if (n + 2 > c->offcap) { c->offcap = c->offcap ? c->offcap * 2 : 1 << 16; while (n + 2 > c->offcap) c->offcap *= 2; c->off = realloc(c->off, c->offcap * sizeof(uint64_t)); if (!c->off) mDie("Out of memory"); }
 }
 
-/* append records until the chunk holds `want_records` / `want_bytes` or the input ends; 1 = more input may follow */
-static int chunk_fill(chunk_t *c, bio_file *in, const bio_hdr *h, size_t want_records, size_t want_bytes, int *eof)
+/* record-wise: append records until the chunk holds `want_records` / `want_bytes` or the input ends */
+static void chunk_fill(chunk_t *c, bio_file *in, const bio_hdr *h, size_t want_records, size_t want_bytes, int *eof)
 {
-    while (c->n < want_records && c->len < want_bytes) {
+    while (!*eof && c->n < want_records && c->len < want_bytes) {
         chunk_reserve_off(c, c->n + 1);
         c->off[c->n] = c->len;
         int rc = bio_read_record(in, h, &c->raw, &c->cap, &c->len);
-        if (rc <= 0) { *eof = 1; break; }              /* EOF or unreadable record ends the stream (msam_filter.c:119) */
+        if (rc < 0) input_die(in);
+        if (rc == 0) { *eof = 1; break; }
         c->n++;
     }
     chunk_reserve_off(c, c->n);
     c->off[c->n] = c->len;
-    return !*eof;
 }
 
-static void chunk_drop_front(chunk_t *c, size_t k)
+/* bulk (BAM): inflate straight into the fixed-capacity buffer, then walk the block_size chain over the new bytes */
+static void chunk_fill_bulk(chunk_t *c, bio_file *in, size_t want_records, size_t want_bytes, int *eof)
 {
-    size_t base = (size_t)c->off[k];
-    memmove(c->raw, c->raw + base, c->len - base);
-    for (size_t i = k; i <= c->n; i++) c->off[i - k] = c->off[i] - base;
-    c->n -= k; c->len -= base;
+    if (want_bytes > c->cap) want_bytes = c->cap;
+    while (!*eof && c->n < want_records && c->len < want_bytes) {
+        int rc = bio_read_raw(in, c->raw, c->cap, &c->len);
+        if (rc < 0) input_die(in);
+        if (rc == 0) { *eof = 1; break; }
+        size_t o = (size_t)c->off[c->n];
+        while (o + 4 <= c->len) {
+            uint32_t bs = (uint32_t)c->raw[o] | (uint32_t)c->raw[o + 1] << 8 | (uint32_t)c->raw[o + 2] << 16 | (uint32_t)c->raw[o + 3] << 24;
+            if (bs < 32 || bs > 0x7fffffffu) mDie("Cannot read input: corrupt BAM record");
+            if (o + 4 + (size_t)bs > c->len) break;
+            o += 4 + (size_t)bs;
+            chunk_reserve_off(c, c->n + 1);
+            c->off[++c->n] = o;
+        }
+        if (rc == 2) break;                                  /* buffer full */
+    }
+    if (*eof && (size_t)c->off[c->n] != c->len) mDie("Cannot read input: truncated BAM record");
 }
 
 static int names_differ(const chunk_t *c, size_t a, size_t b)
@@ -216,14 +241,100 @@ static qn_result qname_preflight(const bio_hdr *h, const chunk_t *c)
 typedef struct {
     msg_config cfg;
     bio_file *in; bio_hdr *hdr;
-    chunk_t chunk; int eof;
+    chunk_t chunk; int eof;               /* filled with the first records by the QNAME pre-flight */
     bio_file *out; bio_hdr *out_hdr;      /* filter only */
+    const char *path;
 } run_t;
 
-#define CHUNK_RECORDS ((size_t)4 << 20)
-#define CHUNK_BYTES   ((size_t)1536 << 20)
+/* chunk size: records / bytes per push (MSAMTOOLS_CHUNK_RECORDS / MSAMTOOLS_CHUNK_MB override, for tests and tuning) */
+static size_t env_size(const char *name, size_t dflt, size_t unit) { const char *e = getenv(name); return e && atol(e) > 0 ? (size_t)atol(e) * unit : dflt; }
+#define CHUNK_RECORDS env_size("MSAMTOOLS_CHUNK_RECORDS", (size_t)4 << 20, 1)
+#define CHUNK_BYTES   env_size("MSAMTOOLS_CHUNK_MB", (size_t)1024 << 20, (size_t)1 << 20)
+#define NBUF 3
 
 static void gpu_die(msg_ctx *ctx) { mDie("%s", msg_last_error(ctx)); }
+
+/* Reader thread <-> GPU thread: a ring of NBUF chunk buffers.  The reader fills buffer i (BGZF blocks are inflated on
+ * worker threads straight into it, msam_helper.c:246-268 becomes bulk ingest), cuts it at a QNAME boundary, moves the
+ * tail behind the cut to the front of buffer i+1 and posts it; the GPU thread pushes posted chunks with msg_push_async
+ * and gives a buffer back two pushes later (the library may still be reading it until then). */
+typedef struct {
+    run_t *r;
+    chunk_t buf[NBUF];
+    int state[NBUF];                      /* 0 free, 1 posted */
+    int posted_last;                      /* the posted chunk with this index is the final one (-1: not yet known) */
+    int bulk;
+    pthread_mutex_t mu; pthread_cond_t cv;
+} ring_t;
+
+static size_t choose_cut(chunk_t *c, int eof)
+{   /* records to hand over: everything at EOF, else the last QNAME boundary msg_split_point accepts (0: need more input) */
+    if (eof) return c->n;
+    if (c->n < 2) return 0;
+    size_t k = msg_split_point(c->raw, c->off, c->n, c->n - 1);
+    return k;
+}
+
+static void *reader_main(void *arg)
+{
+    ring_t *g = arg; run_t *r = g->r;
+    int cur = 0;
+    for (;;) {
+        chunk_t *c = &g->buf[cur];
+        size_t want_n = CHUNK_RECORDS, want_b = CHUNK_BYTES;
+        size_t k;
+        for (;;) {
+            if (g->bulk) chunk_fill_bulk(c, r->in, want_n, want_b, &r->eof);
+            else chunk_fill(c, r->in, r->hdr, want_n, want_b, &r->eof);
+            k = choose_cut(c, r->eof);
+            if (k || r->eof) break;
+            /* no mapped record closes a QNAME group in the whole chunk: read on (growable buffers), or cut at any QNAME change */
+            if (!c->fixed && c->n < 8 * CHUNK_RECORDS && c->len < 8 * CHUNK_BYTES) { want_n = c->n * 2; want_b = c->len * 2; continue; }
+            for (k = c->n - 1; k > 0 && !names_differ(c, k - 1, k); k--) ;
+            if (k) break;
+            if (c->fixed && c->len + (1 << 17) < c->cap) { want_n = c->n * 2; want_b = c->cap; continue; }
+            mDie("A single QNAME group exceeds the chunk buffer (%zu records, %zu bytes)", c->n, c->len);
+        }
+        c->k = k;
+        const int last = r->eof && k == c->n;
+        const int nxt = (cur + 1) % NBUF;
+        pthread_mutex_lock(&g->mu);                          /* post first: the GPU thread only reads raw[0, off[k]) */
+        g->state[cur] = 1;
+        if (last) g->posted_last = cur;
+        pthread_cond_broadcast(&g->cv);
+        pthread_mutex_unlock(&g->mu);
+        if (!last) {
+            /* the records behind the cut (and a partial trailing record) open the next buffer */
+            pthread_mutex_lock(&g->mu);
+            while (g->state[nxt]) pthread_cond_wait(&g->cv, &g->mu);
+            pthread_mutex_unlock(&g->mu);
+            chunk_t *d = &g->buf[nxt];
+            const size_t base = (size_t)c->off[k], tail = c->len - base;
+            if (!d->fixed && tail > d->cap) { d->raw = realloc(d->raw, tail + (1 << 20)); d->cap = tail + (1 << 20); if (!d->raw) mDie("Out of memory"); }
+            if (tail > d->cap) mDie("A single QNAME group exceeds the chunk buffer");
+            memcpy(d->raw, c->raw + base, tail);
+            d->len = tail; d->n = c->n - k;
+            chunk_reserve_off(d, d->n + 1);
+            for (size_t i = 0; i <= d->n; i++) d->off[i] = c->off[k + i] - base;
+        }
+        if (last) return NULL;
+        cur = nxt;
+    }
+}
+
+static void write_kept_records(run_t *r, msg_ctx *ctx, uint8_t **outbuf, size_t *outcap)
+{
+    size_t nb = 0, nr = 0;
+    if (msg_pull_records(ctx, NULL, 0, &nb, &nr)) gpu_die(ctx);
+    if (nb > *outcap) { *outcap = nb + nb / 4; *outbuf = realloc(*outbuf, *outcap); if (!*outbuf) mDie("Out of memory"); }
+    if (msg_pull_records(ctx, *outbuf, *outcap, &nb, &nr)) gpu_die(ctx);
+    for (size_t o = 0; o < nb;) {
+        const uint8_t *p = *outbuf + o;
+        uint32_t bs = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+        if (bio_write_record(r->out, r->out_hdr, p, 4 + (size_t)bs)) mDie("Cannot write alignment record");
+        o += 4 + (size_t)bs;
+    }
+}
 
 static msg_ctx *run_stream(run_t *r)
 {
@@ -233,42 +344,88 @@ static msg_ctx *run_stream(run_t *r)
     if (getenv("MSAMTOOLS_DEVICE")) r->cfg.device = atoi(getenv("MSAMTOOLS_DEVICE"));
     if (msg_create(&r->cfg, &ctx)) mDie("%s", msg_last_error(NULL));
     uint8_t *outbuf = NULL; size_t outcap = 0;
-    size_t want_n = CHUNK_RECORDS, want_b = CHUNK_BYTES;
     double t_push = 0; size_t n_pushed = 0;
-    for (;;) {
-        if (!r->eof) chunk_fill(&r->chunk, r->in, r->hdr, want_n, want_b, &r->eof);
+    struct timespec ta, tb;
+
+    if (!r->eof) chunk_fill(&r->chunk, r->in, r->hdr, r->chunk.n + 1, (size_t)-1, &r->eof);      /* learn whether there is anything beyond the pre-flight sample */
+    if (r->eof) {
+        /* small input: everything is already in the pre-flight chunk, one synchronous push, no reader thread */
         chunk_t *c = &r->chunk;
-        if (c->n == 0) break;
-        size_t k = c->n;
-        if (!r->eof) {
-            k = msg_split_point(c->raw, c->off, c->n, c->n - 1);
-            if (k == 0) {
-                if (c->n < 8 * CHUNK_RECORDS && c->len < 8 * CHUNK_BYTES) { want_n = c->n * 2; want_b = c->len * 2; continue; }
-                /* no mapped record closes a group for a very long stretch: cut at any QNAME change */
-                for (k = c->n - 1; k > 0 && !names_differ(c, k - 1, k); k--) ;
-                if (k == 0) { want_n = c->n * 2; want_b = c->len * 2; continue; }
+        if (c->n) {
+            clock_gettime(CLOCK_MONOTONIC, &ta);
+            if (msg_push(ctx, c->raw, c->len, c->off, c->n)) gpu_die(ctx);
+            clock_gettime(CLOCK_MONOTONIC, &tb);
+            t_push += (tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec); n_pushed += c->n;
+            if (r->cfg.want_records) write_kept_records(r, ctx, &outbuf, &outcap);
+        }
+    } else {
+        ring_t g; memset(&g, 0, sizeof g);
+        g.r = r; g.posted_last = -1;
+        g.bulk = bio_is_bam(r->in);
+        pthread_mutex_init(&g.mu, NULL); pthread_cond_init(&g.cv, NULL);
+        /* BAM: fixed-capacity buffers the inflate workers write into directly; pinned (so that H2D copies run
+           asynchronously at full PCIe rate) once the input is large enough to pay for page-locking them */
+        int pin = 0;
+        if (g.bulk) {
+            struct stat sb;
+            const char *e = getenv("MSAMTOOLS_PINNED");
+            if (e) pin = atoi(e) != 0;
+            else pin = r->path && strcmp(r->path, "-") != 0 && stat(r->path, &sb) == 0 && (size_t)sb.st_size >= ((size_t)192 << 20);
+        }
+        for (int i = 0; i < NBUF; i++) {
+            chunk_t *c = &g.buf[i];
+            if (!g.bulk) continue;
+            c->fixed = 1; c->cap = CHUNK_BYTES + ((size_t)64 << 20);
+            void *pmem = NULL;
+            if (pin && msg_host_alloc(r->cfg.device, c->cap, &pmem) == MSG_OK) { c->raw = pmem; c->pinned = 1; }
+            else { c->raw = malloc(c->cap); if (!c->raw) mDie("Out of memory"); }
+            chunk_reserve_off(c, 1);
+            c->off[0] = 0;
+        }
+        {   /* the pre-flight records open buffer 0 */
+            chunk_t *c = &g.buf[0], *s0 = &r->chunk;
+            if (c->fixed) {
+                if (s0->len > c->cap) mDie("Out of memory");
+                memcpy(c->raw, s0->raw, s0->len);
+            } else { c->raw = s0->raw; c->cap = s0->cap; s0->raw = NULL; }
+            c->len = s0->len; c->n = s0->n;
+            chunk_reserve_off(c, c->n + 1);
+            memcpy(c->off, s0->off, (s0->n + 1) * sizeof(uint64_t));
+        }
+        pthread_t th;
+        if (pthread_create(&th, NULL, reader_main, &g)) mDie("Cannot start the reader thread");
+        int cur = 0, inflight[2] = { -1, -1 };
+        for (;;) {
+            pthread_mutex_lock(&g.mu);
+            while (!g.state[cur]) pthread_cond_wait(&g.cv, &g.mu);
+            const int last = g.posted_last == cur;
+            pthread_mutex_unlock(&g.mu);
+            chunk_t *c = &g.buf[cur];
+            if (c->k) {
+                clock_gettime(CLOCK_MONOTONIC, &ta);
+                if (msg_push_async(ctx, c->raw, (size_t)c->off[c->k], c->off, c->k)) gpu_die(ctx);
+                clock_gettime(CLOCK_MONOTONIC, &tb);
+                t_push += (tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec); n_pushed += c->k;
+                if (r->cfg.want_records) write_kept_records(r, ctx, &outbuf, &outcap);      /* completes the chunk */
             }
-        }
-        {
-            struct timespec a, b; clock_gettime(CLOCK_MONOTONIC, &a);
-            if (msg_push(ctx, c->raw, (size_t)c->off[k], c->off, k)) gpu_die(ctx);
-            clock_gettime(CLOCK_MONOTONIC, &b);
-            t_push += (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec); n_pushed += k;
-        }
-        if (r->cfg.want_records) {
-            size_t nb = 0, nr = 0;
-            if (msg_pull_records(ctx, NULL, 0, &nb, &nr)) gpu_die(ctx);
-            if (nb > outcap) { outcap = nb + nb / 4; outbuf = realloc(outbuf, outcap); if (!outbuf) mDie("Out of memory"); }
-            if (msg_pull_records(ctx, outbuf, outcap, &nb, &nr)) gpu_die(ctx);
-            for (size_t o = 0; o < nb;) {
-                uint32_t bs = (uint32_t)outbuf[o] | (uint32_t)outbuf[o + 1] << 8 | (uint32_t)outbuf[o + 2] << 16 | (uint32_t)outbuf[o + 3] << 24;
-                if (bio_write_record(r->out, r->out_hdr, outbuf + o, 4 + (size_t)bs)) mDie("Cannot write alignment record");
-                o += 4 + (size_t)bs;
+            /* the buffer pushed two calls ago is no longer referenced by the library */
+            if (inflight[0] >= 0) {
+                pthread_mutex_lock(&g.mu);
+                g.state[inflight[0]] = 0;
+                pthread_cond_broadcast(&g.cv);
+                pthread_mutex_unlock(&g.mu);
             }
+            inflight[0] = inflight[1]; inflight[1] = cur;
+            if (last) break;
+            cur = (cur + 1) % NBUF;
         }
-        if (k == c->n) { c->n = 0; c->len = 0; } else chunk_drop_front(c, k);
-        want_n = CHUNK_RECORDS; want_b = CHUNK_BYTES;
-        if (r->eof && c->n == 0) break;
+        if (msg_wait(ctx)) gpu_die(ctx);
+        pthread_join(th, NULL);
+        for (int i = 0; i < NBUF; i++) {
+            if (g.buf[i].pinned) msg_host_free(g.buf[i].raw); else free(g.buf[i].raw);
+            free(g.buf[i].off);
+        }
+        pthread_mutex_destroy(&g.mu); pthread_cond_destroy(&g.cv);
     }
     free(outbuf);
     if (getenv("MSAMTOOLS_TIMING")) {      /* host-ingest vs GPU time, reported separately (BASELINE.json north_star) */
@@ -283,6 +440,7 @@ static msg_ctx *run_stream(run_t *r)
 
 static void open_input(run_t *r, const char *infile)
 {
+    r->path = infile;
     r->in = bio_open_read(infile);
     if (!r->in) mDie("Cannot open %s for reading", infile);
     {   /* BGZF blocks are inflated on worker threads (MSAMTOOLS_THREADS, default: online cores, at most 16) */
@@ -291,7 +449,7 @@ static void open_input(run_t *r, const char *infile)
         bio_set_threads(r->in, n > 16 ? 16 : (int)n);
     }
     r->hdr = bio_read_header(r->in);
-    if (!r->hdr) mDie("Cannot read header from %s", infile);
+    if (!r->hdr) { if (bio_error(r->in)[0]) mDie("Cannot read header from %s: %s", infile, bio_error(r->in)); mDie("Cannot read header from %s", infile); }
 }
 
 /* ============================================================ filter */

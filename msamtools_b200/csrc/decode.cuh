@@ -32,6 +32,7 @@ struct DecodeParams {
     const uint8_t  *raw;
     const uint64_t *off;
     uint64_t n;
+    uint64_t nbytes;                // size of the chunk: offsets beyond it are malformed
     uint64_t nbytes_readable;       // bytes the 16-byte window loads may touch (multiple of 16; may be < nbytes for caller-owned buffers)
     // outputs (any may be null)
     int32_t  *tid;
@@ -402,11 +403,16 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
     const uint32_t hc = p.head_chunks, tc = p.tail_chunks;
     if (!active) return;
     const uint32_t *slot = s_slot + t * SLOT_WORDS;
-    const uint64_t o = s_off[t], len = s_off[t + 1] - o;
+    // an index that is not monotonic or runs past the chunk is reported (MSG_EFORMAT) without following it
+    const uint64_t o = s_off[t], o1 = s_off[t + 1];
+    const bool off_ok = o1 <= p.nbytes && o <= o1;
+    const uint64_t len = off_ok ? o1 - o : 0;
     const uint32_t rel = (uint32_t)(o & 15u);
     uint32_t arel = 0;
     bool slow = force_slow || o + 36 > p.nbytes_readable;            // (fixed header not fully staged: chunk's last, tiny record)
-    RecCore c = slow ? parse_core(GlAcc{p.raw + o}, len) : parse_core(SmAcc{slot, rel}, len);
+    RecCore c;
+    if (!off_ok || len < 36) { c = RecCore{-1, 0, 0, 0, 0, 0, 0, 0, 0, true}; slow = false; }
+    else c = slow ? parse_core(GlAcc{p.raw + o}, len) : parse_core(SmAcc{slot, rel}, len);
     // does the record fit its windows?
     const uint32_t need_head = 36 + c.lq + ((mode & DM_NEED_CIGAR) ? 4 * c.nc : 0);
     if (rel + need_head > 16 * hc) slow = true;
@@ -430,7 +436,7 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
         r = finish_record(p, c, g, gx);
         const uint64_t op = t ? s_off[t - 1] : off_prev;
         GlAcc gp{p.raw + op};
-        h = name_hash_eq(g, c.lq, gp, i > 0 && gp.u8(12) == c.lq, &eq);
+        h = name_hash_eq(g, c.lq, gp, i > 0 && op + 36 <= o && gp.u8(12) == c.lq, &eq);
         if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
             if (c.tid < p.n_targets) cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
             else atomicOr(p.err, DERR_FORMAT);
@@ -454,7 +460,7 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
         } else {
             const uint64_t op = t ? s_off[t - 1] : off_prev;
             GlAcc gp{p.raw + op};
-            h = name_hash_eq(hd, c.lq, gp, i > 0 && gp.u8(12) == c.lq, &eq);
+            h = name_hash_eq(hd, c.lq, gp, i > 0 && op + 36 <= o && gp.u8(12) == c.lq, &eq);
         }
         if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
             if (c.tid < p.n_targets) cover_record(hd, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);

@@ -310,12 +310,14 @@ __global__ void __launch_bounds__(256) fused_guard_kernel(const WinInfo *win, ui
 }
 
 // commit the chunk-local accumulators: ui += ui_tmp, d += d_tmp (then clear them for the next chunk).  Launched before
-// the host has seen the guard flag, so the decision is repeated here on the device.
+// the host has seen the guard flag, so the decision is repeated here on the device; a declined chunk also gives its
+// list space back (cursor[2..3] = the cursors before the chunk), so that the next chunk may already be queued behind it.
 __global__ void __launch_bounds__(256) fused_commit_kernel(uint32_t *ui, double *d, uint32_t *ui_tmp, double *d_tmp, uint32_t F, int use_d,
-                                                           uint32_t *counters, uint32_t *cnt_tmp)
+                                                           uint32_t *counters, uint32_t *cnt_tmp, uint32_t *cursor)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool tripped = cnt_tmp[3] != 0;          // guard flag: drop the chunk's partial sums (the host reruns it on the general path)
+    if (k == 0 && tripped) { cursor[0] = cursor[2]; cursor[1] = cursor[3]; }
     if (k < F) {
         const uint32_t a = ui_tmp[k]; if (a) { if (!tripped) ui[k] += a; ui_tmp[k] = 0; }
         if (use_d) { const double b = d_tmp[k]; if (b != 0.0) { if (!tripped) d[k] += b; d_tmp[k] = 0.0; } }

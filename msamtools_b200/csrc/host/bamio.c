@@ -91,8 +91,11 @@ static void *bgzf_worker(void *arg)
 
 #define BGZF_BATCH ((size_t)48 << 20)
 
-static int rd_fill_bgzf(bio_file *f)
-{   /* refill f->dec with the inflated payload of the next batch of whole blocks; 0 = EOF, 1 = ok, -1 = error */
+/* Inflate the next batch of whole blocks.  dst == NULL: into f->dec (grown as needed), which becomes the readable window.
+ * dst != NULL: straight into the caller's buffer, as many blocks as fit in dst_cap (*out_len = bytes produced; 0 with
+ * return 1 means "the next block does not fit").  0 = EOF, 1 = ok, -1 = error. */
+static int bgzf_batch(bio_file *f, uint8_t *dst, size_t dst_cap, size_t *out_len)
+{
     for (;;) {
         if (!f->in_eof && f->cin_len < BGZF_BATCH) {
             if (grow(&f->cin, &f->cin_cap, BGZF_BATCH + (1 << 17))) { set_err(f, "out of memory"); return -1; }
@@ -101,7 +104,7 @@ static int rd_fill_bgzf(bio_file *f)
             if (got == 0 || feof(f->fp)) f->in_eof = 1;
         }
         /* split into whole blocks */
-        size_t p = 0, nblk = 0, out = 0, cap = 0; bgzf_blk *blk = NULL;
+        size_t p = 0, nblk = 0, out = 0, cap = 0; bgzf_blk *blk = NULL; int full = 0;
         while (p + 18 <= f->cin_len) {
             const uint8_t *h = f->cin + p;
             if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { free(blk); set_err(f, "corrupt BGZF block header"); return -1; }
@@ -114,22 +117,35 @@ static int rd_fill_bgzf(bio_file *f)
             }
             if (!bsize || bsize < 12 + xlen + 8) { free(blk); set_err(f, "corrupt BGZF block header"); return -1; }
             if (p + bsize > f->cin_len) break;
-            if (nblk == cap) { cap = cap ? 2 * cap : 1024; blk = realloc(blk, cap * sizeof *blk); }
+            const uint32_t isize = le32(h + bsize - 4);
+            if (isize > 65536) { free(blk); set_err(f, "corrupt BGZF block header"); return -1; }      /* SAM spec 4.1: ISIZE <= 65536 */
+            if (dst && out + isize > dst_cap) { full = 1; break; }
+            if (nblk == cap) {
+                cap = cap ? 2 * cap : 1024;
+                bgzf_blk *nb = realloc(blk, cap * sizeof *blk);
+                if (!nb) { free(blk); set_err(f, "out of memory"); return -1; }
+                blk = nb;
+            }
             blk[nblk].in_off = p + 12 + xlen; blk[nblk].in_len = bsize - 12 - xlen - 8; blk[nblk].out_off = out;
-            blk[nblk].crc = le32(h + bsize - 8); blk[nblk].isize = le32(h + bsize - 4);
-            out += blk[nblk].isize; nblk++; p += bsize;
+            blk[nblk].crc = le32(h + bsize - 8); blk[nblk].isize = isize;
+            out += isize; nblk++; p += bsize;
         }
         if (nblk == 0) {
             free(blk);
+            if (full) { *out_len = 0; return 1; }
             if (!f->in_eof) continue;
             if (f->cin_len) { set_err(f, "truncated BGZF block"); return -1; }
             return 0;
         }
-        if (grow(&f->dec, &f->dec_cap, out + 16)) { free(blk); set_err(f, "out of memory"); return -1; }
+        uint8_t *target = dst;
+        if (!dst) {
+            if (grow(&f->dec, &f->dec_cap, out + 16)) { free(blk); set_err(f, "out of memory"); return -1; }
+            target = f->dec;
+        }
         int nthr = f->threads; if ((size_t)nthr > nblk) nthr = (int)nblk;
         pthread_t th[64]; bgzf_job job[64];
         for (int i = 0; i < nthr; i++) {
-            job[i] = (bgzf_job){ f->cin, f->dec, blk, nblk, i, nthr, 0, 0, 0 };
+            job[i] = (bgzf_job){ f->cin, target, blk, nblk, i, nthr, 0, 0, 0 };
             if (i && pthread_create(&th[i], NULL, bgzf_worker, &job[i])) { job[i].err = 2; }
         }
         bgzf_worker(&job[0]);
@@ -139,9 +155,16 @@ static int rd_fill_bgzf(bio_file *f)
         free(blk);
         if (err) { set_err(f, "corrupt BGZF block (inflate/CRC)"); return -1; }
         memmove(f->cin, f->cin + p, f->cin_len - p); f->cin_len -= p;
-        f->dec_pos = 0; f->dec_len = out;
+        if (!dst) { f->dec_pos = 0; f->dec_len = out; }
+        *out_len = out;
         if (out) return 1;           /* a batch of empty (EOF-marker) blocks: look at the next one */
     }
+}
+
+static int rd_fill_bgzf(bio_file *f)
+{   /* refill f->dec with the inflated payload of the next batch of whole blocks; 0 = EOF, 1 = ok, -1 = error */
+    size_t out = 0;
+    return bgzf_batch(f, NULL, 0, &out);
 }
 
 static int rd_fill_inner(bio_file *f);
@@ -216,6 +239,33 @@ static int rd_read(bio_file *f, uint8_t *dst, size_t n)
         memcpy(dst + got, f->dec + f->dec_pos, k);
         f->dec_pos += k; got += k;
     }
+    return 1;
+}
+
+int bio_read_raw(bio_file *f, uint8_t *buf, size_t cap, size_t *len)
+{   /* append decompressed stream bytes at buf + *len (see bamio.h); 1 = appended something, 0 = EOF, -1 = error, 2 = buffer full */
+    if (*len >= cap) return 2;
+    if (f->dec_pos < f->dec_len) {                         /* what the record-wise reader left in the window */
+        size_t k = f->dec_len - f->dec_pos; if (k > cap - *len) k = cap - *len;
+        memcpy(buf + *len, f->dec + f->dec_pos, k);
+        f->dec_pos += k; *len += k;
+        return 1;
+    }
+    if (f->bgzf) {                                         /* parallel BGZF: inflate whole blocks straight into the caller's buffer */
+        const double t0 = now_sec();
+        size_t out = 0;
+        const int rc = bgzf_batch(f, buf + *len, cap - *len, &out);
+        f->ingest_sec += now_sec() - t0;
+        if (rc <= 0) return rc;
+        if (out == 0) return 2;
+        f->ingest_bytes += out; *len += out;
+        return 1;
+    }
+    const int rc = rd_fill(f);                             /* streaming inflate / plain file: through the window */
+    if (rc <= 0) return rc;
+    size_t k = f->dec_len - f->dec_pos; if (k > cap - *len) k = cap - *len;
+    memcpy(buf + *len, f->dec + f->dec_pos, k);
+    f->dec_pos += k; *len += k;
     return 1;
 }
 
@@ -431,22 +481,28 @@ bio_hdr *bio_read_header(bio_file *f)
         f->is_bam = 1;
         if (rd_read(f, b, 8) != 1) return NULL;
         uint32_t l_text = le32(b + 4);
+        if (l_text > 0x7fffffffu) { set_err(f, "corrupt BAM header (l_text)"); return NULL; }
         char *text = malloc((size_t)l_text + 1);
-        if (!text || (l_text && rd_read(f, (uint8_t *)text, l_text) != 1)) { free(text); set_err(f, "truncated BAM header"); return NULL; }
+        if (!text || (l_text && rd_read(f, (uint8_t *)text, l_text) != 1)) { free(text); set_err(f, text ? "truncated BAM header" : "out of memory"); return NULL; }
         text[l_text] = 0;
         size_t tl = strlen(text);
-        if (rd_read(f, b, 4) != 1) { free(text); return NULL; }
+        if (rd_read(f, b, 4) != 1) { free(text); set_err(f, "truncated BAM header"); return NULL; }
         int32_t n_ref = (int32_t)le32(b);
+        if (n_ref < 0) { free(text); set_err(f, "corrupt BAM header (n_ref)"); return NULL; }
         bio_hdr *h = calloc(1, sizeof *h);
-        h->text = text; h->l_text = tl; h->n_targets = n_ref;
-        h->target_name = malloc(sizeof(char *) * (size_t)(n_ref ? n_ref : 1));
-        h->target_len = malloc(sizeof(uint32_t) * (size_t)(n_ref ? n_ref : 1));
+        if (!h) { free(text); set_err(f, "out of memory"); return NULL; }
+        h->text = text; h->l_text = tl; h->n_targets = 0;
+        h->target_name = calloc((size_t)(n_ref ? n_ref : 1), sizeof(char *));
+        h->target_len = calloc((size_t)(n_ref ? n_ref : 1), sizeof(uint32_t));
+        if (!h->target_name || !h->target_len) { bio_hdr_free(h); set_err(f, "out of memory"); return NULL; }
         for (int32_t i = 0; i < n_ref; i++) {
-            if (rd_read(f, b, 4) != 1) { set_err(f, "truncated BAM header"); return NULL; }
+            if (rd_read(f, b, 4) != 1) { bio_hdr_free(h); set_err(f, "truncated BAM header"); return NULL; }
             uint32_t ln = le32(b);
+            if (ln == 0 || ln > (1u << 20)) { bio_hdr_free(h); set_err(f, "corrupt BAM header (l_name)"); return NULL; }
             char *nm = malloc((size_t)ln + 1);
-            if (rd_read(f, (uint8_t *)nm, ln) != 1 || rd_read(f, b, 4) != 1) { set_err(f, "truncated BAM header"); return NULL; }
+            if (!nm || rd_read(f, (uint8_t *)nm, ln) != 1 || rd_read(f, b, 4) != 1) { free(nm); bio_hdr_free(h); set_err(f, nm ? "truncated BAM header" : "out of memory"); return NULL; }
             nm[ln] = 0; h->target_name[i] = nm; h->target_len[i] = le32(b);
+            h->n_targets = i + 1;
         }
         return h;
     }

@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
                                                             double *U, double *a, double *inc, double *partial, uint32_t F,
                                                             double *delta_out, int32_t *result, uint32_t *hc_out,
                                                             double *totbuf, uint32_t *bflag,
-                                                            PeerTable peers, int n_ranks, int rank, uint32_t epoch)
+                                                            PeerTable peers, int n_ranks, int rank, uint32_t epoch, unsigned long long timeout_ns)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -731,6 +731,9 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
     const bool part = !cta0 || blockIdx.x == 0;
     const uint32_t ptid = cta0 ? threadIdx.x : gtid, pn = cta0 ? blockDim.x : gsz, nparts = cta0 ? 1u : gridDim.x;
     int timeout = 0;
+    unsigned long long t_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    auto expired = [&]() -> bool { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t - t_start > timeout_ns; };
     // push my vector (getv) to every rank, then wait for everyone's vector and hand the rank-ordered total of every
     // element to put().  Called by the participants only; needs no barrier of its own.
     auto exchange = [&](uint32_t tag, uint32_t parity, auto getv, auto put) {
@@ -744,12 +747,12 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
             double tot = 0;
             for (int r = 0; r < n_ranks; r++) {
                 const unsigned long long *src = ll_slot(peers, rank, parity, r, n_ranks, V) + 2 * (size_t)i;
-                unsigned long long w0, w1, spins = 0;
+                unsigned long long w0, w1; uint32_t spins = 0;
                 for (;;) {
                     ll_load(src, w0, w1);
                     if ((w0 >> 32) == want && (w1 >> 32) == want) break;
-                    // a peer that never shows up costs ONE time limit (~40 s), not one per exchange: the flag is sticky
-                    if (timeout || ++spins > (1ull << 26)) { timeout = 1; break; }
+                    // a peer that never shows up costs ONE time limit (wall clock, MSG_PEER_TIMEOUT_S), not one per exchange: the flag is sticky
+                    if (timeout || ((++spins & 1023u) == 0 && expired())) { timeout = 1; break; }
                 }
                 tot += __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
             }
@@ -759,8 +762,7 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
     };
     // ---- exchange 0: U = a = (sum over ranks of the doubled counts) / 2 (:286); insert counters and list totals for the host.
     //      Small integers are exact in f64, so the totals equal the integer sums.
-    if (gtid < 20) delta_out[gtid] = 0.0;
-    if (gtid < 4) result[gtid] = 0;
+    if (gtid < 20) delta_out[gtid] = 0.0;                   // result[0..3] is cleared by the host before the launch
     if (part)
         exchange(0u, 0u,
                  [&](uint32_t i) -> double { return i < F ? (double)ui[i] : i < F + 4 ? (double)counters[i - F] : i == F + 4 ? (double)nl_lo : i == F + 5 ? (double)nl_hi : 0.0; },
@@ -892,16 +894,250 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
             uint32_t tot = 0;
             for (int r = 0; r < n_ranks; r++) {
                 const unsigned long long *src = reinterpret_cast<const unsigned long long *>(peers.base[rank]) + r;
-                unsigned long long w, spins = 0;
+                unsigned long long w; uint32_t spins = 0;
                 for (;;) {
                     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
                     if ((w >> 32) == want) break;
-                    if (*reinterpret_cast<volatile int32_t *>(result + 2) || ++spins > (1ull << 26)) { result[2] = 1; break; }
+                    if (*reinterpret_cast<volatile int32_t *>(result + 2) || ((++spins & 1023u) == 0 && expired())) { result[2] = 1; break; }
                 }
                 tot += (uint32_t)w;
             }
             result[3] = (int32_t)tot;
             result[0] = k < 20 ? k : 19; result[1] = conv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-GPU PropSharing for gene catalogues (F + 8 > EM_XCHG_CTA0): the same single cooperative launch per GPU, but the
+// per-iteration collective is a REDUCE-SCATTER + ALL-GATHER over peer memory instead of "every rank pushes its whole
+// vector to every rank": rank r owns the slice [r*S, (r+1)*S) of the feature axis.
+//   RS  every rank stores its partial increments of slice s into rank s's region (plain 16-byte stores over NVLink),
+//       block by block (RSAG_BLK values), then fence.sys + one flag word per block.
+//   upd the owner adds the N partials of a block IN RANK ORDER, applies a = U + inc, the 1e-20 flush and the block's
+//       share of sum (a_new - a_old)^2 (msam_profile.c:369-380), and
+//   AG  stores the new abundances of the block into every rank's copy of a[] (double buffered by exchange parity, so the
+//       gather of the next iteration reads a[] where it landed -- no extra copy), followed by fence.sys and a flagged
+//       16-byte word pair {tag|lo32, tag|hi32} carrying the block's delta share.  Every rank sums all N*nblk shares in
+//       the same fixed order => DELTA^2, the stop decision (:383) and a[] are bit-identical on all ranks.
+// Per rank and iteration 2*(N-1)/N * F * 8 bytes leave over NVLink (28 MB at F = 1e6, N = 8, against 128 MB + 128 MB of
+// polling reads for the all-to-all push), the region is (2 + 2) * N*S * 8 bytes (32 MB), and there are two grid barriers
+// per iteration.  Exchange 0 runs the doubled counts through the same path (U = a = total / 2, :286); the six host
+// counters and the final purged count travel as flagged words through the 1 KB scalar area, as in the small-F kernel.
+// Slot reuse is safe by parity exactly as above: a rank can only be one exchange ahead of any peer.
+constexpr uint32_t RSAG_BLK = 512;                 // values per block: 256 threads x one 16-byte store
+
+struct RsagLayout {                                 // byte offsets inside a rank's region (after the 128-byte purged area)
+    uint32_t S, nblk; int n_ranks;
+    __host__ __device__ size_t scal() const { return 128; }                                              // [16 senders][8] u64 flagged scalars
+    __host__ __device__ size_t rs_flag() const { return scal() + 16 * 8 * 8; }                            // [2][N][nblk] u32
+    __host__ __device__ size_t dd() const { return rs_flag() + (((size_t)2 * n_ranks * nblk * 4 + 15) & ~(size_t)15); }   // [2][N][nblk][2] u64
+    __host__ __device__ size_t rs_data() const { return dd() + (size_t)2 * n_ranks * nblk * 16; }        // [2][N][S] f64
+    __host__ __device__ size_t ag_data() const { return rs_data() + (size_t)2 * n_ranks * S * 8; }       // [2][N*S] f64
+    __host__ __device__ size_t total() const { return ag_data() + (size_t)2 * n_ranks * S * 8; }
+};
+__host__ __device__ inline RsagLayout rsag_layout(uint32_t F, int n_ranks)
+{
+    RsagLayout L; L.n_ranks = n_ranks;
+    const uint32_t per = (F + (uint32_t)n_ranks - 1) / (uint32_t)n_ranks;
+    L.nblk = (per + RSAG_BLK - 1) / RSAG_BLK; if (L.nblk == 0) L.nblk = 1;
+    L.S = L.nblk * RSAG_BLK;
+    return L;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_relaxed_sys_u32(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_weak_v2f64(double *p, double a, double b) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" :: "l"(p), "d"(a), "d"(b) : "memory"); }
+__device__ __forceinline__ void ld_cg_v2f64(const double *p, double &a, double &b) { asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p) : "memory"); }
+
+__global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_off, const uint32_t *mm_len, const int32_t *mm_fid, uint32_t nlists,
+                                                           const uint32_t *ui, const uint32_t *counters, uint32_t nl_lo, uint32_t nl_hi,
+                                                           double *U, double *a_out, double *inc, uint32_t F,
+                                                           double *delta_out, int32_t *result, uint32_t *hc_out,
+                                                           PeerTable peers, int n_ranks, int rank, uint32_t epoch, unsigned long long timeout_ns)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double s_red[256];
+    __shared__ int s_to;
+    const RsagLayout L = rsag_layout(F, n_ranks);
+    const uint32_t S = L.S, nblk = L.nblk, N = (uint32_t)n_ranks;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    unsigned char *me = peers.base[rank];
+    const unsigned long long t_start = globaltimer_ns();
+    volatile int32_t *timed_out = result + 2;
+    auto expired = [&]() -> bool {
+        if (*timed_out) return true;
+        if (globaltimer_ns() - t_start > timeout_ns) { *timed_out = 1; return true; }
+        return false;
+    };
+    // a[] after exchange k lives in ag_data[k & 1] of MY region (every owner stored its slice there)
+    auto a_buf = [&](uint32_t par) -> double * { return reinterpret_cast<double *>(me + L.ag_data()) + (size_t)par * N * S; };
+
+    // One exchange.  first: the values are the doubled counts (U = a = total / 2, no delta); else the increments.
+    bool dead = false;                               // a peer never showed up: same value in every thread (read after a grid barrier)
+    auto exchange = [&](uint32_t k, bool first) -> double {
+        const uint32_t par = k & 1u, tag = epoch + k;
+        // ---- reduce-scatter, sender side: block (s, b) of my vector -> rank s
+        for (uint32_t blk = blockIdx.x; blk < N * nblk; blk += gridDim.x) {
+            const uint32_t s = blk / nblk, b = blk - s * nblk;
+            const uint32_t i0 = s * S + b * RSAG_BLK + 2 * threadIdx.x;
+            double v0, v1;
+            if (first) { v0 = i0 < F ? (double)ui[i0] : 0.0; v1 = i0 + 1 < F ? (double)ui[i0 + 1] : 0.0; }
+            else {
+                v0 = i0 < F ? __ldcg(inc + i0) : 0.0; v1 = i0 + 1 < F ? __ldcg(inc + i0 + 1) : 0.0;
+                if (i0 < F) inc[i0] = 0.0;
+                if (i0 + 1 < F) inc[i0 + 1] = 0.0;
+            }
+            double *dst = reinterpret_cast<double *>(peers.base[s] + L.rs_data()) + ((size_t)par * N + (size_t)rank) * S + b * RSAG_BLK + 2 * threadIdx.x;
+            st_weak_v2f64(dst, v0, v1);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                st_relaxed_sys_u32(reinterpret_cast<uint32_t *>(peers.base[s] + L.rs_flag()) + ((size_t)par * N + (size_t)rank) * nblk + b, tag);
+            }
+        }
+        // ---- owner side: blocks of my slice.  Wait for the N partials, reduce in rank order, update, all-gather.
+        const double *a_old = a_buf(par ^ 1u);
+        for (uint32_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+            if (threadIdx.x == 0) s_to = 0;
+            __syncthreads();
+            if (threadIdx.x < N) {
+                const uint32_t *fl = reinterpret_cast<const uint32_t *>(me + L.rs_flag()) + ((size_t)par * N + threadIdx.x) * nblk + b;
+                while (ld_acquire_sys_u32(fl) != tag) if (expired()) { s_to = 1; break; }
+            }
+            __syncthreads();
+            const uint32_t li = b * RSAG_BLK + 2 * threadIdx.x, i0 = (uint32_t)rank * S + li;
+            double t0 = 0, t1 = 0;
+            if (!s_to)
+                for (uint32_t r = 0; r < N; r++) {
+                    double x0, x1;
+                    ld_cg_v2f64(reinterpret_cast<const double *>(me + L.rs_data()) + ((size_t)par * N + r) * S + li, x0, x1);
+                    t0 += x0; t1 += x1;
+                }
+            double n0, n1, dd = 0;
+            if (first) {
+                n0 = t0 / 2; n1 = t1 / 2;                                           // :286
+                if (i0 < F) U[i0] = n0;
+                if (i0 + 1 < F) U[i0 + 1] = n1;
+            } else {
+                n0 = i0 < F ? U[i0] + t0 : 0.0; n1 = i0 + 1 < F ? U[i0 + 1] + t1 : 0.0;   // :371
+                if (n0 < 1e-20) n0 = 0;                                                 // :372-376
+                if (n1 < 1e-20) n1 = 0;
+                double o0, o1;
+                ld_cg_v2f64(a_old + i0, o0, o1);
+                const double d0 = i0 < F ? n0 - o0 : 0.0, d1 = i0 + 1 < F ? n1 - o1 : 0.0;
+                dd = d0 * d0 + d1 * d1;                                                 // :377-379
+            }
+            for (uint32_t r = 0; r < N; r++)
+                st_weak_v2f64(reinterpret_cast<double *>(peers.base[r] + L.ag_data()) + (size_t)par * N * S + i0, n0, n1);
+            s_red[threadIdx.x] = dd;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+            if (threadIdx.x < N) {
+                __threadfence_system();                     // cumulative over the block's stores (they happen-before through the barriers above)
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_red[0]), t = (unsigned long long)tag << 32;
+                unsigned long long *q = reinterpret_cast<unsigned long long *>(peers.base[threadIdx.x] + L.dd()) + (((size_t)par * N + (size_t)rank) * nblk + b) * 2;
+                ll_store(q, t | (bits & 0xffffffffull), t | (bits >> 32));
+            }
+            __syncthreads();
+        }
+        // ---- all-gather, receiver side: every block of every owner must have landed in my copy of a[]
+        {
+            const unsigned long long want = (unsigned long long)tag;
+            for (uint32_t q = gtid; q < N * nblk; q += gsz) {
+                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(me + L.dd()) + ((size_t)par * N * nblk + q) * 2;
+                unsigned long long w0, w1;
+                for (;;) {
+                    ll_load(src, w0, w1);
+                    if ((w0 >> 32) == want && (w1 >> 32) == want) break;
+                    if (expired()) break;
+                }
+            }
+            __threadfence_system();
+        }
+        grid.sync();
+        dead = *timed_out != 0;                      // nobody polls between this barrier and the next exchange: uniform
+        // ---- DELTA^2: all N*nblk block shares, same order on every rank and in every CTA            (:380)
+        double acc = 0;
+        if (!first)
+            for (uint32_t q = threadIdx.x; q < N * nblk; q += 256) {
+                unsigned long long w0, w1;
+                ll_load(reinterpret_cast<const unsigned long long *>(me + L.dd()) + ((size_t)par * N * nblk + q) * 2, w0, w1);
+                acc += __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+            }
+        s_red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+        const double delta = s_red[0] / F;
+        __syncthreads();
+        return delta;
+    };
+    // flagged scalars: sender `rank` writes word j of its row in every peer's scalar area
+    auto scal_send = [&](uint32_t j, uint32_t tag, uint32_t value) {
+        const unsigned long long msg = ((unsigned long long)tag << 32) | value;
+        for (uint32_t r = 0; r < N; r++)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(reinterpret_cast<unsigned long long *>(peers.base[r] + L.scal()) + (size_t)rank * 8 + j), "l"(msg) : "memory");
+    };
+    auto scal_sum = [&](uint32_t j, uint32_t tag) -> uint32_t {
+        uint32_t tot = 0;
+        for (uint32_t r = 0; r < N; r++) {
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(me + L.scal()) + (size_t)r * 8 + j;
+            unsigned long long w;
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                if ((w >> 32) == tag || expired()) break;
+            }
+            tot += (uint32_t)w;
+        }
+        return tot;
+    };
+
+    if (gtid < 20) delta_out[gtid] = 0.0;                   // result[0..3] is cleared by the host before the launch
+    // host counters (inserts, unique, multiple, big groups) and the two halves of the list total: six flagged scalars
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 6) {
+        const uint32_t j = threadIdx.x;
+        scal_send(j, epoch, j < 4 ? counters[j] : (j == 4 ? nl_lo : nl_hi));
+        hc_out[j] = scal_sum(j, epoch);
+    }
+    exchange(0u, true);
+    int k = 1, conv = 0;
+    for (; k < 20; k++) {
+        // gather: s = sum a[f] in list order; inc[f] += a[f]/s            (:341-365)
+        const double *av = a_buf((uint32_t)(k - 1) & 1u);
+        {
+            uint32_t l = gtid;
+            for (; l + gsz < nlists; l += 2 * gsz) em_share_list_pair(mm_fid, mm_off[l], mm_len[l], mm_off[l + gsz], mm_len[l + gsz], av, inc);
+            if (l < nlists) em_share_list(mm_fid, mm_off[l], mm_len[l], av, inc);
+        }
+        grid.sync();
+        const double delta = exchange((uint32_t)k, false);
+        if (gtid == 0) delta_out[k - 1] = delta;
+        if (dead) break;
+        if (delta < 1e-10) { conv = 1; break; }                             // :383
+    }
+    // ---- final abundances to a_out, purged = #lists whose abundances sum to exactly 0 (:394-404), summed over ranks
+    {
+        const uint32_t kl = k < 20 ? (uint32_t)k : 19u;
+        const double *av = a_buf(kl & 1u);
+        for (uint32_t i = gtid; i < F; i += gsz) a_out[i] = av[i];
+        uint32_t z = 0;
+        for (uint32_t l = gtid; l < nlists; l += gsz) {
+            const uint32_t b = mm_off[l], e = b + mm_len[l];
+            double sum = 0;
+            for (uint32_t q = b; q < e; q++) sum += av[mm_fid[q]];
+            z += (sum == 0);
+        }
+        z = __reduce_add_sync(0xffffffffu, z);
+        if ((threadIdx.x & 31u) == 0 && z) atomicAdd(reinterpret_cast<uint32_t *>(result + 3), z);
+        grid.sync();
+        // the purged message also tells the peers that this rank is done reading its copy of a[]: only then may a peer's
+        // next call overwrite it
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            scal_send(6, epoch + 24u, __ldcg(reinterpret_cast<const uint32_t *>(result + 3)));
+            result[3] = (int32_t)scal_sum(6, epoch + 24u);
+            result[0] = (int32_t)kl; result[1] = conv;
         }
     }
 }

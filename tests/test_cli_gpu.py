@@ -219,3 +219,74 @@ def test_cli_data_errors(tmp_path):
     sam = sam.replace("AS:i:5", "NM:i:0")
     r = run(["filter", "-S", "--besthit", "-"], stdin=sam.encode(), check=False)
     assert r.returncode == 1 and b"Fatal Error: Required field AS not found in SAM/BAM input" in r.stderr
+
+
+def _synth_bam(tmp_path, n_records, preset="mixed", seed=99, level=1):
+    from msamtools_b200 import synth
+    p = synth.make_params(preset, n_records=n_records, seed=seed)
+    raw, off, _ = synth.generate(p)
+    tlen = synth.target_lengths(p)
+    names = [f"seq{i:03d}" for i in range(len(tlen))]
+    path = str(tmp_path / "synth.bam")
+    samutil.write_bam(path, samutil.synth_header(names, tlen), names, tlen, raw, level=level)
+    return path, raw, off, tlen, names
+
+
+@pytest.mark.parametrize("pinned", ["0", "1"])
+def test_cli_chunked_reader_thread(tmp_path, oracle, pinned):
+    """many small chunks through the reader thread / buffer ring (bulk BGZF ingest, QNAME-boundary cuts, tails carried
+    into the next buffer): filter output bytes, profile table and coverage summary equal the oracle's on the whole stream"""
+    path, raw, off, tlen, names = _synth_bam(tmp_path, 120_000)
+    env = dict(os.environ, MSAMTOOLS_CHUNK_RECORDS="7000", MSAMTOOLS_PINNED=pinned, MSAMTOOLS_THREADS="4", MSAMTOOLS_TIMING="1")
+    cfg = oracle.filter_cfg(l=80, p=95, z=80, besthit=True)
+    idx = oracle.filter_stream(raw, off, cfg)
+    f = subprocess.run([CLI, "filter", "-b", "-u", "-l", "80", "-p", "95", "-z", "80", "--besthit", path], capture_output=True, env=env)
+    assert f.returncode == 0, f.stderr.decode()[-2000:]
+    assert b"# timing:" in f.stderr
+    tmp = str(tmp_path / "f.bam")
+    with open(tmp, "wb") as fh:
+        fh.write(f.stdout)
+    got = samutil.read_bam(tmp)
+    assert bytes(got.raw) == bytes(oracle.emit_records(raw, off, idx, cfg))
+    # same stream piped on stdin into `profile` (record-wise pre-flight, then bulk ingest from the pipe)
+    outp = str(tmp_path / "p.gz")
+    p = subprocess.run([CLI, "profile", "--label", "x", "--unit", "ab", "--nolen", "--multi", "prop", "-o", outp, "-"], input=f.stdout,
+                       capture_output=True, env=env)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    ab, st, _, _ = oracle.profile(raw, off, idx, len(tlen), 3)
+    comments, body = samutil.read_profile_gz(outp)
+    assert [v for _, v in body[2:]] == ["%.8g" % x for x in ab]
+    assert f"PropSharing Iteration: {st['iterations']:2d}" in p.stderr.decode()
+    # coverage summary over the unfiltered file
+    outc = str(tmp_path / "c.gz")
+    c = subprocess.run([CLI, "coverage", "--summary", "-o", outc, path], capture_output=True, env=env)
+    assert c.returncode == 0 and c.stdout == b"", c.stderr.decode()[-2000:]
+    cov, touched, total, _ = oracle.coverage(raw, off, None, tlen)
+    with gzip.open(outc, "rt") as fh:
+        lines = fh.read().splitlines()
+    exp = [f"{n}\t0\t0" if not cv else "%s\t%.8f\t%.2f" % (n, t / l, s / l) for n, cv, t, s, l in zip(names, cov, touched, total, tlen)]
+    assert lines == exp
+
+
+def test_cli_corrupt_input_is_fatal(tmp_path):
+    """a flipped payload byte (CRC mismatch) or a truncated file must not end the stream silently with exit status 0"""
+    path, raw, off, tlen, names = _synth_bam(tmp_path, 30_000, level=6)
+    data = bytearray(open(path, "rb").read())
+    env = dict(os.environ, MSAMTOOLS_CHUNK_RECORDS="5000")
+    outp = str(tmp_path / "p.gz")
+    for threads in ("1", "4"):
+        bad = bytearray(data)
+        bad[len(bad) // 2] ^= 0x5a
+        p1 = str(tmp_path / f"bad{threads}.bam")
+        open(p1, "wb").write(bad)
+        r = subprocess.run([CLI, "profile", "--label", "x", "-o", outp, p1], capture_output=True, env=dict(env, MSAMTOOLS_THREADS=threads))
+        assert r.returncode == 1 and (b"Fatal Error: Cannot read input" in r.stderr or b"Fatal Error: Cannot read header" in r.stderr), (threads, r.stderr[-500:])
+        assert not os.path.exists(outp)
+        p2 = str(tmp_path / f"trunc{threads}.bam")
+        open(p2, "wb").write(data[:len(data) * 2 // 3])
+        r = subprocess.run([CLI, "filter", "-b", "-l", "50", p2], capture_output=True, env=dict(env, MSAMTOOLS_THREADS=threads))
+        assert r.returncode == 1 and (b"Fatal Error: Cannot read input" in r.stderr or b"Fatal Error: Cannot read header" in r.stderr), (threads, r.stderr[-500:])
+    # malformed SAM text
+    sam = "@HD\tVN:1.6\tSO:queryname\n@SQ\tSN:A\tLN:1000\nr1\t0\tNOPE\t10\t60\t10M\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tNM:i:0\tAS:i:5\n"
+    r = run(["filter", "-S", "-l", "5", "-"], stdin=sam.encode(), check=False)
+    assert r.returncode == 1 and b"Fatal Error: Cannot read input" in r.stderr
