@@ -24,7 +24,9 @@ CASES = {
     # name: (preset, env, share mode, coverage?)
     "p2p_prop_cov": ("mixed", {}, "proportional", True),          # general pipeline (coverage keeps the kept stream)
     "p2p_prop_fused": ("mixed", {}, "proportional", False),       # fused filter->profile pass, exchange by CTA 0
-    "p2p_prop_bigF": ("catalog10k", {}, "proportional", False),   # F + 8 > 8192: grid-wide exchange, no shared-memory a[]
+    "p2p_prop_bigF": ("catalog10k", {}, "proportional", False),   # F + 8 > 8192: reduce-scatter / all-gather exchange (em_loop_rsag_kernel)
+    "p2p_prop_genes1m": ("genes1m", {}, "proportional", False),   # 1 M-gene catalogue, same kernel, 123 blocks per slice
+    "p2p_prop_mid": ("community", {"_n_refs": "3000"}, "proportional", False),   # 2048 < F <= 8184: flagged words by CTA 0, global-memory a[]
     "nccl_prop": ("mixed", {"MSG_NO_P2P": "1"}, "proportional", False),   # NCCL allreduce + per-iteration NCCL loop
     "equal": ("mixed", {}, "equal", False),                        # packed u32 allreduce + f64 allreduce
 }
@@ -33,7 +35,10 @@ CASES = {
 def _case_data(case):
     from msamtools_b200 import synth
     preset = CASES[case][0]
-    p = synth.make_params(preset, n_records=200_000, seed=2024)
+    over = {}
+    if "_n_refs" in CASES[case][1]:
+        over = dict(n_refs=int(CASES[case][1]["_n_refs"]), ref_len_min=2_000, ref_len_max=9_000, shared_fraction=0.3)
+    p = synth.make_params(preset, n_records=200_000, seed=2024, **over)
     raw, off, _ = synth.generate(p)
     return raw, off, synth.target_lengths(p)
 
@@ -41,7 +46,7 @@ def _case_data(case):
 def _worker(rank, world, uid, out_dir, case):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
     _, env, mode, cov_on = CASES[case]
-    os.environ.update(env)
+    os.environ.update({k: v for k, v in env.items() if not k.startswith("_")})
     import msamtools_b200 as m
     from msamtools_b200 import shard
     raw, off, tlen = _case_data(case)
@@ -82,3 +87,37 @@ def test_two_gpu_profile_and_coverage(tmp_path, oracle, case):
         for k in range(2):
             assert np.array_equal(r[k]["cov"], ecov[0]) and np.array_equal(r[k]["touched"], ecov[1]) and np.array_equal(r[k]["total"], ecov[2])
     assert np.array_equal(r[0]["ab"], r[1]["ab"])           # identical on every rank
+
+
+def _skew_worker(rank, world, uid, out_dir):
+    """rank 1 holds NO records (zero lists, zero counts) and arrives 4 s late at msg_finish_profile: the ranks are lined up
+    before the cooperative kernel starts, so nobody times out and rank 1 still gets the full result"""
+    import time
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    os.environ["MSG_PEER_TIMEOUT_S"] = "2"          # far below the skew: only the pre-launch line-up can make this pass
+    import msamtools_b200 as m
+    raw, off, tlen = _case_data("p2p_prop_bigF")
+    with m.Context(l=80, p=95, z=80, besthit=True, profile=True, multi="proportional", kept=False, n_targets=len(tlen),
+                   device=rank, n_ranks=world, rank=rank, nccl_unique_id=uid) as ctx:
+        if rank == 0:
+            ctx.push(raw, off)
+        else:
+            time.sleep(4.0)
+        ab, st = ctx.finish_profile()
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), ab=ab,
+             st=np.array([st["mapped_inserts"], st["uniq"], st["multi"], st["purged"], st["iterations"], st["n_lists"]]))
+
+
+@pytest.mark.skipif(_ndev() < 2, reason="needs two GPUs")
+def test_two_gpu_late_and_empty_rank(tmp_path, oracle):
+    import msamtools_b200 as m
+    uid = m.nccl_unique_id()
+    mp.spawn(_skew_worker, args=(2, uid, str(tmp_path)), nprocs=2, join=True)
+    raw, off, tlen = _case_data("p2p_prop_bigF")
+    idx = oracle.filter_stream(raw, off, oracle.filter_cfg(l=80, p=95, z=80, besthit=True))
+    eab, est, _, _ = oracle.profile(raw, off, idx, len(tlen), 3)
+    r = [np.load(tmp_path / f"s{k}.npz") for k in range(2)]
+    for k in range(2):
+        assert r[k]["st"].tolist() == [est["mapped_inserts"], est["uniq"], est["multi"], est["purged"], est["iterations"], est["n_lists"]]
+        assert np.all(np.abs(r[k]["ab"] - eab) <= 1e-9 * np.maximum(np.abs(eab), np.abs(r[k]["ab"])))
+    assert np.array_equal(r[0]["ab"], r[1]["ab"])
