@@ -6,14 +6,19 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-f
 CSRC    := msamtools_b200/csrc
 LIB     := msamtools_b200/libmsamtools_b200.so
 SYNTH   := msamtools_b200/libmsamsynth.so
+HOSTLIB := msamtools_b200/libmsamhost.so
 
 CLI     := msamtools_b200/bin/msamtools
 HOSTSRC := $(CSRC)/host/bamio.c $(CSRC)/host/finflate.c $(CSRC)/host/margs.c $(CSRC)/host/keyorder.c
 
-all: $(LIB) $(SYNTH) $(CLI) oracle
+all: $(LIB) $(SYNTH) $(HOSTLIB) $(CLI) oracle
 
-$(LIB): $(CSRC)/api.cu $(wildcard $(CSRC)/*.cuh) include/msamtools_b200.h
+$(LIB): $(CSRC)/api.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/host/recindex.c include/msamtools_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/api.cu -ldl
+
+# CPU-only helpers of the ABI (record index, QNAME-boundary split): what the reference arm of bench.py loads
+$(HOSTLIB): $(CSRC)/host/recindex.c
+	$(CC) -O2 -g -std=gnu99 -Wall -Wextra -fPIC -shared -o $@ $<
 
 $(SYNTH): $(CSRC)/synth.c
 	$(CC) -O2 -g -std=gnu99 -Wall -Wextra -fPIC -shared -o $@ $< -lm
@@ -27,6 +32,6 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(LIB) $(SYNTH) $(CLI); $(MAKE) -C oracle clean
+	rm -f $(LIB) $(SYNTH) $(HOSTLIB) $(CLI); $(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

@@ -48,6 +48,12 @@ CONFIGS = {
             ctx=dict(besthit=True, profile=True, multi="proportional", kept=False, **FILTER),
             ref_filter=["filter", "-b", "-u", "-l", "80", "-p", "95", "-z", "80", "--besthit"],
             ref_second=["profile", "--label", "S", "--multi=proportional"]),
+    12: dict(preset="community", records=10_000_000, chunk=10_000_000,       # the round-1 bench line: F = 100, flagged-word exchange
+             workload="configs[1] data shape (synthetic community PE150, 100 genomes) through filter -l 80 -p 95 -z 80 --besthit | "
+                      "profile --multi=proportional",
+             ctx=dict(besthit=True, profile=True, multi="proportional", kept=False, **FILTER),
+             ref_filter=["filter", "-b", "-u", "-l", "80", "-p", "95", "-z", "80", "--besthit"],
+             ref_second=["profile", "--label", "S", "--multi=proportional"]),
     1: dict(preset="community", records=20_000_000, chunk=20_000_000,
             workload="configs[1]: synthetic community PE150, 100 genomes: filter -l 80 -p 95 -z 80 with record output",
             ctx=dict(records=True, kept=False, **FILTER),
@@ -58,7 +64,7 @@ CONFIGS = {
             ref_filter=["profile", "--label", "S", "--multi=proportional"], ref_second=None),
     4: dict(preset="community", records=20_000_000, chunk=20_000_000,
             workload="configs[3]: filter -l 80 -p 95 -z 80 fused with coverage --summary, 100 genomes, 1 GPU",
-            ctx=dict(coverage=True, kept=False, **FILTER),
+            ctx=dict(coverage=True, coverage_summary=True, kept=False, **FILTER),
             ref_filter=["filter", "-b", "-u", "-l", "80", "-p", "95", "-z", "80"], ref_second=["coverage", "--summary"]),
 }
 
@@ -426,7 +432,7 @@ def run_ours(args):
         sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     key = args.config
     cfg = CONFIGS[key]
-    if key != 5 and world > 1:
+    if key not in (5, 12) and world > 1:
         sys.exit("bench.py: --config 1|3|4 are single-GPU lines")
     dist = None
     if world > 1:
@@ -468,7 +474,7 @@ def run_ours(args):
 
     # ---- parity first (also warms every code path up)
     parity_ok, parity = (True, {"skipped": "profile configs only"})
-    if has_profile and key == 5 and not args.no_parity:
+    if has_profile and key in (5, 12) and not args.no_parity:
         parity_ok, parity = parity_check(m, cfg, plan, tlen, rank, world, local, dist, bcast)
         if not parity_ok:
             if rank == 0:

@@ -99,7 +99,8 @@ typedef struct msg_config {
     uint8_t  want_stats;         /* keep per-record (alen,qlen,qclip,edit,AS) for msg_pull_stats */
     uint8_t  share_type;         /* MSG_MULTI_*                                        */
     uint8_t  debug_force_slow;   /* testing: route every record through the global-memory parser */
-    uint8_t  reserved1;
+    uint8_t  coverage_summary;   /* want_coverage: only the per-target summary of msam_coverage.c:189-219 is needed (`coverage
+                                    --summary`): one bit per position instead of a depth cell; msg_pull_coverage unavailable */
 
     int32_t  n_targets;          /* header->n_targets                                  */
     int32_t  n_features;         /* global->n_features (== n_targets when fmap NULL)   */

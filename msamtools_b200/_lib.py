@@ -24,7 +24,7 @@ class MsgConfig(C.Structure):
         ("rescore", C.c_uint8), ("reserved0", C.c_uint8 * 3),
         ("min_length", C.c_int32), ("ppt", C.c_int32), ("max_clip", C.c_int32),
         ("want_kept", C.c_uint8), ("want_records", C.c_uint8), ("want_profile", C.c_uint8), ("want_coverage", C.c_uint8),
-        ("want_stats", C.c_uint8), ("share_type", C.c_uint8), ("debug_force_slow", C.c_uint8), ("reserved1", C.c_uint8),
+        ("want_stats", C.c_uint8), ("share_type", C.c_uint8), ("debug_force_slow", C.c_uint8), ("coverage_summary", C.c_uint8),
         ("n_targets", C.c_int32), ("n_features", C.c_int32),
         ("fmap", C.POINTER(C.c_int32)), ("target_len", C.POINTER(C.c_uint32)),
         ("device", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32),

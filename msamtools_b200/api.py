@@ -36,7 +36,7 @@ class Context:
 
     def __init__(self, *, l=0, p=None, ppt=None, z=None, invert=False, keep_unmapped=False, rescore=False,
                  besthit=False, uniqhit=False, do_filter=None,
-                 profile=False, multi="proportional", coverage=False, records=False, stats=False, kept=True,
+                 profile=False, multi="proportional", coverage=False, coverage_summary=False, records=False, stats=False, kept=True,
                  n_targets=0, n_features=None, fmap=None, target_len=None,
                  device=0, n_ranks=1, rank=0, nccl_unique_id=None, force_slow=False):
         self.lib = L.load()
@@ -55,6 +55,7 @@ class Context:
         cfg.want_coverage, cfg.want_stats = int(coverage), int(stats)
         cfg.share_type = parse_multi(multi) if isinstance(multi, str) else int(multi)
         cfg.debug_force_slow = int(force_slow)
+        cfg.coverage_summary = int(coverage_summary)
         cfg.n_targets = int(n_targets)
         self._fmap = None if fmap is None else np.ascontiguousarray(fmap, dtype=np.int32)
         self._tlen = None if target_len is None else np.ascontiguousarray(target_len, dtype=np.uint32)
@@ -235,9 +236,30 @@ class PinnedBuffer:
         self.close()
 
 
+_host = None
+
+
+def _hostlib():
+    """libmsamhost.so: the CPU-only part of the ABI (csrc/host/recindex.c); never maps the CUDA library."""
+    global _host
+    if _host is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmsamhost.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} not found: run `make`")
+        lib = C.CDLL(path)
+        sz = C.c_size_t
+        lib.msg_index_records.argtypes = [C.c_void_p, sz, C.c_void_p, sz, C.POINTER(sz), C.POINTER(sz), C.c_int]
+        lib.msg_index_records.restype = C.c_int
+        lib.msg_split_point.argtypes = [C.c_void_p, C.c_void_p, sz, sz]
+        lib.msg_split_point.restype = sz
+        _host = lib
+    return _host
+
+
 def index_records(raw):
     """Host offset index over an uncompressed BAM record stream (msg_index_records)."""
-    lib = L.load()
+    lib = _hostlib()
     raw = np.ascontiguousarray(raw, dtype=np.uint8)
     n, used = C.c_size_t(), C.c_size_t()
     rc = lib.msg_index_records(_ptr(raw), raw.nbytes, None, 0, C.byref(n), C.byref(used), 0)
@@ -251,7 +273,7 @@ def index_records(raw):
 
 
 def split_point(raw, rec_off, want):
-    lib = L.load()
+    lib = _hostlib()
     raw = np.ascontiguousarray(raw, dtype=np.uint8)
     rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
     return lib.msg_split_point(_ptr(raw), _ptr(rec_off), len(rec_off) - 1, want)

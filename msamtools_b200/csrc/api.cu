@@ -21,6 +21,8 @@
 #include <string>
 #include <vector>
 
+#include "host/recindex.c"      // msg_index_records, msg_split_point
+
 using namespace msg;
 
 // ------------------------------------------------------------------------------------------------
@@ -141,6 +143,7 @@ struct msg_ctx {
 
     // coverage accumulators
     int32_t *d_diff = nullptr, *d_depth = nullptr; uint8_t *d_covered = nullptr;
+    bool cov_bits = false; unsigned long long *d_covbits = nullptr; uint64_t cov_words = 0;      // summary mode (coverage.cuh)
     unsigned long long *d_touched = nullptr; long long *d_sum = nullptr;
     bool cov_finished = false;
 
@@ -229,6 +232,7 @@ int report_device_errors(msg_ctx *c, const uint32_t *h)
         cudaMemsetAsync(c->d_err + 1, 0xff, 4, c->stream);
     }
     if (h[0] & DERR_FORMAT) return fail(c, MSG_EFORMAT, "malformed BAM record or reference id out of range (first near record %u)", h[1]);
+    if (h[0] & DERR_CGTAG)  return fail(c, MSG_EFORMAT, "CIGAR with more than 65535 operations (CG tag, near record %u) is not supported", h[1]);
     if (h[0] & DERR_NOTAG)  return fail(c, MSG_ENOTAG, "Either NM or MD must be present in SAM/BAM input for 'filter' command. Type 'msamtools filter -h' for details.");
     if (h[0] & DERR_NOAS)   return fail(c, MSG_ENOAS, "Required field AS not found in SAM/BAM input. Type 'msamtools -h' for details.");
     return MSG_OK;
@@ -472,6 +476,7 @@ int launch_decode(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t re
     if (need_stats || c->cov_fused) mode |= DM_NEED_CIGAR;
     if (need_stats || (need_score && !(g.do_filter && g.rescore))) mode |= DM_NEED_AUX;
     p.mode = mode;
+    p.covbits = c->d_covbits; p.covsum = reinterpret_cast<unsigned long long *>(c->d_sum);
     p.diff = c->d_diff; p.covbase = c->d_covbase; p.tlen = c->d_tlen; p.covered = c->d_covered; p.n_targets = g.n_targets;
     p.err = c->d_err; p.acct = c->d_acct;
 
@@ -548,7 +553,8 @@ int run_chunk_general(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_
     if (g.want_profile) { rc = profile_stage(c, stream, m); if (rc) return rc; c->cursor_dirty = true; }
     if (g.want_coverage && !c->cov_fused && m) {
         coverage_stream_kernel<<<nblocks(m, 256), 256, 0, c->stream>>>(d_raw, d_off, stream, m, g.n_targets, c->d_diff, c->d_covbase,
-                                                                      c->d_tlen, c->d_covered, c->d_err); LAUNCHED(c);
+                                                                      c->d_tlen, c->d_covered, c->d_err,
+                                                                      c->cov_bits ? c->d_covbits : nullptr, reinterpret_cast<unsigned long long *>(c->d_sum)); LAUNCHED(c);
         c->cov_finished = false;
     }
     if (g.want_coverage) c->cov_finished = false;
@@ -766,6 +772,8 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     if (g.do_filter && g.hit_mode) mode |= DM_NEED_AS;
     if (g.want_profile) mode |= DM_WANT_HASH;
     if (ctx->cov_fused) mode |= DM_COV_FUSED;
+    ctx->cov_bits = g.want_coverage && g.coverage_summary && g.n_ranks <= 1;      // (the cross-rank combine of the bitmap would need a bitwise-OR allreduce)
+    if (ctx->cov_bits) mode |= DM_COV_BITS;
     if (g.debug_force_slow) mode |= DM_FORCE_SLOW;
     ctx->decode_mode = mode;
 
@@ -792,13 +800,19 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     }
     if (g.want_coverage) {
         std::vector<uint64_t> base(T + 1, 0);
-        for (int32_t t = 0; t < g.n_targets; t++) base[t + 1] = base[t] + (uint64_t)cfg->target_len[t] + 1;
-        ctx->cov_cells = base[g.n_targets];
+        if (ctx->cov_bits) for (int32_t t = 0; t < g.n_targets; t++) base[t + 1] = base[t] + ((uint64_t)cfg->target_len[t] + 63) / 64;     // 64-bit words
+        else               for (int32_t t = 0; t < g.n_targets; t++) base[t + 1] = base[t] + (uint64_t)cfg->target_len[t] + 1;            // cells + spill cell
         CUC(cudaMalloc(&ctx->d_tlen, T * 4)); CUC(cudaMalloc(&ctx->d_covbase, (T + 1) * 8));
         CUC(cudaMemcpy(ctx->d_tlen, cfg->target_len, (size_t)g.n_targets * 4, cudaMemcpyHostToDevice));
         CUC(cudaMemcpy(ctx->d_covbase, base.data(), (T + 1) * 8, cudaMemcpyHostToDevice));
-        const size_t cells = (size_t)(ctx->cov_cells ? ctx->cov_cells : 1);
-        CUC(cudaMalloc(&ctx->d_diff, cells * 4)); CUC(cudaMalloc(&ctx->d_depth, cells * 4));
+        if (ctx->cov_bits) {
+            ctx->cov_words = base[g.n_targets];
+            CUC(cudaMalloc(&ctx->d_covbits, (size_t)(ctx->cov_words ? ctx->cov_words : 1) * 8));
+        } else {
+            ctx->cov_cells = base[g.n_targets];
+            const size_t cells = (size_t)(ctx->cov_cells ? ctx->cov_cells : 1);
+            CUC(cudaMalloc(&ctx->d_diff, cells * 4)); CUC(cudaMalloc(&ctx->d_depth, cells * 4));
+        }
         CUC(cudaMalloc(&ctx->d_covered, T)); CUC(cudaMalloc(&ctx->d_touched, T * 8)); CUC(cudaMalloc(&ctx->d_sum, T * 8));
     }
     if (g.n_ranks > 1) {
@@ -868,7 +882,7 @@ void msg_destroy(msg_ctx *c)
                       &c->csr_off, &c->csr_len, &c->csr_fid, &c->win, &c->t_ui, &c->t_d, &c->t_cnt, &c->t_cov};
     for (DevBuf *b : bufs) b->release();
     void *ptrs[] = {c->d_fmap, c->d_tlen, c->d_covbase, c->d_err, c->d_acct, c->d_total, c->d_ui, c->d_d, c->d_counters, c->d_stamp, c->d_U, c->d_a,
-                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_bflag, c->d_wl, c->d_ui_tmp, c->d_d_tmp, c->d_fcnt, c->d_cursor, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum};
+                    c->d_inc, c->d_partial, c->d_delta, c->d_purged, c->d_bflag, c->d_wl, c->d_ui_tmp, c->d_d_tmp, c->d_fcnt, c->d_cursor, c->d_diff, c->d_depth, c->d_covered, c->d_touched, c->d_sum, c->d_covbits};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_ab) cudaFreeHost(c->h_ab);
@@ -897,7 +911,10 @@ int msg_reset(msg_ctx *c)
         c->csr_lists = c->csr_ent = 0;
     }
     if (g.want_coverage) {
-        CU(cudaMemsetAsync(c->d_diff, 0, (size_t)(c->cov_cells ? c->cov_cells : 1) * 4, c->stream));
+        if (c->cov_bits) {
+            CU(cudaMemsetAsync(c->d_covbits, 0, (size_t)(c->cov_words ? c->cov_words : 1) * 8, c->stream));
+            CU(cudaMemsetAsync(c->d_sum, 0, T * 8, c->stream));
+        } else CU(cudaMemsetAsync(c->d_diff, 0, (size_t)(c->cov_cells ? c->cov_cells : 1) * 4, c->stream));
         CU(cudaMemsetAsync(c->d_covered, 0, T, c->stream));
         c->cov_finished = false;
     }
@@ -906,37 +923,7 @@ int msg_reset(msg_ctx *c)
     return MSG_OK;
 }
 
-// ------------------------------------------------------------------ host index helpers
-int msg_index_records(const uint8_t *raw, size_t nbytes, uint64_t *rec_off, size_t cap, size_t *nrec, size_t *consumed, int allow_partial)
-{
-    size_t o = 0, n = 0;
-    while (o + 4 <= nbytes) {
-        uint32_t bs = (uint32_t)raw[o] | (uint32_t)raw[o + 1] << 8 | (uint32_t)raw[o + 2] << 16 | (uint32_t)raw[o + 3] << 24;
-        if (bs < 32 || bs > 0x7fffffffu) return MSG_EFORMAT;
-        if (o + 4 + (size_t)bs > nbytes) break;
-        if (rec_off) { if (n + 1 >= cap) return MSG_ERANGE; rec_off[n] = o; }
-        n++; o += 4 + (size_t)bs;
-    }
-    if (rec_off) { if (n >= cap) return MSG_ERANGE; rec_off[n] = o; }
-    if (nrec) *nrec = n;
-    if (consumed) *consumed = o;
-    if (o != nbytes && !allow_partial) return MSG_EFORMAT;
-    return MSG_OK;
-}
-
-size_t msg_split_point(const uint8_t *raw, const uint64_t *rec_off, size_t nrec, size_t want)
-{
-    if (want > nrec) want = nrec;
-    if (want == nrec) return nrec;
-    for (size_t k = want; k > 0; k--) {
-        const uint8_t *a = raw + rec_off[k - 1], *b = raw + rec_off[k];
-        uint32_t flag = (uint32_t)a[18] | (uint32_t)a[19] << 8;
-        int32_t tid = (int32_t)((uint32_t)a[4] | (uint32_t)a[5] << 8 | (uint32_t)a[6] << 16 | (uint32_t)a[7] << 24);
-        if ((flag & 4u) || tid < 0) continue;
-        if (a[12] != b[12] || memcmp(a + 36, b + 36, a[12]) != 0) return k;
-    }
-    return 0;
-}
+// ------------------------------------------------------------------ host index helpers: csrc/host/recindex.c (plain C, also built into libmsamhost.so)
 
 // ------------------------------------------------------------------ data path
 int msg_device_alloc(msg_ctx *c, size_t nbytes, void **d_ptr)
@@ -1296,6 +1283,20 @@ int msg_finish_coverage(msg_ctx *c, uint8_t *covered, int64_t *touched, int64_t 
     const size_t T = (size_t)g.n_targets;
     int rc;
     if (T == 0) return MSG_OK;
+    if (c->cov_bits) {
+        // summary mode: touched = popcount of every target's bitmap, sum = the run lengths added up during the pushes
+        CU(cudaMemsetAsync(c->d_touched, 0, T * 8, c->stream));
+        if (c->cov_words) {
+            coverage_popcount_kernel<<<nblocks(nblocks(c->cov_words, 4), 256), 256, 0, c->stream>>>(c->d_covbits, c->cov_words, c->d_covbase, g.n_targets, c->d_touched);
+            LAUNCHED(c);
+        }
+        if (covered) CU(cudaMemcpyAsync(covered, c->d_covered, T, cudaMemcpyDeviceToHost, c->stream));
+        if (touched) CU(cudaMemcpyAsync(touched, c->d_touched, T * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (sum)     CU(cudaMemcpyAsync(sum, c->d_sum, T * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += T * 17;
+        return check_device_errors(c);
+    }
     CU(cudaMemcpyAsync(c->d_depth, c->d_diff, (size_t)c->cov_cells * 4, cudaMemcpyDeviceToDevice, c->stream));
     DevBuf &t_cov = c->t_cov;
     uint8_t *cov = c->d_covered;
@@ -1323,6 +1324,7 @@ int msg_finish_coverage(msg_ctx *c, uint8_t *covered, int64_t *touched, int64_t 
 int msg_pull_coverage(msg_ctx *c, int32_t tid, int32_t *depth)
 {
     if (!c || !depth) return MSG_EINVAL;
+    if (c->cov_bits) return fail(c, MSG_ESTATE, "context was created with coverage_summary: per-position depth is not kept");
     if (!c->cfg.want_coverage || !c->cov_finished) return fail(c, MSG_ESTATE, "call msg_finish_coverage first");
     if (tid < 0 || tid >= c->cfg.n_targets) return fail(c, MSG_EINVAL, "tid out of range");
     CU(cudaSetDevice(c->cfg.device));

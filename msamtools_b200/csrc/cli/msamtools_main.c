@@ -784,7 +784,7 @@ static int coverage_main(int argc, char *argv[])
     run_t r; memset(&r, 0, sizeof r);
     open_input(&r, a_file->filename[0]);
     const int T = r.hdr->n_targets;
-    r.cfg.do_filter = 0; r.cfg.want_coverage = 1; r.cfg.n_targets = T; r.cfg.n_features = T; r.cfg.target_len = r.hdr->target_len;
+    r.cfg.do_filter = 0; r.cfg.want_coverage = 1; r.cfg.coverage_summary = a_summary->count > 0; r.cfg.n_targets = T; r.cfg.n_features = T; r.cfg.target_len = r.hdr->target_len;
     msg_ctx *ctx = run_stream(&r);
     uint8_t *covered = calloc((size_t)(T ? T : 1), 1);
     int64_t *touched = calloc((size_t)(T ? T : 1), sizeof(int64_t)), *sum = calloc((size_t)(T ? T : 1), sizeof(int64_t));

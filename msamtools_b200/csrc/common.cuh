@@ -16,6 +16,7 @@
 #define DERR_NOTAG   1u           // mapped record without NM and MD while stats are needed
 #define DERR_NOAS    2u           // best-hit candidate without AS
 #define DERR_FORMAT  4u           // malformed record / tid out of range
+#define DERR_CGTAG   8u           // CIGAR of more than 65535 operations stored in the CG tag (SAM spec 4.2.2): not expanded here
 
 #define BAM_FUNMAP 4u
 #define BAM_FREAD1 0x40u
@@ -35,6 +36,7 @@
 #define DM_NEED_CIGAR  (1u << 10)
 #define DM_NEED_AUX    (1u << 11)
 #define DM_REQ_STATS   (1u << 12)  // reference's need_alignment_stats: a mapped record without NM/MD is fatal
+#define DM_COV_BITS    (1u << 13)  // coverage in summary mode: one bit per position + per-target sums
 
 __device__ __forceinline__ uint4 ldg_stream128(const uint4 *p)
 {

@@ -17,7 +17,8 @@ namespace msg {
 // stream-driven coverage (used when the kept list is only known after best-hit selection)
 __global__ void __launch_bounds__(256) coverage_stream_kernel(const uint8_t *raw, const uint64_t *off, const uint32_t *stream, uint64_t m,
                                                               int32_t n_targets, int32_t *diff, const uint64_t *covbase,
-                                                              const uint32_t *tlen, uint8_t *covered, uint32_t *err)
+                                                              const uint32_t *tlen, uint8_t *covered, uint32_t *err,
+                                                              unsigned long long *covbits, unsigned long long *covsum)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
@@ -28,7 +29,8 @@ __global__ void __launch_bounds__(256) coverage_stream_kernel(const uint8_t *raw
     if (c.bad) { atomicOr(err, DERR_FORMAT); return; }
     if (c.tid < 0) return;                                              // msam_coverage.c:42
     if (c.tid >= n_targets) { atomicOr(err, DERR_FORMAT); return; }
-    cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, diff, covbase, tlen, covered);
+    if (covbits) cover_record_bits(g, 36 + c.lq, c.nc, c.tid, c.pos, covbits, covbase, tlen, covered, covsum);
+    else cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, diff, covbase, tlen, covered);
 }
 
 // after the prefix sum: per-target (#cells != 0, sum of cells) over [covbase[t], covbase[t]+tlen[t])
@@ -46,10 +48,10 @@ __device__ __forceinline__ void cov_flush(unsigned long long *touched, long long
         tc = warp_sum_u64(tc);
         sm = (long long)warp_sum_u64((unsigned long long)sm);
         if ((threadIdx.x & 31u) == 0 && (tc | (unsigned long long)sm)) {
-            atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm);
+            atomicAdd(touched + t, tc); if (sum) atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm);
         }
     } else if (t >= 0 && (tc | (unsigned long long)sm)) {
-        atomicAdd(touched + t, tc); atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm);
+        atomicAdd(touched + t, tc); if (sum) atomicAdd((unsigned long long *)(sum + t), (unsigned long long)sm);
     }
 }
 
@@ -78,6 +80,31 @@ __global__ void __launch_bounds__(256) coverage_reduce_kernel(const int32_t *dep
         }
     }
     cov_flush(touched, sum, t, tc, sm);
+}
+
+// summary mode: touched[t] = popcount of target t's bitmap.  Each thread owns 4 consecutive 64-bit words; targets start
+// on word boundaries (wbase), bits past tlen are never set.
+__global__ void __launch_bounds__(256) coverage_popcount_kernel(const unsigned long long *bits, uint64_t total_words, const uint64_t *wbase,
+                                                                int32_t n_targets, unsigned long long *touched)
+{
+    const uint64_t start = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    int32_t t = -1;
+    unsigned long long tc = 0;
+    if (start < total_words) {
+        const uint64_t stop = min(total_words, start + 4);
+        int32_t lo = 0, hi = n_targets - 1;
+        while (lo < hi) { int32_t mid = (lo + hi + 1) >> 1; if (wbase[mid] <= start) lo = mid; else hi = mid - 1; }
+        t = lo;
+        uint64_t tend = wbase[t + 1];
+        for (uint64_t x = start; x < stop; x++) {
+            while (x >= tend) {                        // crossed into the next target (possibly over empty ones)
+                if (tc) atomicAdd(touched + t, tc);
+                tc = 0; t++; tend = wbase[t + 1];
+            }
+            tc += (unsigned long long)__popcll(bits[x]);
+        }
+    }
+    cov_flush(touched, nullptr, t, tc, 0);
 }
 
 struct InI32 { const int32_t *v; __device__ __forceinline__ int32_t operator()(uint64_t i) const { return v[i]; } };

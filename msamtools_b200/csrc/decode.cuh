@@ -44,8 +44,10 @@ struct DecodeParams {
     int32_t  min_length, ppt, max_clip;
     uint32_t mode;
     // fused coverage
-    int32_t  *diff;
-    const uint64_t *covbase;
+    int32_t  *diff;                 // per-position difference array (depth mode) ...
+    unsigned long long *covbits;    // ... or one bit per position + per-target depth sums (summary mode, DM_COV_BITS)
+    unsigned long long *covsum;
+    const uint64_t *covbase;        // first cell (depth mode) / first 64-bit word (summary mode) of every target
     const uint32_t *tlen;
     uint8_t  *covered;
     int32_t  n_targets;
@@ -330,7 +332,7 @@ template <class A>
 __device__ __forceinline__ void cover_record(const A &hd, uint32_t x0, uint32_t nc, int32_t tid, int32_t pos,
                                              int32_t *diff, const uint64_t *covbase, const uint32_t *tlen, uint8_t *covered)
 {
-    covered[tid] = 1;                                          // :45-49, any record with tid >= 0
+    if (!covered[tid]) covered[tid] = 1;                       // :45-49, any record with tid >= 0 (test first, see cover_record_bits)
     const long long tl = tlen[tid];
     int32_t *d = diff + covbase[tid];
     long long q = pos;
@@ -343,6 +345,58 @@ __device__ __forceinline__ void cover_record(const A &hd, uint32_t x0, uint32_t 
             q += w;
         } else if (op == 2 || op == 3) q += w;
     }
+}
+
+// Summary-only coverage (msam_coverage.c:189-219 needs, per target, "#positions with depth != 0" and "sum of depths"):
+// one BIT per reference position instead of a 4-byte difference cell -- a position is touched iff some M/=/X run covers
+// it, and the sum of depths is the sum of the (clamped) run lengths.  The bitmap of a 400 Mbp reference set is 50 MB and
+// stays in L2, where the diff array (1.6 GB) sends two random read-modify-writes per run to HBM.  Interior words of a
+// run are plain stores of all-ones (any interleaving with another run's atomicOr leaves all-ones), the two edge words
+// are atomicOr.
+__device__ __forceinline__ void cover_bits(unsigned long long *w, long long lo, long long hi)
+{
+    const long long wlo = lo >> 6, whi = (hi - 1) >> 6;
+    const unsigned long long mlo = ~0ull << (lo & 63), mhi = ~0ull >> (63 - ((hi - 1) & 63));
+    if (wlo == whi) { atomicOr(w + wlo, mlo & mhi); return; }
+    atomicOr(w + wlo, mlo);
+    for (long long k = wlo + 1; k < whi; k++) w[k] = ~0ull;
+    atomicOr(w + whi, mhi);
+}
+template <class A>
+__device__ __forceinline__ void cover_record_bits(const A &hd, uint32_t x0, uint32_t nc, int32_t tid, int32_t pos,
+                                                  unsigned long long *bits, const uint64_t *wbase, const uint32_t *tlen, uint8_t *covered,
+                                                  unsigned long long *sum, uint32_t *deferred = nullptr)
+{
+    if (!covered[tid]) covered[tid] = 1;                       // :45-49, any record with tid >= 0 (test first: tens of millions of
+                                                               // stores into the same few cache lines serialise in L2)
+    const long long tl = tlen[tid];
+    unsigned long long *w = bits + wbase[tid];
+    long long q = pos, total = 0;
+    for (uint32_t k = 0; k < nc; k++) {
+        uint32_t c = hd.u32(x0 + 4 * k);
+        uint32_t op = c & 0xfu; long long wd = (long long)(c >> 4);
+        if (op == 0 || op == 7 || op == 8) {
+            long long lo = q < 0 ? 0 : q, hi = q + wd > tl ? tl : q + wd;
+            if (hi > lo) { cover_bits(w, lo, hi); total += hi - lo; }
+            q += wd;
+        } else if (op == 2 || op == 3) q += wd;
+    }
+    // sum of depths += covered bases of this record; with `deferred` the caller adds it (warp-aggregated per target)
+    if (deferred && total < (1ll << 26)) *deferred = (uint32_t)total;
+    else if (total) atomicAdd(sum + tid, (unsigned long long)total);
+}
+
+// one atomic per (warp, target) instead of one per record: lanes with the same target find each other with MATCH.ANY
+// and add up with REDUX over the match group.  Called by all 32 lanes at a converged point; tid < 0 or bases == 0:
+// nothing to add.  (bases < 2^26 per lane, so the group sum stays inside 32 bits.)
+__device__ __forceinline__ void cover_sum_flush(unsigned long long *sum, int32_t tid, uint32_t bases)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool have = tid >= 0 && bases != 0;
+    if (!__any_sync(0xffffffffu, have)) return;
+    const uint32_t grp = __match_any_sync(0xffffffffu, have ? tid : -1 - (int32_t)lane);
+    const uint32_t tot = __reduce_add_sync(grp, have ? bases : 0u);
+    if (have && lane == (uint32_t)__ffs((int)grp) - 1u) atomicAdd(sum + tid, (unsigned long long)tot);
 }
 
 // everything after the core: qname hash/compare inputs, cigar, aux, filter, outputs
@@ -396,7 +450,7 @@ __device__ __forceinline__ RecResult finish_record(const DecodeParams &p, const 
 // s_off[0..nrec] are the tile's offsets, off_prev the offset of the record before the tile.
 template <int SLOT_WORDS>
 __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t, uint64_t i, bool active, const uint32_t *s_slot,
-                                               const uint64_t *s_off, uint64_t off_prev, uint32_t &alg, uint32_t &nslow)
+                                               const uint64_t *s_off, uint64_t off_prev, uint32_t &alg, uint32_t &nslow, int32_t &cov_tid, uint32_t &cov_bases)
 {
     const uint32_t mode = p.mode;
     const bool force_slow = mode & DM_FORCE_SLOW;
@@ -427,6 +481,13 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
     }
     RecResult r;
     uint32_t h = 0; bool eq = false;
+    if (!c.bad && (mode & DM_NEED_CIGAR) && c.nc == 2 && c.lseq > 0) {
+        // htslib stores CIGARs of > 65535 operations in the CG:B,I tag behind the placeholder "<l_seq>S<ref_len>N" (SAM spec
+        // 4.2.2) and sam_read1 swaps the real CIGAR in; this parser does not, so it refuses the record instead of mis-counting it
+        const GlAcc g0{p.raw + o};
+        const uint32_t c0 = g0.u32(36 + c.lq), c1 = g0.u32(36 + c.lq + 4);
+        if (c0 == (((uint32_t)c.lseq << 4) | 4u) && (c1 & 0xfu) == 3u) { atomicOr(p.err, DERR_CGTAG); atomicMin(p.err + 1, (uint32_t)min(i, (uint64_t)0xffffffffu)); }
+    }
     if (c.bad) {
         r = RecResult{0, 0, 0, 0, 0, c.flag & FB_FLAG_MASK, false};
         atomicOr(p.err, DERR_FORMAT); atomicMin(p.err + 1, (uint32_t)min(i, (uint64_t)0xffffffffu));
@@ -438,8 +499,9 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
         GlAcc gp{p.raw + op};
         h = name_hash_eq(g, c.lq, gp, i > 0 && op + 36 <= o && gp.u8(12) == c.lq, &eq);
         if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
-            if (c.tid < p.n_targets) cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
-            else atomicOr(p.err, DERR_FORMAT);
+            if (c.tid >= p.n_targets) atomicOr(p.err, DERR_FORMAT);
+            else if (mode & DM_COV_BITS) { cov_tid = c.tid; cover_record_bits(g, 36 + c.lq, c.nc, c.tid, c.pos, p.covbits, p.covbase, p.tlen, p.covered, p.covsum, &cov_bases); }
+            else cover_record(g, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
         }
         r.fbits |= FB_SLOW; nslow = 1;
     } else {
@@ -463,8 +525,9 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
             h = name_hash_eq(hd, c.lq, gp, i > 0 && op + 36 <= o && gp.u8(12) == c.lq, &eq);
         }
         if ((mode & DM_COV_FUSED) && (r.fbits & FB_INPOOL) && c.tid >= 0) {
-            if (c.tid < p.n_targets) cover_record(hd, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
-            else atomicOr(p.err, DERR_FORMAT);
+            if (c.tid >= p.n_targets) atomicOr(p.err, DERR_FORMAT);
+            else if (mode & DM_COV_BITS) { cov_tid = c.tid; cover_record_bits(hd, 36 + c.lq, c.nc, c.tid, c.pos, p.covbits, p.covbase, p.tlen, p.covered, p.covsum, &cov_bases); }
+            else cover_record(hd, 36 + c.lq, c.nc, c.tid, c.pos, p.diff, p.covbase, p.tlen, p.covered);
         }
     }
     if (r.notag) { atomicOr(p.err, DERR_NOTAG); atomicMin(p.err + 1, (uint32_t)min(i, (uint64_t)0xffffffffu)); }
@@ -479,15 +542,242 @@ __device__ __forceinline__ void parse_and_emit(const DecodeParams &p, uint32_t t
     alg += a > (1u << 20) ? (1u << 20) : a;                          // keeps the per-warp sum inside 32 bits
 }
 
-// One CTA per tile of 128 records; ~11 CTAs are resident per SM, which is what hides the two
-// dependent DRAM latencies (offsets -> windows) and keeps the issue slots of the (low-ILP) parser
-// busy.  A persistent, register-staged software pipeline was measured and lost (profiles/r01_notes.md):
-// at the 4 CTAs/SM its 123 registers allow, the parser alone cannot fill the schedulers.
+// ---------------------------------------------------------------- fast path
+// Sequential reader over a staged window: one LDS + one funnel shift per 32-bit word at an arbitrary byte alignment
+// (the generic SmAcc::u32 recomputes the word index and loads two words for every access).
+struct SeqRd {
+    const uint32_t *p; uint32_t sh, cur;
+    __device__ __forceinline__ void init(const uint32_t *w, uint32_t byte) { p = w + (byte >> 2); sh = (byte & 3u) << 3; cur = *p; }
+    __device__ __forceinline__ uint32_t next() { const uint32_t nx = *++p; const uint32_t v = __funnelshift_r(cur, nx, sh); cur = nx; return v; }
+};
+
+// integer aux types c C s S i I: value size in bytes (0 for every other type) and the value itself (bam_aux2i, then the
+// reference's int32 truncation) from the 32 bits at the value's position
+__device__ __forceinline__ uint32_t aux_int_size(uint32_t ty)
+{
+    const uint32_t lo = ty | 0x20u;
+    return lo == 'c' ? 1u : lo == 's' ? 2u : lo == 'i' ? 4u : 0u;
+}
+__device__ __forceinline__ int32_t aux_int_value(uint32_t ty, uint32_t sz, uint32_t v)
+{
+    const uint32_t sh = 32u - 8u * sz;                                   // sz in {1, 2, 4}
+    return (ty & 0x20u) ? ((int32_t)(v << sh) >> sh) : (int32_t)((v << sh) >> sh);
+}
+
+// The common record, straight-line: windows fit, aux block opens with [NM:<int>] MD:Z:<up to 32 chars> [AS:<int>] (what
+// bwa-style aligners and the reference's own generator write, msam validation generator :1034).  Everything is computed
+// exactly as finish_record does; anything unusual returns false and the record goes through the generic parser instead.
+template <int SLOT_WORDS>
+__device__ __forceinline__ bool parse_fast(const DecodeParams &p, uint32_t t, uint64_t i, const uint32_t *s_slot, const uint64_t *s_off,
+                                           uint64_t off_prev, uint32_t hc, uint32_t tc, uint32_t &alg, int32_t &cov_tid, uint32_t &cov_bases)
+{
+    const uint32_t mode = p.mode;
+    const uint64_t o = s_off[t], o1 = s_off[t + 1];
+    if (!(o1 <= p.nbytes_readable && o <= o1)) return false;           // also covers o1 > nbytes: nbytes_readable <= nbytes + 64 and the generic path re-checks
+    const uint64_t len64 = o1 - o;
+    if (len64 < 36 || len64 > 0x0fffffffull || o1 > p.nbytes) return false;
+    const uint32_t len = (uint32_t)len64, rel = (uint32_t)o & 15u;
+    const uint32_t *slot = s_slot + t * SLOT_WORDS;
+    // ---- core (6 aligned LDS + 5 funnel shifts)
+    const uint32_t *w = slot + (rel >> 2);
+    const uint32_t sh = (rel & 3u) << 3;
+    const uint32_t w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5], w6 = w[6];
+    const int32_t tid = (int32_t)__funnelshift_r(w1, w2, sh);
+    const int32_t pos = (int32_t)__funnelshift_r(w2, w3, sh);
+    const uint32_t lq = __funnelshift_r(w3, w4, sh) & 0xffu;
+    const uint32_t f4 = __funnelshift_r(w4, w5, sh);
+    const uint32_t nc = f4 & 0xffffu, flag = f4 >> 16;
+    const uint32_t lseq = __funnelshift_r(w5, w6, sh);
+    if (lseq > 0x07ffffffu) return false;
+    const uint32_t aux_off = 36u + lq + 4u * nc + ((lseq + 1u) >> 1) + lseq;
+    if (aux_off > len) return false;
+    const uint32_t aux_len = len - aux_off;
+    const bool need_cigar = mode & DM_NEED_CIGAR, need_aux = mode & DM_NEED_AUX;
+    const uint32_t need_head = 36u + lq + (need_cigar ? 4u * nc : 0u);
+    if (rel + need_head > 16u * hc) return false;
+    if (need_cigar && nc == 2 && lseq) {                           // "<l_seq>S<n>N" announces a CG-tag CIGAR: the generic parser reports it
+        SeqRd cr; cr.init(slot, rel + 36u + lq);
+        if (cr.next() == ((lseq << 4) | 4u)) return false;
+    }
+    uint32_t arel = 0;
+    if (need_aux && aux_len) {
+        const uint64_t wend = (o1 + 15ull) & ~15ull;
+        if (wend < 16ull * tc) return false;
+        const uint32_t back = (uint32_t)(wend - o1) + aux_len;       // bytes from the start of the aux block to the end of the tail window
+        if (back > 16u * tc) return false;
+        arel = 16u * tc - back;
+    }
+    // ---- QNAME hash + exact compare with the previous record's name (both from their slots)
+    bool do_eq = false;
+    SeqRd pr; pr.p = slot; pr.sh = 0; pr.cur = 0;
+    if (t > 0) {
+        const uint64_t op = s_off[t - 1];
+        const uint32_t prel = (uint32_t)op & 15u;
+        const uint32_t *pslot = slot - SLOT_WORDS;
+        const uint32_t plq = (pslot[(prel + 12u) >> 2] >> (((prel + 12u) & 3u) << 3)) & 0xffu;
+        if (!(o - op >= 36 && prel + 36u + plq <= 16u * hc)) return false;        // previous name not staged: generic path reads it from global memory
+        do_eq = plq == lq;
+        if (do_eq) pr.init(pslot, prel + 36u);
+    }
+    uint32_t h = 0x811c9dc5u ^ lq, diff = 0;
+    bool eq_glob = false;
+    if (t == 0 && i > 0) {
+        // first record of the tile: its predecessor lives in another CTA's tile, read that name from global memory
+        const GlAcc gp{p.raw + off_prev};
+        h = name_hash_eq(SmAcc{slot, rel}, lq, gp, off_prev + 36 <= o && gp.u8(12) == lq, &eq_glob);
+    } else {
+        SeqRd nr; nr.init(slot, rel + 36u);
+        const uint32_t nfull = lq >> 2, remb = lq & 3u;                  // same words and masks as name_hash_eq
+        for (uint32_t k = 0; k < nfull; k++) {
+            const uint32_t x = nr.next();
+            h = hash_step(h, x);
+            if (do_eq) diff |= x ^ pr.next();
+        }
+        if (remb) {
+            const uint32_t mask = (1u << (remb * 8)) - 1u;
+            const uint32_t x = nr.next() & mask;
+            h = hash_step(h, x);
+            if (do_eq) diff |= (x ^ pr.next()) & mask;
+        }
+        h = hash_fin(h);
+    }
+    const bool eq = (do_eq && diff == 0) || eq_glob;
+    // ---- CIGAR
+    const bool need_stats = mode & DM_NEED_STATS;
+    CigSum cs = {0, 0, 0, 0, 0};
+    if (need_stats && nc) {
+        SeqRd cr; cr.init(slot, rel + 36u + lq);
+        for (uint32_t k = 0; k < nc; k++) {
+            const uint32_t c = cr.next();
+            const uint32_t bit = 1u << (c & 0xfu); const int32_t wd = (int32_t)(c >> 4);
+            cs.wM     += (bit & 0x0181u) ? wd : 0;
+            cs.wI     += (bit & 0x0002u) ? wd : 0;
+            cs.wD     += (bit & 0x0004u) ? wd : 0;
+            cs.wClip  += (bit & 0x0030u) ? wd : 0;
+            cs.wOther += (bit & 0xfe00u) ? wd : 0;
+        }
+    }
+    // ---- aux: [NM int] MD:Z [AS int] at the head of the block
+    const bool want_as = (p.score != nullptr) && !(mode & DM_RESCORE);
+    bool hasMD = false, hasNM = false, hasAS = false; int32_t md_letters = 0, nm = 0, as = 0;
+    if (need_aux) {
+        const uint32_t *axw = slot + hc * 4;
+        uint32_t y = 0;
+        if (need_stats) {
+            if (aux_len < 4) return false;
+            SeqRd ar; ar.init(axw, arel);
+            uint32_t a0 = ar.next();
+            if ((a0 & 0xffffu) == ('N' | ('M' << 8))) {
+                const uint32_t ty = (a0 >> 16) & 0xffu, sz = aux_int_size(ty);
+                uint32_t v = a0 >> 24;
+                if (sz == 0 || 3u + sz + 4u > aux_len) return false;
+                if (sz > 1) { SeqRd vr; vr.init(axw, arel + 3u); v = vr.next(); }
+                nm = aux_int_value(ty, sz, v); hasNM = true;
+                y = 3u + sz;
+                SeqRd a1; a1.init(axw, arel + y); a0 = a1.next();
+            }
+            if ((a0 & 0xffffffu) != ('M' | ('D' << 8) | ('Z' << 16))) return false;
+            // MD string: one bit per character, as md_scan (strings up to 32 chars)
+            const uint32_t ms = y + 3u;
+            SeqRd mr; mr.init(axw, arel + ms);
+            uint32_t L = 0, C = 0, zend = 0; bool done = false;
+#pragma unroll 1
+            for (uint32_t q = 0; q < 32; q += 4) {
+                if (ms + q >= aux_len) return false;
+                const uint32_t x = mr.next();
+                if (x & 0x80808080u) return false;
+                uint32_t nul = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+                const uint32_t xc = x ^ 0x5e5e5e5eu;
+                uint32_t car = ~(((xc & 0x7f7f7f7fu) + 0x7f7f7f7fu) | xc | 0x7f7f7f7fu);
+                const uint32_t dig = (x + 0x50505050u) & ~(x + 0x46464646u) & 0x80808080u;
+                uint32_t let = ~(nul | car | dig) & 0x80808080u;
+                if (nul) {
+                    const uint32_t kk = (uint32_t)(__ffs((int)nul) - 8) >> 3;
+                    const uint32_t keep = (1u << (8 * kk)) - 1u;
+                    let &= keep; car &= keep;
+                    zend = ms + q + kk; done = true;
+                }
+                L |= byteflags_to_bits(let) << q;
+                C |= byteflags_to_bits(car) << q;
+                if (done) break;
+            }
+            if (!done || zend >= aux_len) return false;
+            const uint32_t S = ((C << 1) | 1u) & L;
+            md_letters = __popc(L & (L + S));
+            hasMD = true;
+            y = zend + 1u;
+        }
+        if (want_as) {
+            if (y + 4u > aux_len) return false;
+            SeqRd ar; ar.init(axw, arel + y);
+            const uint32_t a2 = ar.next();
+            if ((a2 & 0xffffu) != ('A' | ('S' << 8))) return false;
+            const uint32_t ty = (a2 >> 16) & 0xffu, sz = aux_int_size(ty);
+            uint32_t v = a2 >> 24;
+            if (sz == 0 || y + 3u + sz > aux_len) return false;
+            if (sz > 1) { SeqRd vr; vr.init(axw, arel + y + 3u); v = vr.next(); }
+            as = aux_int_value(ty, sz, v); hasAS = true;
+        }
+    }
+    // ---- statistics, filter, outputs: same arithmetic as finish_record
+    int32_t alen = 0, qlen = 0, qclip = 0, edit = 0; int path = 0;
+    if (need_stats) {
+        qclip = cs.wClip; qlen = cs.wM + cs.wI + cs.wClip;
+        if (hasMD) { alen = cs.wM + cs.wI + cs.wD; edit = cs.wI + cs.wD + md_letters; path = 2; }
+        else if (hasNM) { alen = cs.wM + cs.wI + cs.wD + cs.wOther; edit = nm; path = 1; }
+        else { alen = qlen = qclip = edit = 0; }
+    }
+    const bool mapped = !(flag & BAM_FUNMAP);
+    bool has_as = hasAS; int32_t score = as; bool inpool, notag = false;
+    if (!(mode & DM_DO_FILTER)) inpool = true;
+    else if (!mapped) inpool = (mode & DM_HAS_FILTER) && (mode & DM_KEEP_UNMAP) && p.ppt >= 0 && (mode & DM_INVERT);
+    else {
+        if ((mode & DM_REQ_STATS) && path == 0) notag = true;
+        if (mode & DM_RESCORE) { score = (alen - edit) - edit; has_as = true; }
+        if (!(mode & DM_HAS_FILTER)) inpool = true;
+        else {
+            bool fail = false;
+            if (p.min_length > 0 && alen < p.min_length) fail = true;
+            if (p.ppt != 0) {
+                if (p.ppt < 0) fail |= (1000 * (edit - alen) < alen * p.ppt);
+                else           fail |= (1000 * (alen - edit) < alen * p.ppt);
+            }
+            if (p.max_clip < 100) fail |= (100 * qclip > p.max_clip * qlen);
+            inpool = (fail == ((mode & DM_INVERT) != 0));
+        }
+    }
+    uint32_t fbits = (flag & FB_FLAG_MASK) | (inpool ? FB_INPOOL : 0u) | (has_as ? FB_HAS_AS : 0u) | (eq ? FB_EQPREV : 0u);
+    if ((mode & DM_COV_FUSED) && inpool && tid >= 0) {
+        if (tid >= p.n_targets) atomicOr(p.err, DERR_FORMAT);
+        else if (mode & DM_COV_BITS) { cov_tid = tid; cover_record_bits(SmAcc{slot, rel}, 36 + lq, nc, tid, pos, p.covbits, p.covbase, p.tlen, p.covered, p.covsum, &cov_bases); }
+        else cover_record(SmAcc{slot, rel}, 36 + lq, nc, tid, pos, p.diff, p.covbase, p.tlen, p.covered);
+    }
+    if (notag) { atomicOr(p.err, DERR_NOTAG); atomicMin(p.err + 1, (uint32_t)min(i, (uint64_t)0xffffffffu)); }
+    if (p.tid)   p.tid[i] = tid;
+    if (p.fb)    p.fb[i] = fbits;
+    if (p.score) p.score[i] = score;
+    if (p.hash)  p.hash[i] = h;
+    if (p.alen)  { p.alen[i] = alen; p.qlen[i] = qlen; p.qclip[i] = qclip; p.edit[i] = edit; }
+    const uint32_t a = 8u + 36u + lq + (need_cigar ? 4u * nc : 0u) + (need_aux ? aux_len : 0u);
+    alg += a > (1u << 20) ? (1u << 20) : a;                          // keeps the per-warp sum inside 32 bits
+    return true;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr, bool g64)
+{
+    if (g64) asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
+    else     asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
+}
+
+// One CTA per tile of 128 records; ~10 CTAs are resident per SM, which is what hides the two dependent DRAM
+// latencies (offsets -> windows) and keeps the issue slots of the (low-ILP) parser busy.  Staging is LDGSTS
+// (cp.async.cg, 16 bytes, no register round trip, `.L2::64B` fill granularity): LPR lanes per record, slots are
+// 16-byte aligned with one pad chunk (stride LPR*16 + 16 bytes).
 template <int LPR, bool G64>
 __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ DecodeParams p)
 {
-    constexpr int SLOT_WORDS = LPR * 4 + 1;            // odd stride: thread-per-slot reads are conflict-free
-    __shared__ uint32_t s_slot[DEC_R * SLOT_WORDS + 2];
+    constexpr int SLOT_WORDS = LPR * 4 + 4;
+    __shared__ __align__(16) uint32_t s_slot[DEC_R * SLOT_WORDS + 4];
     __shared__ uint64_t s_off[DEC_R + 1];
     __shared__ uint32_t s_hb[DEC_R], s_tb[DEC_R];
 
@@ -508,36 +798,35 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
         s_hb[t] = (uint32_t)(o >> 4);                                       // head window: first chunk
         s_tb[t] = (uint32_t)((o1 + 15ull) >> 4) - (hc + tc);                // tail window: chunk index of lane `sub` is s_tb + sub
         if (t == 0 && t0) off_prev = p.off[t0 - 1];
-    }
+    } else { s_hb[t] = 0xffffffffu - 64u; s_tb[t] = 0xffffffffu - 64u; }    // (fails the bound check below)
     __syncthreads();
 
-    // ---- stage both windows of every record: LPR lanes per record, one 16-byte load each
+    // ---- stage both windows of every record: LPR lanes per record, one 16-byte LDGSTS each
     if (!(p.mode & DM_FORCE_SLOW)) {
         const uint32_t nchunks = (uint32_t)(p.nbytes_readable >> 4);
         const uint32_t sub = t % LPR, r0 = t / LPR;
-        const bool head = sub < hc, go = sub < hc + tc;
-        // all LPR loads are issued before the first store so that every thread keeps LPR x 16 B in flight
-        uint4 v[LPR];
+        if (sub < hc + tc) {
+            const uint32_t *wb = (sub < hc ? s_hb : s_tb) + r0;
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_slot + r0 * SLOT_WORDS + sub * 4);
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.raw);
 #pragma unroll
-        for (uint32_t it = 0; it < LPR; it++) {
-            const uint32_t r = it * (DEC_R / LPR) + r0;
-            v[it] = make_uint4(0, 0, 0, 0);
-            if (go && r < nrec) {
-                const uint32_t cidx = (head ? s_hb[r] : s_tb[r]) + sub;     // a tail window that starts before the buffer wraps to a huge index
-                if (cidx < nchunks) v[it] = G64 ? ldg_stream128(reinterpret_cast<const uint4 *>(p.raw) + cidx)
-                                                : ldg_stream128_line(reinterpret_cast<const uint4 *>(p.raw) + cidx);
+            for (uint32_t it = 0; it < LPR; it++) {
+                const uint32_t cidx = wb[it * (DEC_R / LPR)] + sub;         // a tail window that starts before the buffer wraps to a huge index
+                if (cidx < nchunks) cp_async16(dst + it * (DEC_R / LPR) * SLOT_WORDS * 4, src + cidx, G64);
             }
         }
-#pragma unroll
-        for (uint32_t it = 0; it < LPR; it++) {
-            const uint32_t r = it * (DEC_R / LPR) + r0;
-            if (go && r < nrec) { uint32_t *d = s_slot + r * SLOT_WORDS + sub * 4; d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w; }
-        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 
-    uint32_t alg = 0, nslow = 0;
-    parse_and_emit<SLOT_WORDS>(p, t, i, active, s_slot, s_off, off_prev, alg, nslow);
+    uint32_t alg = 0, nslow = 0, cov_bases = 0; int32_t cov_tid = -1;
+    if (active) {
+        bool done = false;
+        if (!(p.mode & DM_FORCE_SLOW)) done = parse_fast<SLOT_WORDS>(p, t, i, s_slot, s_off, off_prev, hc, tc, alg, cov_tid, cov_bases);
+        if (!done) parse_and_emit<SLOT_WORDS>(p, t, i, true, s_slot, s_off, off_prev, alg, nslow, cov_tid, cov_bases);
+    }
+    if (p.mode & DM_COV_BITS) cover_sum_flush(p.covsum, cov_tid, cov_bases);
     alg = __reduce_add_sync(0xffffffffu, alg);         // REDUX: one instruction per warp
     nslow = __reduce_add_sync(0xffffffffu, nslow);
     if ((t & 31u) == 0) {

@@ -9,6 +9,8 @@
 namespace msg {
 
 struct GatherPlan {          // per stream record
+    unsigned long long src;  // byte offset of the record in the chunk (so that the copy kernel needs no stream[] -> off[] chain)
+    uint32_t len;            // bytes of the source record
     uint32_t cut0, cut1;     // byte span [cut0,cut1) of the record to drop (AS field), cut0==cut1 -> none
     uint32_t append;         // 1 -> append AS:i
 };
@@ -23,7 +25,7 @@ __global__ void __launch_bounds__(256) gather_plan_kernel(const uint8_t *raw, co
     const uint64_t o = off[r];
     const uint32_t len = (uint32_t)(off[r + 1] - o);
     uint32_t nl = len;
-    GatherPlan pl = {0, 0, 0};
+    GatherPlan pl = {o, len, 0, 0, 0};
     if (rescore) {
         GlAcc g{raw + o};
         RecCore c = parse_core(g, len);
@@ -63,7 +65,12 @@ __global__ void __launch_bounds__(256) gather_plan_kernel(const uint8_t *raw, co
     plan[j] = pl;
 }
 
-// warp per stream record: byte copy (source and destination are both unaligned)
+// warp per stream record.  Source and destination are both byte-aligned at best, with different misalignments: the copy
+// runs on the DESTINATION's 32-bit grid -- every lane stores one aligned word assembled from two aligned source words
+// with a funnel shift (neighbouring lanes share those loads in L1), so a 300-byte record is three coalesced 128-byte
+// store rounds instead of ten rounds of single bytes; only the <= 3 bytes before the first and after the last whole
+// destination word are copied bytewise.  --rescore records (AS field cut out, AS:i appended, block_size patched) keep
+// the byte loop.
 __global__ void __launch_bounds__(256) gather_copy_kernel(const uint8_t *raw, const uint64_t *off, const uint32_t *stream, uint64_t m,
                                                           const unsigned long long *out_off, const uint32_t *out_len,
                                                           const GatherPlan *plan, const int32_t *score, uint8_t *out)
@@ -71,11 +78,39 @@ __global__ void __launch_bounds__(256) gather_copy_kernel(const uint8_t *raw, co
     const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (j >= m) return;
-    const uint32_t r = stream ? stream[j] : (uint32_t)j;
-    const uint8_t *src = raw + off[r];
-    const uint32_t len = (uint32_t)(off[r + 1] - off[r]);
-    uint8_t *dst = out + out_off[j];
     const GatherPlan pl = plan[j];
+    const uint8_t *src = raw + pl.src;
+    const uint32_t len = pl.len;
+    uint8_t *dst = out + out_off[j];
+    if (!pl.append && pl.cut0 == pl.cut1) {
+        uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+        if (head > len) head = len;
+        const uint32_t nwords = (len - head) >> 2;
+        const uint8_t *sb = src + head;
+        const uint32_t *sa = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sb) & ~(uintptr_t)3);
+        const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(sb) & 3u) << 3;
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+        // four rounds of loads are issued before the first store: ~1 KB in flight per warp (the copy is latency bound otherwise)
+        for (uint32_t k0 = 0; k0 < nwords; k0 += 128) {
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = k0 + u * 32 + lane;
+                lo[u] = k < nwords ? __ldg(sa + k) : 0u;
+                hi[u] = (k < nwords && sh) ? __ldg(sa + k + 1) : 0u;   // the last needed byte of word k+1 lies inside the record
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = k0 + u * 32 + lane;
+                if (k < nwords) dw[k] = __funnelshift_r(lo[u], hi[u], sh);
+            }
+        }
+        if (lane < head) dst[lane] = src[lane];
+        const uint32_t done = head + 4u * nwords, tail = len - done;
+        if (lane < tail) dst[done + lane] = src[done + lane];
+        return;
+    }
+    const uint32_t r = stream ? stream[j] : (uint32_t)j;
     const uint32_t nl = out_len[j];
     const uint32_t gap = pl.cut1 - pl.cut0;
     const uint32_t body = len - gap;                 // bytes copied from the source

@@ -926,6 +926,7 @@ __global__ void __launch_bounds__(256) em_loop_multi_kernel(const uint32_t *mm_o
 // counters and the final purged count travel as flagged words through the 1 KB scalar area, as in the small-F kernel.
 // Slot reuse is safe by parity exactly as above: a rank can only be one exchange ahead of any peer.
 constexpr uint32_t RSAG_BLK = 512;                 // values per block: 256 threads x one 16-byte store
+constexpr uint32_t RSAG_MAXB = 32;                 // owner blocks per CTA announced with one fence
 
 struct RsagLayout {                                 // byte offsets inside a rank's region (after the 128-byte purged area)
     uint32_t S, nblk; int n_ranks;
@@ -959,7 +960,7 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    __shared__ double s_red[256];
+    __shared__ double s_red[256], s_dd[RSAG_MAXB];
     __shared__ int s_to;
     const RsagLayout L = rsag_layout(F, n_ranks);
     const uint32_t S = L.S, nblk = L.nblk, N = (uint32_t)n_ranks;
@@ -979,7 +980,8 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
     bool dead = false;                               // a peer never showed up: same value in every thread (read after a grid barrier)
     auto exchange = [&](uint32_t k, bool first) -> double {
         const uint32_t par = k & 1u, tag = epoch + k;
-        // ---- reduce-scatter, sender side: block (s, b) of my vector -> rank s
+        // ---- reduce-scatter, sender side: block (s, b) of my vector -> rank s.  All of this CTA's blocks first, then ONE
+        //      fence.sys (it waits for the NVLink writes to be acknowledged: microseconds), then their flags.
         for (uint32_t blk = blockIdx.x; blk < N * nblk; blk += gridDim.x) {
             const uint32_t s = blk / nblk, b = blk - s * nblk;
             const uint32_t i0 = s * S + b * RSAG_BLK + 2 * threadIdx.x;
@@ -992,20 +994,40 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
             }
             double *dst = reinterpret_cast<double *>(peers.base[s] + L.rs_data()) + ((size_t)par * N + (size_t)rank) * S + b * RSAG_BLK + 2 * threadIdx.x;
             st_weak_v2f64(dst, v0, v1);
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            for (uint32_t blk = blockIdx.x; blk < N * nblk; blk += gridDim.x) {
+                const uint32_t s = blk / nblk, b = blk - s * nblk;
                 st_relaxed_sys_u32(reinterpret_cast<uint32_t *>(peers.base[s] + L.rs_flag()) + ((size_t)par * N + (size_t)rank) * nblk + b, tag);
             }
         }
-        // ---- owner side: blocks of my slice.  Wait for the N partials, reduce in rank order, update, all-gather.
+        // ---- owner side: blocks of my slice.  Wait for the N partials, reduce in rank order, update, all-gather; the
+        //      blocks' delta shares are announced (flagged word pairs) after one fence.sys for all of them.
         const double *a_old = a_buf(par ^ 1u);
+        uint32_t nmine = 0, b_first = blockIdx.x;
+        auto announce = [&]() {                             // thread 0: one fence for the buffered blocks, then their flagged delta shares
+            __threadfence_system();                         // cumulative over this CTA's stores (they happen-before through the barriers)
+            uint32_t bb = b_first;
+            for (uint32_t j = 0; j < nmine; j++, bb += gridDim.x) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_dd[j]), t = (unsigned long long)tag << 32;
+                for (uint32_t r = 0; r < N; r++)
+                    ll_store(reinterpret_cast<unsigned long long *>(peers.base[r] + L.dd()) + (((size_t)par * N + (size_t)rank) * nblk + bb) * 2,
+                             t | (bits & 0xffffffffull), t | (bits >> 32));
+            }
+        };
         for (uint32_t b = blockIdx.x; b < nblk; b += gridDim.x) {
             if (threadIdx.x == 0) s_to = 0;
             __syncthreads();
             if (threadIdx.x < N) {
                 const uint32_t *fl = reinterpret_cast<const uint32_t *>(me + L.rs_flag()) + ((size_t)par * N + threadIdx.x) * nblk + b;
-                while (ld_acquire_sys_u32(fl) != tag) if (expired()) { s_to = 1; break; }
+                uint32_t v;
+                for (;;) {
+                    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+                    if (v == tag) break;
+                    if (expired()) { s_to = 1; break; }
+                }
             }
             __syncthreads();
             const uint32_t li = b * RSAG_BLK + 2 * threadIdx.x, i0 = (uint32_t)rank * S + li;
@@ -1035,14 +1057,16 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
             s_red[threadIdx.x] = dd;
             __syncthreads();
             for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
-            if (threadIdx.x < N) {
-                __threadfence_system();                     // cumulative over the block's stores (they happen-before through the barriers above)
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_red[0]), t = (unsigned long long)tag << 32;
-                unsigned long long *q = reinterpret_cast<unsigned long long *>(peers.base[threadIdx.x] + L.dd()) + (((size_t)par * N + (size_t)rank) * nblk + b) * 2;
-                ll_store(q, t | (bits & 0xffffffffull), t | (bits >> 32));
+            if (threadIdx.x == 0) s_dd[nmine] = s_red[0];
+            nmine++;
+            if (nmine == RSAG_MAXB) {                       // (huge catalogues only)
+                __syncthreads();
+                if (threadIdx.x == 0) announce();
+                nmine = 0; b_first = b + gridDim.x;
             }
             __syncthreads();
         }
+        if (threadIdx.x == 0 && nmine) announce();
         // ---- all-gather, receiver side: every block of every owner must have landed in my copy of a[]
         {
             const unsigned long long want = (unsigned long long)tag;

@@ -19,7 +19,7 @@ K = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 CASES = [
     ("1_filter_records_100_genomes", "community", dict(l=80, p=95, z=80, records=True, kept=False)),
     ("3_profile_10k_refs", "catalog10k", dict(profile=True, multi="proportional", do_filter=False)),
-    ("4_filter+coverage_100_genomes", "community", dict(l=80, p=95, z=80, coverage=True, kept=False)),
+    ("4_filter+coverage_100_genomes", "community", dict(l=80, p=95, z=80, coverage=True, coverage_summary=True, kept=False)),
     ("5_besthit+profile_1M_genes", "genes1m", dict(l=80, p=95, z=80, besthit=True, profile=True, multi="proportional", kept=False)),
 ]
 for name, preset, opts in CASES:

@@ -70,17 +70,21 @@ def test_golden_profile(m, c, force_slow, kept):
     assert close(st["delta"], exp["delta"], 1e-6) or (np.array(exp["delta"]) < 1e-12).all()
 
 
+@pytest.mark.parametrize("summary", [False, True], ids=["depth", "summary"])
 @pytest.mark.parametrize("c", G.cases("coverage"), ids=G.case_id)
-def test_golden_coverage(m, c):
+def test_golden_coverage(m, c, summary):
     s = G.fixture(c["fixture"])
     pre = c["pre"] or {}
-    with m.Context(coverage=True, n_targets=len(s.ref_names), target_len=s.target_len, **pre) as ctx:
+    with m.Context(coverage=True, coverage_summary=summary, n_targets=len(s.ref_names), target_len=s.target_len, **pre) as ctx:
         ctx.push(s.raw, s.off)
         cov, touched, total = ctx.finish_coverage()
         assert np.nonzero(cov)[0].tolist() == c["nz"]
         assert touched.tolist() == G.dense(c, "touched", np.int64).tolist()
         assert total.tolist() == G.dense(c, "sum", np.int64).tolist()
-        if c["depth"] is not None:
+        if summary:
+            with pytest.raises(m.MsgError):
+                ctx.pull_coverage(0)
+        elif c["depth"] is not None:
             for t, dexp in enumerate(c["depth"]):
                 assert ctx.pull_coverage(t).tolist() == dexp
 
@@ -209,17 +213,21 @@ def test_synth_profile_genome_map(m, oracle, mixed):
     assert (st["uniq"], st["multi"], st["purged"], st["iterations"]) == (est["uniq"], est["multi"], est["purged"], est["iterations"])
 
 
+@pytest.mark.parametrize("summary", [False, True], ids=["depth", "summary"])
 @pytest.mark.parametrize("pre", [None, dict(l=80, p=95, z=80), dict(l=80, p=95, z=80, besthit=True)], ids=["plain", "fused", "besthit"])
-def test_synth_coverage(m, oracle, mixed, pre):
+def test_synth_coverage(m, oracle, mixed, pre, summary):
     raw, off, tlen, p = mixed
     idx = None if pre is None else oracle.filter_stream(raw, off, oracle.filter_cfg(**pre))
     ecov, et, es, edepth = oracle.coverage(raw, off, idx, tlen, want_depth=True)
-    with m.Context(coverage=True, n_targets=len(tlen), target_len=tlen, **(pre or {})) as ctx:
-        ctx.push(raw, off)
-        cov, touched, total = ctx.finish_coverage()
-        assert np.array_equal(cov, ecov) and np.array_equal(touched, et) and np.array_equal(total, es)
-        for t in (0, len(tlen) // 2, len(tlen) - 1):
-            assert np.array_equal(ctx.pull_coverage(t), edepth[t])
+    with m.Context(coverage=True, coverage_summary=summary, n_targets=len(tlen), target_len=tlen, **(pre or {})) as ctx:
+        for rep in range(2):                                     # the second pass checks that msg_reset clears the bitmap / sums
+            ctx.reset()
+            ctx.push(raw, off)
+            cov, touched, total = ctx.finish_coverage()
+            assert np.array_equal(cov, ecov) and np.array_equal(touched, et) and np.array_equal(total, es)
+        if not summary:
+            for t in (0, len(tlen) // 2, len(tlen) - 1):
+                assert np.array_equal(ctx.pull_coverage(t), edepth[t])
 
 
 def test_chunked_push_equals_single(m, oracle, mixed):
@@ -517,3 +525,18 @@ def test_full_size_properties(m, oracle):
         ui1, _ = ctx.pull_counts()
     assert np.array_equal(ui1, eui) and close(ab1, eab)
     assert (st1["iterations"], st1["purged"], st1["multi"]) == (est["iterations"], est["purged"], est["multi"])
+
+
+def test_cg_tag_cigar_is_refused(m):
+    """htslib's placeholder for CIGARs of > 65535 operations ("<l_seq>S<ref_len>N" + CG:B,I tag, SAM spec 4.2.2) is not
+    expanded on the device: the record is refused (MSG_EFORMAT) instead of being silently mis-counted."""
+    text = HDR + "r1\t0\tA\t10\t60\t10S100N\t*\t0\t0\tAAAAAAAAAA\tIIIIIIIIII\tNM:i:0\tAS:i:5\tCG:B:I,160,16\n"
+    s = _sam(text)
+    for kw in (dict(l=5), dict(coverage=True, target_len=s.target_len)):
+        with m.Context(n_targets=3, **kw) as ctx:
+            with pytest.raises(m.MsgError) as e:
+                ctx.push(s.raw, s.off)
+            assert e.value.code == m._lib.MSG_EFORMAT and "CG tag" in e.value.text
+    with m.Context(besthit=True, n_targets=3) as ctx:            # --besthit alone never looks at the CIGAR (msam_filter.c:104,145)
+        ctx.push(s.raw, s.off)
+        assert ctx.pull_kept().tolist() == [0]
