@@ -144,6 +144,7 @@ struct msg_ctx {
     // coverage accumulators
     int32_t *d_diff = nullptr, *d_depth = nullptr; uint8_t *d_covered = nullptr;
     bool cov_bits = false; unsigned long long *d_covbits = nullptr; uint64_t cov_words = 0;      // summary mode (coverage.cuh)
+    bool l2_window = false;
     unsigned long long *d_touched = nullptr; long long *d_sum = nullptr;
     bool cov_finished = false;
 
@@ -451,7 +452,7 @@ int probe_layout(msg_ctx *c, const uint8_t *h_raw, const uint64_t *h_off, const 
 
 // Decode + filter statistics of one chunk: reserves the SoA columns, picks the window layout, launches decode_kernel.
 int launch_decode(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t readable, const uint64_t *d_off, uint64_t n,
-                  const uint8_t *h_raw, const uint64_t *h_off, DecodeParams *out)
+                  const uint8_t *h_raw, const uint64_t *h_off, DecodeParams *out, bool host_mapped = false)
 {
     const msg_config &g = c->cfg;
     const bool hit = g.do_filter && g.hit_mode != MSG_HIT_NONE;
@@ -487,8 +488,15 @@ int launch_decode(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t re
     // L2 fill granularity of the window loads: 64-byte granules (.L2::64B) or whole 128-byte lines.  MSG_L2_GRANULE=64|128 overrides.
     static const int g_env = getenv("MSG_L2_GRANULE") ? atoi(getenv("MSG_L2_GRANULE")) : 0;
     const bool g64 = g_env ? g_env == 64 : true;
-    if (c->lay_lpr == 8) { if (g64) decode_kernel<8, true><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); else decode_kernel<8, false><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); }
-    else                 { if (g64) decode_kernel<16, true><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); else decode_kernel<16, false><<<nblocks(n, DEC_R), DEC_R, 0, c->stream>>>(p); }
+    // staging: LDGSTS (cp.async) for chunks in device memory, register-staged loads for chunks decoded in place from pinned host
+    // memory.  MSG_STAGING=async|ldg overrides (A/B runs).
+    static const char *st_env = getenv("MSG_STAGING");
+    const bool async = st_env ? st_env[0] == 'a' : !host_mapped;
+    const dim3 grid(nblocks(n, DEC_R)), block(DEC_R);
+#define DEC_LAUNCH(L, G, A) decode_kernel<L, G, A><<<grid, block, 0, c->stream>>>(p)
+    if (c->lay_lpr == 8) { if (g64) { if (async) DEC_LAUNCH(8, true, true); else DEC_LAUNCH(8, true, false); } else { if (async) DEC_LAUNCH(8, false, true); else DEC_LAUNCH(8, false, false); } }
+    else                 { if (g64) { if (async) DEC_LAUNCH(16, true, true); else DEC_LAUNCH(16, true, false); } else { if (async) DEC_LAUNCH(16, false, true); else DEC_LAUNCH(16, false, false); } }
+#undef DEC_LAUNCH
     LAUNCHED(c);
     CU(cudaEventRecord(k1, c->stream));
     c->ev_decode.push_back({k0, k1});
@@ -660,7 +668,7 @@ int push_chunk(msg_ctx *c, const uint8_t *h_raw, const uint8_t *dev_raw, size_t 
     if (fused) {
         DecodeParams p;
         const uint64_t before = c->h2d_bytes;
-        rc = launch_decode(c, sl.d_raw, nbytes, sl.readable, sl.d_off, nrec, h_raw, h_off, &p);
+        rc = launch_decode(c, sl.d_raw, nbytes, sl.readable, sl.d_off, nrec, h_raw, h_off, &p, sl.zero_copy);
         if (rc) return rc;
         // bytes the decode kernel asks for over PCIe (window chunks)
         if (sl.zero_copy && c->h2d_bytes == before) c->h2d_bytes += (uint64_t)nrec * (c->lay_hc + c->lay_tc) * 16;
@@ -807,7 +815,24 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
         CUC(cudaMemcpy(ctx->d_covbase, base.data(), (T + 1) * 8, cudaMemcpyHostToDevice));
         if (ctx->cov_bits) {
             ctx->cov_words = base[g.n_targets];
-            CUC(cudaMalloc(&ctx->d_covbits, (size_t)(ctx->cov_words ? ctx->cov_words : 1) * 8));
+            const size_t bytes = (size_t)(ctx->cov_words ? ctx->cov_words : 1) * 8;
+            CUC(cudaMalloc(&ctx->d_covbits, bytes));
+            // The bitmap is hit at random while gigabytes of records stream through the same L2: pin it there (persisting
+            // access-policy window on the context's stream, as much of it as the device allows to set aside).
+            cudaDeviceProp prop;
+            if (!getenv("MSG_NO_L2_PERSIST") && cudaGetDeviceProperties(&prop, g.device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                const size_t aside = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside) == cudaSuccess) {
+                    cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+                    av.accessPolicyWindow.base_ptr = ctx->d_covbits;
+                    av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+                    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)aside / (double)av.accessPolicyWindow.num_bytes);
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) ctx->l2_window = true;
+                }
+                cudaGetLastError();
+            }
         } else {
             ctx->cov_cells = base[g.n_targets];
             const size_t cells = (size_t)(ctx->cov_cells ? ctx->cov_cells : 1);
@@ -867,6 +892,7 @@ void msg_destroy(msg_ctx *c)
     cudaSetDevice(c->cfg.device);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->l2_window) { cudaCtxResetPersistingL2Cache(); cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); cudaGetLastError(); }
     for (Slot &sl : c->slot) {
         sl.raw.release(); sl.off.release();
         if (sl.h_res) cudaFreeHost(sl.h_res);

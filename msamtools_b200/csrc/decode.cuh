@@ -773,7 +773,7 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr,
 // latencies (offsets -> windows) and keeps the issue slots of the (low-ILP) parser busy.  Staging is LDGSTS
 // (cp.async.cg, 16 bytes, no register round trip, `.L2::64B` fill granularity): LPR lanes per record, slots are
 // 16-byte aligned with one pad chunk (stride LPR*16 + 16 bytes).
-template <int LPR, bool G64>
+template <int LPR, bool G64, bool ASYNC>
 __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ DecodeParams p)
 {
     constexpr int SLOT_WORDS = LPR * 4 + 4;
@@ -809,14 +809,31 @@ __global__ void __launch_bounds__(DEC_R) decode_kernel(const __grid_constant__ D
             const uint32_t *wb = (sub < hc ? s_hb : s_tb) + r0;
             uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_slot + r0 * SLOT_WORDS + sub * 4);
             const uint4 *src = reinterpret_cast<const uint4 *>(p.raw);
+            if (ASYNC) {
 #pragma unroll
-            for (uint32_t it = 0; it < LPR; it++) {
-                const uint32_t cidx = wb[it * (DEC_R / LPR)] + sub;         // a tail window that starts before the buffer wraps to a huge index
-                if (cidx < nchunks) cp_async16(dst + it * (DEC_R / LPR) * SLOT_WORDS * 4, src + cidx, G64);
+                for (uint32_t it = 0; it < LPR; it++) {
+                    const uint32_t cidx = wb[it * (DEC_R / LPR)] + sub;     // a tail window that starts before the buffer wraps to a huge index
+                    if (cidx < nchunks) cp_async16(dst + it * (DEC_R / LPR) * SLOT_WORDS * 4, src + cidx, G64);
+                }
+            } else {
+                // register-staged variant (all LPR loads in flight before the first 16-byte shared-memory store): what chunks that
+                // live in pinned HOST memory use -- LDGSTS from system memory over PCIe ran at half the rate of plain loads
+                uint4 v[LPR]; bool ok[LPR];
+#pragma unroll
+                for (uint32_t it = 0; it < LPR; it++) {
+                    const uint32_t cidx = wb[it * (DEC_R / LPR)] + sub;
+                    ok[it] = cidx < nchunks;
+                    if (ok[it]) v[it] = G64 ? ldg_stream128(src + cidx) : ldg_stream128_line(src + cidx);
+                }
+#pragma unroll
+                for (uint32_t it = 0; it < LPR; it++)
+                    if (ok[it]) *reinterpret_cast<uint4 *>(s_slot + (r0 + it * (DEC_R / LPR)) * SLOT_WORDS + sub * 4) = v[it];
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (ASYNC) {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
     }
     __syncthreads();
 
