@@ -88,7 +88,8 @@ def source_stamp(files):
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "clocks.mem,temperature.gpu")
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
@@ -115,19 +116,24 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
+        sm, mx, pw, mem, temp, reasons = [], [], [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
+            try:
+                mem.append(float(r[9])); temp.append(float(r[10]))
+            except (ValueError, IndexError):
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         # median over the samples taken under load (power above the idle floor), else over all of them
         hot = [s for s, p in zip(sm, pw) if p > 300.0]
         return {"sm_mhz": statistics.median(hot or sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(hot), "power_w_max": max(pw) if pw else None}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(hot), "power_w_max": max(pw) if pw else None,
+                "mem_mhz_min": min(mem) if mem else None, "temp_c_max": max(temp) if temp else None}
 
 
 def dist_env():
@@ -529,19 +535,32 @@ def run_ours(args):
         ctx.sync()
         return None
 
+    host_t = [0.0, 0.0, 0.0]                       # wall clock spent inside reset / pushes / finish (diagnostics: where a step's time goes on the host)
+
     def step_resident():
+        t_a = time.perf_counter()
         ctx.reset()
+        t_b = time.perf_counter()
         for k in order:
-            ctx.push_device(*dev_chunks[k])
-        return finish()
+            ctx.push_device_async(*dev_chunks[k])
+        ctx.wait()
+        t_c = time.perf_counter()
+        out_ = finish()
+        t_d = time.perf_counter()
+        host_t[0] += t_b - t_a; host_t[1] += t_c - t_b; host_t[2] += t_d - t_c
+        return out_
 
     for _ in range(args.warmup):
         out = step_resident()
     ctx.timing(reset=True)
+    host_t[:] = [0.0, 0.0, 0.0]
+    # every rank samples its own GPU; the samplers start BEFORE the barrier: round 1 started rank 0's nvidia-smi between the
+    # barrier and the first timed step, and the other ranks' timed regions then contained their wait for rank 0 (tens of ms of
+    # process start-up on an 8-GPU node, i.e. +1 ms per step of a 20 x 1 ms region: the "N = 2 anomaly" of round 1)
     sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.05)
     barrier()
-    if rank == 0:
-        sampler.start()
     ctx.mark(0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -611,7 +630,15 @@ def run_ours(args):
                "api": "msg_push_async x chunks (pinned host buffers, two chunks in flight) + msg_wait + msg_finish_*",
                "h2d_mode": ("zero-copy: decode windows pulled from the pinned host chunks over PCIe (h2d bytes = window chunks requested + offset "
                             "index DMA; SEQ/QUAL never leave the host)") if tim2.get("zero_copy_chunks", 0) else "staged: whole chunks DMA'd into two device slots"}
-    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (resident + e2e)
+    clocks = sampler.stop()                             # sampled across both timed regions (resident + e2e)
+    per_rank = {"rank": rank, "decode_launch_ms": tim["decode_ms"] / max(tim["decode_launches"], 1), "step_ms": max(dev_ms, 0.0) / args.steps,
+                "host_ms_per_step": {"reset": 1e3 * host_t[0] / args.steps, "push": 1e3 * host_t[1] / args.steps, "finish": 1e3 * host_t[2] / args.steps},
+                "sm_mhz": clocks["sm_mhz"], "mem_mhz_min": clocks.get("mem_mhz_min"), "temp_c_max": clocks.get("temp_c_max"), "reasons": clocks["reasons"]}
+    if dist is not None:
+        ranks_info = [None] * world
+        dist.all_gather_object(ranks_info, per_rank)
+    else:
+        ranks_info = [per_rank]
 
     for k in order:
         ctx.device_free(dev_chunks[k][0]); ctx.device_free(dev_chunks[k][2])
@@ -639,7 +666,9 @@ def run_ours(args):
             "dtype": "int32+f64", "data": "synthetic",
             "config": config_json(cfg, key, plan, records, len(tlen)),
             "run": {"records_per_gpu": int(n_local), "raw_bytes_per_gpu": int(raw_bytes), "kept_records_last_chunk": kept_last,
-                    "wall_ms_per_step": wall_step_ms, "generation_s": round(t_gen, 1), "job": job_check},
+                    "wall_ms_per_step": wall_step_ms, "generation_s": round(t_gen, 1),
+                    "host_ms_per_step": {"reset": 1e3 * host_t[0] / args.steps, "push": 1e3 * host_t[1] / args.steps, "finish": 1e3 * host_t[2] / args.steps},
+                    "job": job_check},
             "parity_checked": bool(parity_ok), "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "decode_kernel (record decode + fused filter statistics)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -649,6 +678,7 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": int(tim["kernel_launches"]),
             "clocks": clocks,
+            "ranks": ranks_info,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_entry(cfg, args, plan, tlen)

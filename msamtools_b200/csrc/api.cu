@@ -1202,8 +1202,10 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 unsigned long long timeout_ns = (unsigned long long)(peer_timeout_s * 1e9);
                 void *margs[] = {&a0, &a1, &a2, &nl_arg, &ui_arg, &cnt_arg, &nl_lo, &nl_hi, &Uw, &av, &inc, &partial, &F_arg, &dout, &d_res, &hc_dev,
                                  &totbuf, &bflag, &pt, &nr, &rk, &epoch, &timeout_ns};
+                unsigned long long *d_trace = nullptr;
+                if (trace && g.n_ranks > 1) { CU(c->t_ui.reserve(20 * 8 * 8)); d_trace = c->t_ui.as<unsigned long long>(); CU(cudaMemsetAsync(d_trace, 0, 20 * 8 * 8, c->stream)); }
                 void *rargs[] = {&a0, &a1, &a2, &nl_arg, &ui_arg, &cnt_arg, &nl_lo, &nl_hi, &Uw, &av, &inc, &F_arg, &dout, &d_res, &hc_dev,
-                                 &pt, &nr, &rk, &epoch, &timeout_ns};
+                                 &pt, &nr, &rk, &epoch, &timeout_ns, &d_trace};
                 // single GPU: inc[3F], delta and d_res were cleared by em_init_kernel; the multi-GPU kernel clears its own state
                 if (g.n_ranks > 1) {
                     // The kernels of all ranks wait for one another inside the loop: line the ranks up first (a 4-byte NCCL
@@ -1288,6 +1290,18 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
         if (!c->ev_decode.empty()) cudaEventElapsedTime(&dec, c->ev_decode.back().first, c->ev_decode.back().second);
         fprintf(stderr, "[msg finish rank %d] last chunk %.3f ms (decode %.3f), gap %.3f ms, allreduce %.3f ms, init %.3f ms, loop %.3f ms, tail %.3f ms\n",
                 g.rank, chunk, dec, gap, ms[0], ms[1], ms[2], ms[3]);
+        if (g.n_ranks > 1 && F + 8 > EM_XCHG_CTA0 && c->t_ui.p && g.share_type == MSG_MULTI_PROPORTIONAL) {
+            // CTA 0's view of the exchanges (ns): RS stores | fence+flags | owner blocks | announce | AG wait | grid barrier | delta ; gather = gap to the next exchange
+            unsigned long long tr[160]; cudaMemcpy(tr, c->t_ui.p, sizeof tr, cudaMemcpyDeviceToHost);
+            double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int nx = 0;
+            for (int k = 1; k < 20 && tr[k * 8 + 7]; k++) {
+                for (int j = 0; j < 7; j++) acc[j] += (double)(tr[k * 8 + j + 1] - tr[k * 8 + j]);
+                if (k + 1 < 20 && tr[(k + 1) * 8]) acc[7] += (double)(tr[(k + 1) * 8] - tr[k * 8 + 7]);
+                nx++;
+            }
+            if (nx) fprintf(stderr, "[msg finish rank %d] rsag exchange, mean over %d (us): rs-store %.1f fence+flags %.1f owner %.1f announce %.1f ag-wait %.1f barrier %.1f delta %.1f | gather+barrier %.1f\n",
+                            g.rank, nx, acc[0] / nx / 1e3, acc[1] / nx / 1e3, acc[2] / nx / 1e3, acc[3] / nx / 1e3, acc[4] / nx / 1e3, acc[5] / nx / 1e3, acc[6] / nx / 1e3, acc[7] / nx / 1e3);
+        }
         for (auto e : tev) if (e) cudaEventDestroy(e);
     }
     if (abundance && F) memcpy(abundance, c->h_ab, (size_t)F * 8);

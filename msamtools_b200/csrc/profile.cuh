@@ -946,6 +946,9 @@ __host__ __device__ inline RsagLayout rsag_layout(uint32_t F, int n_ranks)
     return L;
 }
 
+// release / acquire fence at system scope (what a flag store after peer-memory data stores needs; cheaper than the
+// sequentially consistent __threadfence_system)
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_relaxed_sys_u32(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
@@ -956,7 +959,8 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
                                                            const uint32_t *ui, const uint32_t *counters, uint32_t nl_lo, uint32_t nl_hi,
                                                            double *U, double *a_out, double *inc, uint32_t F,
                                                            double *delta_out, int32_t *result, uint32_t *hc_out,
-                                                           PeerTable peers, int n_ranks, int rank, uint32_t epoch, unsigned long long timeout_ns)
+                                                           PeerTable peers, int n_ranks, int rank, uint32_t epoch, unsigned long long timeout_ns,
+                                                           unsigned long long *trace /* diagnostics: [20][8] ns stamps of CTA 0, or null */)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -978,8 +982,10 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
 
     // One exchange.  first: the values are the doubled counts (U = a = total / 2, no delta); else the increments.
     bool dead = false;                               // a peer never showed up: same value in every thread (read after a grid barrier)
+    auto stamp = [&](uint32_t k, uint32_t j) { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && k < 20) trace[k * 8 + j] = globaltimer_ns(); };
     auto exchange = [&](uint32_t k, bool first) -> double {
         const uint32_t par = k & 1u, tag = epoch + k;
+        stamp(k, 0);
         // ---- reduce-scatter, sender side: block (s, b) of my vector -> rank s.  All of this CTA's blocks first, then ONE
         //      fence.sys (it waits for the NVLink writes to be acknowledged: microseconds), then their flags.
         for (uint32_t blk = blockIdx.x; blk < N * nblk; blk += gridDim.x) {
@@ -996,19 +1002,21 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
             st_weak_v2f64(dst, v0, v1);
         }
         __syncthreads();
+        stamp(k, 1);
         if (threadIdx.x == 0) {
-            __threadfence_system();
+            fence_acq_rel_sys();
             for (uint32_t blk = blockIdx.x; blk < N * nblk; blk += gridDim.x) {
                 const uint32_t s = blk / nblk, b = blk - s * nblk;
                 st_relaxed_sys_u32(reinterpret_cast<uint32_t *>(peers.base[s] + L.rs_flag()) + ((size_t)par * N + (size_t)rank) * nblk + b, tag);
             }
         }
+        stamp(k, 2);
         // ---- owner side: blocks of my slice.  Wait for the N partials, reduce in rank order, update, all-gather; the
         //      blocks' delta shares are announced (flagged word pairs) after one fence.sys for all of them.
         const double *a_old = a_buf(par ^ 1u);
         uint32_t nmine = 0, b_first = blockIdx.x;
         auto announce = [&]() {                             // thread 0: one fence for the buffered blocks, then their flagged delta shares
-            __threadfence_system();                         // cumulative over this CTA's stores (they happen-before through the barriers)
+            fence_acq_rel_sys();                         // cumulative over this CTA's stores (they happen-before through the barriers)
             uint32_t bb = b_first;
             for (uint32_t j = 0; j < nmine; j++, bb += gridDim.x) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(s_dd[j]), t = (unsigned long long)tag << 32;
@@ -1066,7 +1074,9 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
             }
             __syncthreads();
         }
+        stamp(k, 3);
         if (threadIdx.x == 0 && nmine) announce();
+        stamp(k, 4);
         // ---- all-gather, receiver side: every block of every owner must have landed in my copy of a[]
         {
             const unsigned long long want = (unsigned long long)tag;
@@ -1079,9 +1089,11 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
                     if (expired()) break;
                 }
             }
-            __threadfence_system();
+            fence_acq_rel_sys();
         }
+        stamp(k, 5);
         grid.sync();
+        stamp(k, 6);
         dead = *timed_out != 0;                      // nobody polls between this barrier and the next exchange: uniform
         // ---- DELTA^2: all N*nblk block shares, same order on every rank and in every CTA            (:380)
         double acc = 0;
@@ -1096,6 +1108,7 @@ __global__ void __launch_bounds__(256) em_loop_rsag_kernel(const uint32_t *mm_of
         for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
         const double delta = s_red[0] / F;
         __syncthreads();
+        stamp(k, 7);
         return delta;
     };
     // flagged scalars: sender `rank` writes word j of its row in every peer's scalar area
