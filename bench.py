@@ -380,6 +380,86 @@ def cpu_baseline_entry(cfg, args, plan, tlen):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ host ingest (R3: file to result)
+def write_bgzf_threads(path, blobs, level=1, threads=8):
+    """BGZF at `level` with the blocks deflated on worker threads (zlib releases the GIL)"""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    data = b"".join(bytes(b) for b in blobs)
+    starts = list(range(0, len(data), 0xff00))
+
+    def pack(group):
+        out = []
+        for o in group:
+            blk = data[o:o + 0xff00]
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            comp = co.compress(blk) + co.flush()
+            out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp +
+                       struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))
+        return b"".join(out)
+
+    groups = [starts[i:i + 64] for i in range(0, len(starts), 64)]
+    with ThreadPoolExecutor(max_workers=threads) as ex, open(path, "wb") as fh:
+        for part in ex.map(pack, groups):
+            fh.write(part)
+        fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    return len(data)
+
+
+def ingest_entry(cfg, plan, tlen, raw, off):
+    """R3 of SURVEY 8d, reported separately from the kernels (north_star): a level-1 BGZF BAM of the workload on tmpfs through the
+    drop-in CLI (`filter ... | profile ...`, file to result) with 1 / 4 / 16 inflate threads -- host read+inflate GB/s from the
+    CLI's own timers, alignments/s by wall clock -- and the reference's object code on the same file."""
+    import re
+    import tempfile
+    cli = os.path.join(ROOT, "msamtools_b200", "bin", "msamtools")
+    if not os.path.exists(cli):
+        return {"unavailable": "msamtools_b200/bin/msamtools not built"}
+    n = len(off) - 1
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="msb200_ingest_", dir=base)
+    path = os.path.join(d, "in.bam")
+    cores = os.cpu_count() or 1
+    payload = write_bgzf_threads(path, [bam_header_blob([f"g{i:07d}" for i in range(len(tlen))], tlen), raw], level=1, threads=min(cores, 16))
+    out = {"file": f"{n} alignments of chunk 0, BGZF level 1 on tmpfs", "payload_bytes": int(payload), "file_bytes": os.path.getsize(path), "threads": {}}
+    f_args = cfg["ref_filter"][:1] + [a for a in cfg["ref_filter"][1:]]
+
+    def pipe(binary, env):
+        t0 = time.perf_counter()
+        if cfg["ref_second"] is None:
+            a = [binary] + f_args + (["-o", os.path.join(d, "o.gz")] if f_args[0] == "profile" else []) + [path]
+            p1 = subprocess.run(a, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+            err, rc = p1.stderr, p1.returncode
+        else:
+            p1 = subprocess.Popen([binary] + f_args + [path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+            p2 = subprocess.Popen([binary] + cfg["ref_second"] + ["-o", os.path.join(d, "o.gz"), "-"], stdin=p1.stdout, stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL, env=env)
+            p1.stdout.close()
+            err = p1.stderr.read()
+            rc = p2.wait() | p1.wait()
+        return time.perf_counter() - t0, err.decode(errors="replace"), rc
+
+    try:
+        for thr in (1, 4, 16):
+            if thr > cores and thr != 1:
+                continue
+            env = dict(os.environ, MSAMTOOLS_TIMING="1", MSAMTOOLS_THREADS=str(thr))
+            pipe(cli, env)                                  # warm-up (CUDA context creation is part of every CLI run; page cache)
+            dt, err, rc = pipe(cli, env)
+            m = re.search(r"host ingest ([0-9.]+) GB in ([0-9.]+) s", err)
+            out["threads"][str(thr)] = {"file_to_result_M_aln_per_s": n / dt / 1e6, "wall_s": dt, "rc": rc,
+                                        "inflate_gbs": (float(m.group(1)) / float(m.group(2))) if m and float(m.group(2)) > 0 else None}
+        if have_ref_binary():
+            dt, _, rc = pipe(REF_BIN, dict(os.environ))
+            out["reference_single_pipe"] = {"file_to_result_M_aln_per_s": n / dt / 1e6, "wall_s": dt, "rc": rc,
+                                            "note": "the reference's object code on the same file: one process per command, single-threaded inflate (shim I/O)"}
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ parity inside the bench
 def close_rel(a, b, rel=1e-9):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
@@ -682,6 +762,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_entry(cfg, args, plan, tlen)
+        if world == 1 and not args.no_ingest:
+            line["ingest"] = ingest_entry(cfg, plan, tlen, *host_chunks[0])
         print(json.dumps(line))
     ctx.close()
     for a, b in pinned:
@@ -707,6 +789,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the BGZF file-to-result (host ingest) leg")
     ap.add_argument("--cpu-port", action="store_true", help="time the in-memory oracle port even when oracle/_ref exists")
     args = ap.parse_args()
     if args.impl == "reference":

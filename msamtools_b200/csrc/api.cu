@@ -215,7 +215,10 @@ int run_scan(msg_ctx *c, In in, Out out, uint64_t n, T *h_total)
 }
 
 int report_device_errors(msg_ctx *c, const uint32_t *h);
-static const int EM_CTAS_PER_SM = getenv("MSG_EM_CTAS") ? atoi(getenv("MSG_EM_CTAS")) : 3;
+// CTAs per SM of the cooperative PropSharing kernels: 3 where a[] lives in shared memory (F <= 2048: measured best, round 1),
+// 6 for the global-memory kernels of larger feature sets (latency-bound gathers; 2: 3.38, 4: 3.30, 6: 3.20, 8: 3.19 ms per
+// 20 M-record config-5 step).  MSG_EM_CTAS overrides both.
+static const int EM_CTAS_ENV = getenv("MSG_EM_CTAS") ? atoi(getenv("MSG_EM_CTAS")) : 0;
 
 int check_device_errors(msg_ctx *c)
 {
@@ -1180,7 +1183,8 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<false>, 256, shm));
             }
             if (per_sm < 1 && coop_multi) return fail(c, MSG_ECUDA, "cannot launch the cooperative PropSharing kernel (F = %u needs too much shared memory?)", F);
-            if (per_sm > EM_CTAS_PER_SM) per_sm = EM_CTAS_PER_SM;
+            const int want_ctas = EM_CTAS_ENV > 0 ? EM_CTAS_ENV : (sm ? 3 : 6);
+            if (per_sm > want_ctas) per_sm = want_ctas;
             if (per_sm >= 1) {
                 uint32_t grid = (uint32_t)(nsm * per_sm);
                 CU(c->tile_sums.reserve((size_t)grid * 8 + 16));
