@@ -469,19 +469,28 @@ def close_rel(a, b, rel=1e-9):
 def parity_check(m, cfg, plan, tlen, rank, world, local, dist, bcast):
     """A subsample of this workload (the first `v` records of every rank's chunk 0, >= 1 M records in total) through the
     same contexts' code path (same options, same n_ranks: fused pass + the in-kernel cross-GPU exchange) vs the CPU
-    oracle run over the concatenation of all ranks' subsamples.  Integers exact, abundances within 1e-9 relative."""
+    oracle run over the concatenation of all ranks' subsamples.  Integers / bytes exact, abundances within 1e-9 relative."""
     from oracle import oracle as orc
+    opts = cfg["ctx"]
     v = 1_000_000 if world == 1 else 500_000
     raw, off = gen_chunk(cfg, rank, 0, plan, n_records=v)
     uid = bcast(m.nccl_unique_id() if (world > 1 and rank == 0) else None)
-    with m.Context(n_targets=len(tlen), device=local, n_ranks=world, rank=rank, nccl_unique_id=uid, **cfg["ctx"]) as ctx:
+    kw = dict(n_targets=len(tlen), device=local, n_ranks=world, rank=rank, nccl_unique_id=uid)
+    if opts.get("coverage"):
+        kw["target_len"] = tlen
+    ab = st = cov = rec = None
+    with m.Context(**kw, **opts) as ctx:
         ctx.push(raw, off)
         kept = ctx.kept_count()
-        ab, st = ctx.finish_profile()
+        if opts.get("profile"):
+            ab, st = ctx.finish_profile()
+        if opts.get("coverage"):
+            cov = ctx.finish_coverage()
+        if opts.get("records"):
+            rec = ctx.pull_records()[0]
     res = {"subsample_records_per_rank": int(len(off) - 1)}
-    digest = hashlib.sha1(ab.tobytes()).hexdigest()
+    digest = hashlib.sha1(ab.tobytes()).hexdigest() if ab is not None else ""
     if dist is not None:
-        import torch
         box = [None] * world
         dist.all_gather_object(box, (digest, int(kept)))
         digests, kepts = [b[0] for b in box], [b[1] for b in box]
@@ -495,16 +504,29 @@ def parity_check(m, cfg, plan, tlen, rank, world, local, dist, bcast):
         for r in range(1, world):
             rr, ro = gen_chunk(cfg, r, 0, plan, n_records=v)
             raws.append(rr); offs.append(ro[1:] + np.uint64(base)); base += int(ro[-1])
-        raw_all, off_all = np.concatenate(raws), np.concatenate(offs)
-        eab, est = orc.pipeline(raw_all, off_all, orc.filter_cfg(besthit=True, **FILTER), len(tlen), 3)
-        ints = {k: (int(st[k]), int(est[k])) for k in ("mapped_inserts", "uniq", "multi", "purged", "iterations", "converged", "n_lists")}
-        ints["kept_records"] = (int(sum(kepts)), int(est["n_kept"]))
-        res.update(records=int(len(off_all) - 1), integers_exact=all(a == b for a, b in ints.values()),
-                   abundance_within_1e9=close_rel(ab, eab), em_iterations=int(est["iterations"]), multi_lists=int(est["n_lists"]),
-                   max_rel_err=float(np.max(np.abs(ab - eab) / np.maximum(np.maximum(np.abs(ab), np.abs(eab)), 1e-300))))
+        raw_all, off_all = (np.concatenate(raws), np.concatenate(offs)) if world > 1 else (raw, off)
+        res["records"] = int(len(off_all) - 1)
+        do_filter = opts.get("do_filter", True)
+        ocfg = orc.filter_cfg(besthit=bool(opts.get("besthit")), **FILTER) if do_filter else None
+        idx = orc.filter_stream(raw_all, off_all, ocfg) if do_filter else None
+        ints = {"kept_records": (int(sum(kepts)), int(len(idx)) if idx is not None else int(len(off_all) - 1))}
+        if opts.get("profile"):
+            eab, est, _, _ = orc.profile(raw_all, off_all, idx, len(tlen), 3)
+            ints.update({k: (int(st[k]), int(est[k])) for k in ("mapped_inserts", "uniq", "multi", "purged", "iterations", "converged", "n_lists")})
+            res.update(abundance_within_1e9=close_rel(ab, eab), em_iterations=int(est["iterations"]), multi_lists=int(est["n_lists"]),
+                       max_rel_err=float(np.max(np.abs(ab - eab) / np.maximum(np.maximum(np.abs(ab), np.abs(eab)), 1e-300))))
+            ok = ok and res["abundance_within_1e9"]
+        if opts.get("coverage"):
+            ecov = orc.coverage(raw_all, off_all, idx, tlen)
+            res["coverage_exact"] = bool(all(np.array_equal(a_, b_) for a_, b_ in zip(cov, ecov[:3])))
+            ok = ok and res["coverage_exact"]
+        if opts.get("records"):
+            res["record_bytes_exact"] = bool(bytes(rec) == bytes(orc.emit_records(raw_all, off_all, idx, ocfg)))
+            ok = ok and res["record_bytes_exact"]
+        res["integers_exact"] = all(a_ == b_ for a_, b_ in ints.values())
         if not res["integers_exact"]:
             res["integer_mismatches"] = {k: v2 for k, v2 in ints.items() if v2[0] != v2[1]}
-        ok = ok and res["integers_exact"] and res["abundance_within_1e9"]
+        ok = ok and res["integers_exact"]
     ok = bool(bcast(ok if rank == 0 else None))
     return ok, res
 
@@ -559,8 +581,8 @@ def run_ours(args):
     has_rec = bool(cfg["ctx"].get("records"))
 
     # ---- parity first (also warms every code path up)
-    parity_ok, parity = (True, {"skipped": "profile configs only"})
-    if has_profile and key in (5, 12) and not args.no_parity:
+    parity_ok, parity = (None, {"skipped": "--no-parity"})
+    if not args.no_parity:
         parity_ok, parity = parity_check(m, cfg, plan, tlen, rank, world, local, dist, bcast)
         if not parity_ok:
             if rank == 0:
@@ -671,7 +693,7 @@ def run_ours(args):
                      "abundance_sum_eq_inserts_minus_purged": bool(abs(ab.sum() - (st["mapped_inserts"] - st["purged"])) <= 1e-6 * max(st["mapped_inserts"], 1)),
                      "inserts": int(st["mapped_inserts"]), "multi_lists": int(st["n_lists"]), "purged": int(st["purged"]),
                      "em_iterations": int(st["iterations"]), "em_converged": int(st["converged"])}
-        parity_ok = parity_ok and all(v for k2, v in job_check.items() if isinstance(v, bool))
+        parity_ok = bool(parity_ok is not False and all(v for k2, v in job_check.items() if isinstance(v, bool))) if parity_ok is not None else None
 
     # ---- end to end: pinned HOST chunks through the public push API, H2D + D2H inside the timed region
     e2e_order = sorted(host_chunks)
@@ -749,7 +771,7 @@ def run_ours(args):
                     "wall_ms_per_step": wall_step_ms, "generation_s": round(t_gen, 1),
                     "host_ms_per_step": {"reset": 1e3 * host_t[0] / args.steps, "push": 1e3 * host_t[1] / args.steps, "finish": 1e3 * host_t[2] / args.steps},
                     "job": job_check},
-            "parity_checked": bool(parity_ok), "parity": parity,
+            "parity_checked": bool(parity_ok) if parity_ok is not None else False, "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "decode_kernel (record decode + fused filter statistics)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "traffic": traffic, "alg_bytes_per_launch": alg_per_launch, "launch_ms": dec_ms, "launches_per_step": launches / args.steps,
@@ -770,7 +792,7 @@ def run_ours(args):
         a.close(); b.close()
     if dist is not None:
         dist.destroy_process_group()
-    if not parity_ok:
+    if parity_ok is False:
         sys.exit("bench.py: result checks FAILED")
 
 
