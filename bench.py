@@ -697,6 +697,7 @@ def run_ours(args):
 
     # ---- end to end: pinned HOST chunks through the public push API, H2D + D2H inside the timed region
     e2e_order = sorted(host_chunks)
+    rec_out = m.PinnedBuffer(max(host_chunks[k][0].nbytes for k in e2e_order) + 4096, device=local) if has_rec else None
 
     def step_e2e():
         ctx.reset()
@@ -705,7 +706,7 @@ def run_ours(args):
         ctx.wait()
         res = finish()
         if has_rec:
-            ctx.pull_records()
+            ctx.pull_records(rec_out.array)          # the filtered records come back into pinned host memory
         return res
 
     n_e2e_local = sum(len(host_chunks[k][1]) - 1 for k in e2e_order)
@@ -788,6 +789,8 @@ def run_ours(args):
             line["ingest"] = ingest_entry(cfg, plan, tlen, *host_chunks[0])
         print(json.dumps(line))
     ctx.close()
+    if rec_out is not None:
+        rec_out.close()
     for a, b in pinned:
         a.close(); b.close()
     if dist is not None:

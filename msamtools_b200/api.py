@@ -154,12 +154,14 @@ class Context:
         self._check(self.lib.msg_pull_kept(self.h, _ptr(idx), n, C.byref(got)))
         return idx
 
-    def pull_records(self):
+    def pull_records(self, out=None):
+        """filtered record bytes of the last completed chunk; `out` = caller's (ideally pinned) uint8 buffer to fill"""
         nb, nr = C.c_size_t(), C.c_size_t()
         self._check(self.lib.msg_pull_records(self.h, None, 0, C.byref(nb), C.byref(nr)))
-        out = np.empty(nb.value, dtype=np.uint8)
+        if out is None:
+            out = np.empty(nb.value, dtype=np.uint8)
         self._check(self.lib.msg_pull_records(self.h, _ptr(out), out.nbytes, C.byref(nb), C.byref(nr)))
-        return out, nr.value
+        return out[:nb.value], nr.value
 
     def pull_stats(self):
         n = self._last_n

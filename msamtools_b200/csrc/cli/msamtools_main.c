@@ -328,6 +328,10 @@ static void write_kept_records(run_t *r, msg_ctx *ctx, uint8_t **outbuf, size_t 
     if (msg_pull_records(ctx, NULL, 0, &nb, &nr)) gpu_die(ctx);
     if (nb > *outcap) { *outcap = nb + nb / 4; *outbuf = realloc(*outbuf, *outcap); if (!*outbuf) mDie("Out of memory"); }
     if (msg_pull_records(ctx, *outbuf, *outcap, &nb, &nr)) gpu_die(ctx);
+    if (bio_is_bam(r->out)) {                         /* the bytes already are BAM records: blocks are packed on the worker threads */
+        if (bio_write_raw(r->out, *outbuf, nb)) mDie("Cannot write alignment record");
+        return;
+    }
     for (size_t o = 0; o < nb;) {
         const uint8_t *p = *outbuf + o;
         uint32_t bs = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
@@ -533,6 +537,11 @@ static int filter_main(int argc, char *argv[])
     }
     r.out = bio_open_write("-", outmode);
     if (!r.out) mDie("Cannot open - for writing");
+    {
+        long n = sysconf(_SC_NPROCESSORS_ONLN);
+        if (getenv("MSAMTOOLS_THREADS")) n = atol(getenv("MSAMTOOLS_THREADS"));
+        bio_set_threads(r.out, n > 16 ? 16 : (int)n);
+    }
     if (bio_write_header(r.out, r.out_hdr) < 0) mDie("Cannot write SAM header");
 
     /* mFilterFileWrapper, msam_filter.c:79-84 */

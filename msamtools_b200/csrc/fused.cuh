@@ -168,8 +168,9 @@ __global__ void __launch_bounds__(256) fused_warp_kernel(const FusedParams p)
 // One thread per pool that straddles a window: the head walks its run twice (best score per mate
 // class, then the winners) and finishes the group from a small local list.  Pools longer than
 // big_threshold records or with more than FUSED_MAXM winners send the chunk to the general pipeline.
-constexpr int FUSED_MAXM = 48;
+constexpr int FUSED_MAXM = 48;    // distinct features per walked pool (more: the chunk goes to the general pipeline)
 constexpr int FUSED_PF = 8;       // records whose columns are prefetched per walked pool
+constexpr int FUSED_DR = 8;       // distinct features kept in registers
 
 __global__ void __launch_bounds__(128) fused_walk_kernel(const FusedParams p)
 {
@@ -179,8 +180,17 @@ __global__ void __launch_bounds__(128) fused_walk_kernel(const FusedParams p)
     // warp-uniform trip count, so that the list-space allocation below can be aggregated per warp
     for (uint32_t qb = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; qb < nw; qb += gridDim.x * blockDim.x) {
       const uint32_t q = qb + lane;
-      int32_t df[FUSED_MAXM]; uint32_t nd = 0, nm = 0; bool emit = false;
+      int32_t df[FUSED_MAXM]; uint32_t dr[FUSED_DR]; uint32_t nd = 0, nm = 0; bool emit = false;
       uint64_t i = 0;
+#pragma unroll
+      for (int k = 0; k < FUSED_DR; k++) dr[k] = 0xffffffffu;
+      // k-th distinct feature: registers first, local-memory list beyond FUSED_DR
+      auto feat_at = [&](uint32_t k) -> int32_t {
+          int32_t v = k >= FUSED_DR ? df[k] : 0;
+#pragma unroll
+          for (int j = 0; j < FUSED_DR; j++) if ((uint32_t)j == k) v = (int32_t)dr[j];
+          return v;
+      };
       if (q < nw) do {
         i = p.worklist[q];
         // The walk is latency bound (one thread per pool, dependent loads), so the first FUSED_PF records' columns are
@@ -214,36 +224,43 @@ __global__ void __launch_bounds__(128) fused_walk_kernel(const FusedParams p)
         for (int k = 0; k < FUSED_PF; k++) if ((uint32_t)k < len) pass1(fr[k], sr[k]);
         for (uint64_t j = i + FUSED_PF; j < end; j++) pass1(p.fb[j], p.score[j]);
         if (paired ? (noas & 6u) : (noas & 1u)) atomicOr(p.err, DERR_NOAS);
-        // pass 2: winners with tid != -1, as (feature, READ2-class?) in input order
-        int32_t mf[FUSED_MAXM]; uint32_t r2bits_lo = 0, r2bits_hi = 0; bool overflow = false;
-        auto pass2 = [&](uint32_t f, int32_t sc, int32_t tt) {
+        // pass 2: the winners' features, distinct, in the order READ1-class winners then READ2-class winners, each in input
+        // order (msam_filter.c:247-254 -> msam_profile.c:136-142).  Two sweeps over the run (the usual short pool sits in the
+        // prefetched registers); the first FUSED_DR distinct features live in registers (compare / insert fully unrolled),
+        // only larger sets touch the local-memory list.
+        bool overflow = false;
+        auto add_feature = [&](int32_t fe) {
+            bool seen = false;
+#pragma unroll
+            for (int k = 0; k < FUSED_DR; k++) seen |= (dr[k] == (uint32_t)fe);
+            for (uint32_t d2 = FUSED_DR; d2 < nd && !seen; d2++) seen = (df[d2] == fe);
+            if (seen) return;
+            if (nd >= FUSED_MAXM) { overflow = true; return; }
+#pragma unroll
+            for (int k = 0; k < FUSED_DR; k++) if ((uint32_t)k == nd) dr[k] = (uint32_t)fe;
+            if (nd >= FUSED_DR) df[nd] = fe;
+            nd++;
+        };
+        auto pass2 = [&](uint32_t f, int32_t sc, int32_t tt, int want_r2) {
             if (overflow || !(f & FB_INPOOL)) return;
             const int c = mate_class(f);
             if (paired ? !(c == 1 || c == 2) : c != 0) return;
+            if ((c == 2) != (want_r2 != 0)) return;
             const int32_t bb = c == 0 ? b0 : (c == 1 ? b1 : b2); const uint32_t cc = c == 0 ? c0 : (c == 1 ? c1 : c2);
             if (sc != bb || (p.uniq && cc != 1)) return;
             keptn++;
             if (tt == -1) return;
             if (tt < 0 || tt >= p.n_targets) { atomicOr(p.err, DERR_FORMAT); return; }
-            if (nm >= FUSED_MAXM) { overflow = true; return; }
-            mf[nm] = fused_feature(p, tt);
-            if (c == 2) { if (nm < 32) r2bits_lo |= 1u << nm; else r2bits_hi |= 1u << (nm - 32); }
             nm++;
+            add_feature(fused_feature(p, tt));
         };
+        for (int ph = 0; ph < 2; ph++) {
 #pragma unroll
-        for (int k = 0; k < FUSED_PF; k++) if ((uint32_t)k < len) pass2(fr[k], sr[k], tr[k]);
-        for (uint64_t j = i + FUSED_PF; j < end; j++) pass2(p.fb[j], p.score[j], p.tid[j]);
-        if (overflow) { atomicOr(p.cnt + 3, 1u); nm = 0; break; }
+            for (int k = 0; k < FUSED_PF; k++) if ((uint32_t)k < len) pass2(fr[k], sr[k], tr[k], ph);
+            for (uint64_t j = i + FUSED_PF; j < end; j++) pass2(p.fb[j], p.score[j], p.tid[j], ph);
+        }
+        if (overflow) { atomicOr(p.cnt + 3, 1u); nm = 0; nd = 0; break; }
         if (nm == 0) break;
-        // distinct features in the order READ1-class winners, then READ2-class winners (msam_filter.c:247-254 -> msam_profile.c:136-142)
-        for (int phase = 0; phase < 2; phase++)
-            for (uint32_t k = 0; k < nm; k++) {
-                const bool isr2 = k < 32 ? (r2bits_lo >> k) & 1u : (r2bits_hi >> (k - 32)) & 1u;
-                if (isr2 != (phase == 1)) continue;
-                bool seen = false;
-                for (uint32_t d2 = 0; d2 < nd; d2++) seen |= (df[d2] == mf[k]);
-                if (!seen) df[nd++] = mf[k];
-            }
         emit = true;
       } while (0);
       if (emit) {
@@ -251,13 +268,13 @@ __global__ void __launch_bounds__(128) fused_walk_kernel(const FusedParams p)
         wi->cross_hash = p.hash[i];
         atomicOr(&wi->n_nonempty, 0x80000000u);
         ins++;
-        if (nd == 1) { atomicAdd(p.ui + df[0], 2u); uq++; }
+        if (nd == 1) { atomicAdd(p.ui + dr[0], 2u); uq++; }
         else {
             mu++;
-            if (p.share_type == 1) { for (uint32_t k = 0; k < nd; k++) atomicAdd(p.ui + df[k], 2u); }
+            if (p.share_type == 1) { for (uint32_t k = 0; k < nd; k++) atomicAdd(p.ui + feat_at(k), 2u); }
             else if (p.share_type == 2) {
-                if (nm == 2) { atomicAdd(p.ui + df[0], 1u); atomicAdd(p.ui + df[1], 1u); }
-                else { const double share = 1.0 / (int)nd; for (uint32_t k = 0; k < nd; k++) atomicAdd(p.d + df[k], share); }
+                if (nm == 2) { atomicAdd(p.ui + dr[0], 1u); atomicAdd(p.ui + dr[1], 1u); }
+                else { const double share = 1.0 / (int)nd; for (uint32_t k = 0; k < nd; k++) atomicAdd(p.d + feat_at(k), share); }
             }
         }
       }
@@ -274,7 +291,9 @@ __global__ void __launch_bounds__(128) fused_walk_kernel(const FusedParams p)
         if (lhead) {
             const uint32_t li = lb + (uint32_t)__popc(lmask & ((1u << lane) - 1u)), base = eb + incl - x;
             p.l_start[li] = base; p.l_len[li] = nd;
-            for (uint32_t k = 0; k < nd; k++) p.l_fid[base + k] = df[k];
+#pragma unroll
+            for (int k = 0; k < FUSED_DR; k++) if ((uint32_t)k < nd) p.l_fid[base + k] = (int32_t)dr[k];
+            for (uint32_t k = FUSED_DR; k < nd; k++) p.l_fid[base + k] = df[k];
         }
       }
     }

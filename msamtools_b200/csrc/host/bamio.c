@@ -30,8 +30,10 @@ struct bio_file {
     /* name -> tid hash for SAM parsing */
     int32_t *ht; size_t ht_size; const bio_hdr *ht_hdr;
     /* writer */
-    int w_bam, w_header, w_level;
+    int w_bam, w_header, w_level, wz_init;
+    z_stream wzs;
     uint8_t *wbuf; size_t wlen;
+    uint8_t *wout; size_t *wolen;        /* bulk writer: packed blocks of one batch */
     char *fmt; size_t fmt_cap;
 };
 
@@ -58,7 +60,7 @@ static int grow(uint8_t **buf, size_t *cap, size_t need)
 /* ============================================================ decompressed byte stream */
 static double now_sec(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
-void bio_set_threads(bio_file *f, int n) { if (f && !f->writing) f->threads = n < 1 ? 1 : (n > 64 ? 64 : n); }
+void bio_set_threads(bio_file *f, int n) { if (f) f->threads = n < 1 ? 1 : (n > 64 ? 64 : n); }
 void bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds) { if (bytes) *bytes = f->ingest_bytes; if (seconds) *seconds = f->ingest_sec; }
 void bio_inflate_stats(const bio_file *f, uint64_t *fast_blocks, uint64_t *zlib_blocks) { if (fast_blocks) *fast_blocks = f->blocks_fast; if (zlib_blocks) *zlib_blocks = f->blocks_zlib; }
 
@@ -758,24 +760,66 @@ int bio_sam_format(const uint8_t *r, size_t len, const bio_hdr *h, char **out, s
 }
 
 /* ============================================================ writer */
-static int bgzf_flush_block(bio_file *f, const uint8_t *data, size_t n)
+/* one BGZF block (gzip member with the BC extra field) of n <= BGZF_BLOCK payload bytes into out (>= n + 64 + n/1000 bytes);
+ * returns its size, 0 on error.  Level 0 ("-u") writes the stored deflate block by hand: no zlib state at all.  zs: a
+ * deflate stream to reuse (deflateReset), or NULL to set one up for this block. */
+#define BGZF_OUT_STRIDE (65536 + 1024)
+static size_t bgzf_pack_block(int level, z_stream *zs, const uint8_t *data, size_t n, uint8_t *out)
 {
-    uint8_t out[65536 + 64];
-    z_stream zs; memset(&zs, 0, sizeof zs);
-    if (deflateInit2(&zs, f->w_level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return -1;
-    zs.next_in = (Bytef *)data; zs.avail_in = (uInt)n;
-    zs.next_out = out + 18; zs.avail_out = sizeof out - 18 - 8;
-    int rc = deflate(&zs, Z_FINISH);
-    if (rc != Z_STREAM_END) { deflateEnd(&zs); return -1; }
-    size_t clen = sizeof out - 18 - 8 - zs.avail_out;
-    deflateEnd(&zs);
-    static const uint8_t hdr[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
-    memcpy(out, hdr, 12);
-    out[12] = 'B'; out[13] = 'C'; out[14] = 2; out[15] = 0;
+    static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    size_t clen;
+    memcpy(out, hdr, 16);
+    if (level == 0) {
+        out[18] = 1;                                            /* BFINAL = 1, BTYPE = 00 (stored) */
+        put16(out + 19, (uint32_t)n); put16(out + 21, (uint32_t)(~n & 0xffffu));
+        memcpy(out + 23, data, n);
+        clen = 5 + n;
+    } else {
+        z_stream local; int own = 0;
+        if (!zs) {
+            memset(&local, 0, sizeof local);
+            if (deflateInit2(&local, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return 0;
+            zs = &local; own = 1;
+        } else if (deflateReset(zs) != Z_OK) return 0;
+        zs->next_in = (Bytef *)data; zs->avail_in = (uInt)n;
+        zs->next_out = out + 18; zs->avail_out = BGZF_OUT_STRIDE - 18 - 8;
+        int rc = deflate(zs, Z_FINISH);
+        clen = BGZF_OUT_STRIDE - 18 - 8 - zs->avail_out;
+        if (own) deflateEnd(zs);
+        if (rc != Z_STREAM_END) return 0;
+    }
     put16(out + 16, (uint32_t)(clen + 18 + 8 - 1));
     put32(out + 18 + clen, (uint32_t)crc32(crc32(0L, NULL, 0), data, (uInt)n));
     put32(out + 18 + clen + 4, (uint32_t)n);
-    return fwrite(out, 1, clen + 26, f->fp) == clen + 26 ? 0 : -1;
+    return clen + 26;
+}
+
+static int bgzf_flush_block(bio_file *f, const uint8_t *data, size_t n)
+{
+    uint8_t out[BGZF_OUT_STRIDE];
+    if (f->w_level != 0 && !f->wz_init) {
+        memset(&f->wzs, 0, sizeof f->wzs);
+        if (deflateInit2(&f->wzs, f->w_level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return -1;
+        f->wz_init = 1;
+    }
+    const size_t k = bgzf_pack_block(f->w_level, f->w_level ? &f->wzs : NULL, data, n, out);
+    if (!k) return -1;
+    return fwrite(out, 1, k, f->fp) == k ? 0 : -1;
+}
+
+/* ---- bulk output: whole blocks of a large buffer are packed (deflate / stored + CRC) on worker threads, written in order */
+typedef struct { int level; const uint8_t *data; size_t nblk; uint8_t *out; size_t *olen; int id, nthr, err; } bgzf_wjob;
+static void *bgzf_wworker(void *arg)
+{
+    bgzf_wjob *j = arg;
+    z_stream zs; int have = 0;
+    if (j->level != 0) { memset(&zs, 0, sizeof zs); if (deflateInit2(&zs, j->level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { j->err = 1; return NULL; } have = 1; }
+    for (size_t k = (size_t)j->id; k < j->nblk; k += (size_t)j->nthr) {
+        j->olen[k] = bgzf_pack_block(j->level, have ? &zs : NULL, j->data + k * BGZF_BLOCK, BGZF_BLOCK, j->out + k * BGZF_OUT_STRIDE);
+        if (!j->olen[k]) { j->err = 1; break; }
+    }
+    if (have) deflateEnd(&zs);
+    return NULL;
 }
 
 static int w_bytes(bio_file *f, const uint8_t *p, size_t n)
@@ -787,6 +831,36 @@ static int w_bytes(bio_file *f, const uint8_t *p, size_t n)
         if (f->wlen == BGZF_BLOCK) { if (bgzf_flush_block(f, f->wbuf, f->wlen)) return -1; f->wlen = 0; }
     }
     return 0;
+}
+
+int bio_write_raw(bio_file *f, const uint8_t *p, size_t n)
+{   /* BAM output: append n bytes of whole records (see bamio.h) */
+    if (!f->w_bam) return -1;
+    if (f->wlen) {                                           /* complete the pending block first */
+        size_t k = BGZF_BLOCK - f->wlen; if (k > n) k = n;
+        if (w_bytes(f, p, k)) return -1;
+        p += k; n -= k;
+    }
+    enum { BATCH = 256 };
+    int nthr = f->threads > 1 ? f->threads : 1;
+    while (n >= BGZF_BLOCK) {
+        size_t nblk = n / BGZF_BLOCK; if (nblk > BATCH) nblk = BATCH;
+        if (!f->wout) { f->wout = malloc((size_t)BATCH * BGZF_OUT_STRIDE); f->wolen = malloc(sizeof(size_t) * BATCH); if (!f->wout || !f->wolen) return -1; }
+        int t = nthr; if ((size_t)t > nblk) t = (int)nblk;
+        pthread_t th[64]; bgzf_wjob job[64];
+        for (int i = 0; i < t; i++) {
+            job[i] = (bgzf_wjob){ f->w_level, p, nblk, f->wout, f->wolen, i, t, 0 };
+            if (i && pthread_create(&th[i], NULL, bgzf_wworker, &job[i])) job[i].err = 2;
+        }
+        bgzf_wworker(&job[0]);
+        int err = job[0].err;
+        for (int i = 1; i < t; i++) { if (job[i].err == 2) { job[i].err = 0; bgzf_wworker(&job[i]); } else pthread_join(th[i], NULL); err |= job[i].err; }
+        if (err) return -1;
+        for (size_t k = 0; k < nblk; k++)
+            if (fwrite(f->wout + k * BGZF_OUT_STRIDE, 1, f->wolen[k], f->fp) != f->wolen[k]) return -1;
+        p += nblk * BGZF_BLOCK; n -= nblk * BGZF_BLOCK;
+    }
+    return n ? w_bytes(f, p, n) : 0;
 }
 
 bio_file *bio_open_write(const char *path, const char *mode)
@@ -842,9 +916,10 @@ int bio_close(bio_file *f)
             if (fwrite(eof, 1, 28, f->fp) != 28) rc = -1;
         }
         if (fflush(f->fp)) rc = -1;
+        if (f->wz_init) deflateEnd(&f->wzs);
     } else if (f->z_init) inflateEnd(&f->zs);
     if (f->own_fp && fclose(f->fp)) rc = -1;
-    free(f->in); free(f->dec); free(f->line); free(f->cin); free(f->ht); free(f->wbuf); free(f->fmt); free(f);
+    free(f->in); free(f->dec); free(f->line); free(f->cin); free(f->ht); free(f->wbuf); free(f->wout); free(f->wolen); free(f->fmt); free(f);
     return rc;
 }
 

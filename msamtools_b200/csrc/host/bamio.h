@@ -34,8 +34,8 @@ int       bio_read_record(bio_file *f, const bio_hdr *h, uint8_t **buf, size_t *
  * 2 = the next block does not fit in cap - *len.  May be mixed with bio_read_record only in the order records-then-raw. */
 int       bio_read_raw(bio_file *f, uint8_t *buf, size_t cap, size_t *len);
 const char *bio_error(const bio_file *f);
-/* BGZF input only: inflate blocks on `n` worker threads (blocks are independent gzip members).
- * Default 1 (streaming inflate on the caller's thread).  Call before bio_read_header.          */
+/* BGZF input: inflate blocks on `n` worker threads (blocks are independent gzip members); default 1 (streaming inflate on the
+ * caller's thread); call before bio_read_header.  BAM output: threads that pack blocks in bio_write_raw.                    */
 void      bio_set_threads(bio_file *f, int n);
 /* bytes of decompressed input produced so far / seconds spent producing them (read + inflate)  */
 void      bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds);
@@ -46,6 +46,9 @@ void      bio_inflate_stats(const bio_file *f, uint64_t *fast_blocks, uint64_t *
 bio_file *bio_open_write(const char *path, const char *mode);
 int       bio_write_header(bio_file *f, const bio_hdr *h);
 int       bio_write_record(bio_file *f, const bio_hdr *h, const uint8_t *rec, size_t len);
+/* BAM output, bulk: append n bytes holding whole raw records.  Full BGZF blocks are packed (deflate, or the stored block of
+ * "-u", plus CRC32) on the worker threads of bio_set_threads and written in order -- same bytes as record-wise writing.  */
+int       bio_write_raw(bio_file *f, const uint8_t *p, size_t n);
 int       bio_close(bio_file *f);
 int       bio_is_bam(const bio_file *f);
 

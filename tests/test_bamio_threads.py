@@ -68,3 +68,50 @@ def test_corrupt_block_is_reported(harness, stream):
     for thr in (1, 4):
         r = subprocess.run([exe, path, str(thr)], capture_output=True)
         assert r.returncode == 1 and (b"corrupt" in r.stderr or b"inflate" in r.stderr or b"CRC" in r.stderr or b"truncated" in r.stderr), r.stderr
+
+
+@pytest.fixture(scope="module")
+def bulk(tmp_path_factory):
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    d = tmp_path_factory.mktemp("bamio_bulk")
+    exe = str(d / "bulk")
+    srcs = [os.path.join(ROOT, "tests", "c", "bamio_bulk_harness.c"), os.path.join(HOST, "bamio.c"), os.path.join(HOST, "finflate.c")]
+    subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", HOST] + srcs +
+                   ["-lz", "-lpthread", "-o", exe], check=True)
+    return exe, d
+
+
+@pytest.mark.parametrize("level", [0, 6])
+def test_bulk_reader_into_fixed_buffer(bulk, stream, level):
+    """bio_read_raw (what the CLI's reader thread uses): BGZF blocks inflated straight into a fixed-capacity buffer, for buffer
+    sizes below / around / far above a batch of blocks, with and without worker threads: always the original record stream"""
+    exe, d = bulk
+    raw, names, tlen = stream
+    import numpy as np
+    path = str(d / f"r{level}.bam")
+    samutil.write_bam(path, samutil.synth_header(names, tlen), names, tlen, np.frombuffer(raw, dtype=np.uint8), level=level)
+    for thr in (1, 3):
+        for cap in (70_000, 200_001, 64 << 20):
+            r = subprocess.run([exe, "read", path, str(thr), str(cap)], capture_output=True)
+            assert r.returncode == 0, r.stderr.decode()
+            assert r.stdout == raw, (thr, cap)
+
+
+@pytest.mark.parametrize("mode", ["wbu", "wb"])
+def test_bulk_writer_equals_recordwise(bulk, stream, mode):
+    """bio_write_raw (blocks packed on worker threads; level 0 as hand-made stored blocks) writes byte for byte what
+    bio_write_record writes, and the file reads back as the original stream"""
+    exe, d = bulk
+    raw, names, tlen = stream
+    import numpy as np
+    path = str(d / "w_in.bam")
+    samutil.write_bam(path, samutil.synth_header(names, tlen), names, tlen, np.frombuffer(raw, dtype=np.uint8), level=1)
+    outs = {}
+    for how, thr in (("copyr", 1), ("copy", 1), ("copy", 4)):
+        out = str(d / f"w_{how}_{thr}_{mode}.bam")
+        r = subprocess.run([exe, how, path, str(thr), mode, out], capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()
+        outs[(how, thr)] = open(out, "rb").read()
+        assert bytes(samutil.read_bam(out).raw) == raw
+    assert outs[("copy", 1)] == outs[("copyr", 1)] and outs[("copy", 4)] == outs[("copyr", 1)]
