@@ -216,8 +216,8 @@ int run_scan(msg_ctx *c, In in, Out out, uint64_t n, T *h_total)
 
 int report_device_errors(msg_ctx *c, const uint32_t *h);
 // CTAs per SM of the cooperative PropSharing kernels: 3 where a[] lives in shared memory (F <= 2048: measured best, round 1),
-// 6 for the global-memory kernels of larger feature sets (latency-bound gathers; 2: 3.38, 4: 3.30, 6: 3.20, 8: 3.19 ms per
-// 20 M-record config-5 step).  MSG_EM_CTAS overrides both.
+// 4 for the global-memory kernels of larger feature sets (latency-bound gathers; config-5 step at 100 M records: 2: 13.01,
+// 3: 12.50, 4: 12.10, 6: 12.14 ms; at 20 M records: 2: 3.38, 4: 3.30, 6: 3.20, 8: 3.19 ms).  MSG_EM_CTAS overrides both.
 static const int EM_CTAS_ENV = getenv("MSG_EM_CTAS") ? atoi(getenv("MSG_EM_CTAS")) : 0;
 
 int check_device_errors(msg_ctx *c)
@@ -1183,7 +1183,7 @@ int msg_finish_profile(msg_ctx *c, double *abundance, msg_profile_stats *st)
                 else    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_loop_kernel<false>, 256, shm));
             }
             if (per_sm < 1 && coop_multi) return fail(c, MSG_ECUDA, "cannot launch the cooperative PropSharing kernel (F = %u needs too much shared memory?)", F);
-            const int want_ctas = EM_CTAS_ENV > 0 ? EM_CTAS_ENV : (sm ? 3 : 6);
+            const int want_ctas = EM_CTAS_ENV > 0 ? EM_CTAS_ENV : (sm ? 3 : 4);
             if (per_sm > want_ctas) per_sm = want_ctas;
             if (per_sm >= 1) {
                 uint32_t grid = (uint32_t)(nsm * per_sm);
