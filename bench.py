@@ -91,12 +91,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
          "clocks.mem,temperature.gpu")
 
-    def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+    def __init__(self, device, interval_ms=20):
+        self.device, self.rows, self.proc, self.interval_ms = device, [], None, interval_ms
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.interval_ms),
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -659,7 +659,7 @@ def run_ours(args):
     # every rank samples its own GPU; the samplers start BEFORE the barrier: round 1 started rank 0's nvidia-smi between the
     # barrier and the first timed step, and the other ranks' timed regions then contained their wait for rank 0 (tens of ms of
     # process start-up on an 8-GPU node, i.e. +1 ms per step of a 20 x 1 ms region: the "N = 2 anomaly" of round 1)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, 20 if rank == 0 else 100)
     sampler.start()
     time.sleep(0.05)
     barrier()

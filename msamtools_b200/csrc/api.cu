@@ -491,10 +491,14 @@ int launch_decode(msg_ctx *c, const uint8_t *d_raw, uint64_t nbytes, uint64_t re
     // L2 fill granularity of the window loads: 64-byte granules (.L2::64B) or whole 128-byte lines.  MSG_L2_GRANULE=64|128 overrides.
     static const int g_env = getenv("MSG_L2_GRANULE") ? atoi(getenv("MSG_L2_GRANULE")) : 0;
     const bool g64 = g_env ? g_env == 64 : true;
-    // staging: LDGSTS (cp.async) for chunks in device memory, register-staged loads for chunks decoded in place from pinned host
-    // memory.  MSG_STAGING=async|ldg overrides (A/B runs).
+    // staging: register-staged 16-byte loads + STS.128 by default.  LDGSTS (cp.async) measured the same on device-resident
+    // chunks of a single GPU (0.4172 vs 0.4190 ms), HALF the rate on chunks decoded in place from pinned host memory, and every
+    // 8-rank run that used it had about half of the ranks -- a different set each time -- running each decode launch in 0.689 ms
+    // instead of 0.420 ms while all their other kernels kept their times (profiles/r02/scale8/README.md); round 1's 8-rank runs,
+    // which staged through registers, did not.  MSG_STAGING=async selects LDGSTS.
     static const char *st_env = getenv("MSG_STAGING");
-    const bool async = st_env ? st_env[0] == 'a' : !host_mapped;
+    const bool async = st_env ? st_env[0] == 'a' : false;
+    (void)host_mapped;
     const dim3 grid(nblocks(n, DEC_R)), block(DEC_R);
 #define DEC_LAUNCH(L, G, A) decode_kernel<L, G, A><<<grid, block, 0, c->stream>>>(p)
     if (c->lay_lpr == 8) { if (g64) { if (async) DEC_LAUNCH(8, true, true); else DEC_LAUNCH(8, true, false); } else { if (async) DEC_LAUNCH(8, false, true); else DEC_LAUNCH(8, false, false); } }

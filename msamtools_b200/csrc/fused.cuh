@@ -185,12 +185,14 @@ __global__ void __launch_bounds__(128) fused_walk_kernel(const FusedParams p)
 #pragma unroll
       for (int k = 0; k < FUSED_DR; k++) dr[k] = 0xffffffffu;
       // k-th distinct feature: registers first, local-memory list beyond FUSED_DR
+#pragma nv_diag_suppress 549      // df[k] is only read for k >= FUSED_DR, which add_feature has written by then
       auto feat_at = [&](uint32_t k) -> int32_t {
           int32_t v = k >= FUSED_DR ? df[k] : 0;
 #pragma unroll
           for (int j = 0; j < FUSED_DR; j++) if ((uint32_t)j == k) v = (int32_t)dr[j];
           return v;
       };
+#pragma nv_diag_default 549
       if (q < nw) do {
         i = p.worklist[q];
         // The walk is latency bound (one thread per pool, dependent loads), so the first FUSED_PF records' columns are
