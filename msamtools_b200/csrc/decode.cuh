@@ -774,7 +774,7 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr,
 // (cp.async.cg, 16 bytes, no register round trip, `.L2::64B` fill granularity): LPR lanes per record, slots are
 // 16-byte aligned with one pad chunk (stride LPR*16 + 16 bytes).
 template <int LPR, bool G64, bool ASYNC>
-__global__ void __launch_bounds__(DEC_R, 10) decode_kernel(const __grid_constant__ DecodeParams p)
+__global__ void __launch_bounds__(DEC_R, ASYNC ? 10 : 9) decode_kernel(const __grid_constant__ DecodeParams p)
 {
     constexpr int SLOT_WORDS = LPR * 4 + 4;
     __shared__ __align__(16) uint32_t s_slot[DEC_R * SLOT_WORDS + 4];
