@@ -308,8 +308,10 @@ def ref_sample(cfg, args, plan, cores):
     """host-side sample of the workload for the CPU arm: chunk 0 of rank 0, `pipes x per` records"""
     procs = 2 if cfg["ref_second"] is not None else 1
     pipes = args.cpu_threads // procs if args.cpu_threads else max(1, min(cores // procs, 16))
-    per = args.cpu_sample // pipes if args.cpu_sample else 1_000_000
-    raw, off = gen_chunk(cfg, 0, 0, plan, n_records=min(plan[1], pipes * per + 1000))
+    # per pipe: enough records that the reference's per-process fixed cost (parsing a 1 M-line header, writing a 1 M-row table:
+    # about a second at config 5) does not dominate its rate
+    per = args.cpu_sample // pipes if args.cpu_sample else 2_000_000
+    raw, off = gen_chunk(cfg, 0, 0, plan, n_records=pipes * per + 1000)      # the same generator stream as rank 0's chunk 0, continued
     return raw, off, pipes, per
 
 
