@@ -792,9 +792,9 @@ int msg_create(const msg_config *cfg, msg_ctx **out)
     if (g.debug_force_slow) mode |= DM_FORCE_SLOW;
     ctx->decode_mode = mode;
 
-    CUC(cudaMalloc(&ctx->d_err, 8)); CUC(cudaMalloc(&ctx->d_acct, 16)); CUC(cudaMalloc(&ctx->d_total, 16));
+    CUC(cudaMalloc(&ctx->d_err, 8)); CUC(cudaMalloc(&ctx->d_acct, ACCT_SLOTS * 128)); CUC(cudaMalloc(&ctx->d_total, 16));
     CUC(cudaHostAlloc((void **)&ctx->h_pin, 512, cudaHostAllocPortable)); memset(ctx->h_pin, 0, 512);
-    CUC(cudaMemset(ctx->d_acct, 0, 16));
+    CUC(cudaMemset(ctx->d_acct, 0, ACCT_SLOTS * 128));
     CUC(cudaMalloc(&ctx->d_wl, 8));
     const size_t T = (size_t)(g.n_targets > 0 ? g.n_targets : 1), F = (size_t)(g.n_features > 0 ? g.n_features : 1);
     if (cfg->fmap) {
@@ -1390,8 +1390,9 @@ int msg_get_timing(msg_ctx *c, msg_timing *t, int reset)
     { int wrc = wait_all(c); if (wrc) return wrc; }
     CU(cudaStreamSynchronize(c->stream));
     harvest_events(c);
-    unsigned long long acct[2];
-    CU(cudaMemcpy(acct, c->d_acct, 16, cudaMemcpyDeviceToHost));
+    unsigned long long acct[2] = {0, 0}, slots[ACCT_SLOTS * 16];
+    CU(cudaMemcpy(slots, c->d_acct, sizeof slots, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < ACCT_SLOTS; k++) { acct[0] += slots[k * 16]; acct[1] += slots[k * 16 + 1]; }
     t->decode_ms = c->decode_ms; t->decode_launches = c->decode_launches; t->total_ms = c->total_ms;
     t->kernel_launches = c->kernel_launches; t->h2d_bytes = c->h2d_bytes; t->d2h_bytes = c->d2h_bytes;
     t->alg_bytes = acct[0]; t->slow_records = acct[1];
@@ -1399,7 +1400,7 @@ int msg_get_timing(msg_ctx *c, msg_timing *t, int reset)
     if (reset) {
         c->decode_ms = c->total_ms = 0; c->decode_launches = c->kernel_launches = 0; c->h2d_bytes = c->d2h_bytes = 0;
         c->fused_chunks = c->fused_fallbacks = 0; c->zc_chunks = 0;
-        CU(cudaMemset(c->d_acct, 0, 16));
+        CU(cudaMemset(c->d_acct, 0, ACCT_SLOTS * 128));
     }
     return MSG_OK;
 }

@@ -26,6 +26,7 @@
 
 namespace msg {
 
+constexpr int ACCT_SLOTS = 64;                         // accounting counters are spread over this many 128-byte slots
 constexpr int DEC_R = 128;                              // records == threads per CTA (64 measured 4 % slower; 256 exceeds static smem at LPR=16)
 
 struct DecodeParams {
@@ -54,7 +55,7 @@ struct DecodeParams {
     uint32_t head_chunks, tail_chunks;   // window split, head_chunks + tail_chunks <= LPR
     // accounting
     uint32_t *err;                  // [0] flags, [1] first offending record (atomicMin)
-    unsigned long long *acct;       // [0] algorithmic bytes, [1] slow records
+    unsigned long long *acct;       // ACCT_SLOTS slots of 128 bytes: [0] algorithmic bytes, [1] slow records (summed by the host)
 };
 
 // ---------------------------------------------------------------- accessors
@@ -847,8 +848,11 @@ __global__ void __launch_bounds__(DEC_R, ASYNC ? 10 : 9) decode_kernel(const __g
     alg = __reduce_add_sync(0xffffffffu, alg);         // REDUX: one instruction per warp
     nslow = __reduce_add_sync(0xffffffffu, nslow);
     if ((t & 31u) == 0) {
-        if (alg) atomicAdd(p.acct, (unsigned long long)alg);
-        if (nslow) atomicAdd(p.acct + 1, (unsigned long long)nslow);
+        // 300 k warps per launch would otherwise add to ONE address (0.7 G same-address atomics/s, not far from what an L2 slice
+        // does): 64 slots, 128 bytes apart, picked by CTA
+        unsigned long long *slot = p.acct + (size_t)(blockIdx.x & (ACCT_SLOTS - 1)) * 16;
+        if (alg) atomicAdd(slot, (unsigned long long)alg);
+        if (nslow) atomicAdd(slot + 1, (unsigned long long)nslow);
     }
 }
 
