@@ -196,6 +196,19 @@ def have_ref_binary():
     return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
 
 
+def scratch_dir(prefix, need_bytes):
+    """tmpfs if it has room for the shards (so that the CPU arm does not wait for a disk), else the default temp dir"""
+    import shutil
+    import tempfile
+    for base in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if os.path.isdir(base) and shutil.disk_usage(base).free > need_bytes * 1.25 + (1 << 28):
+                return tempfile.mkdtemp(prefix=prefix, dir=base)
+        except OSError:
+            pass
+    return tempfile.mkdtemp(prefix=prefix)
+
+
 def bam_header_blob(names, tlen):
     import struct
     text = ("@HD\tVN:1.6\tSO:queryname\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (n, int(l)) for n, l in zip(names, tlen))).encode()
@@ -227,13 +240,11 @@ class RefPipelines:
     tmpfs as level-0 BGZF BAM so that inflate cost is negligible."""
 
     def __init__(self, cfg, raw, off, tlen, n_pipes, per_pipe):
-        import tempfile
         import msamtools_b200 as m
-        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
         self.cfg = cfg
-        self.dir = tempfile.mkdtemp(prefix="msb200_ref_", dir=base)
         hdr = bam_header_blob([f"g{i:07d}" for i in range(len(tlen))], tlen)
         n = len(off) - 1
+        self.dir = scratch_dir("msb200_ref_", int(off[min(n, n_pipes * per_pipe)]) + n_pipes * (len(hdr) + (64 << 20)))
         self.paths, self.n = [], 0
         a = 0
         for k in range(n_pipes):
@@ -419,8 +430,7 @@ def ingest_entry(cfg, plan, tlen, raw, off):
     if not os.path.exists(cli):
         return {"unavailable": "msamtools_b200/bin/msamtools not built"}
     n = len(off) - 1
-    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
-    d = tempfile.mkdtemp(prefix="msb200_ingest_", dir=base)
+    d = scratch_dir("msb200_ingest_", int(raw.nbytes))
     path = os.path.join(d, "in.bam")
     cores = os.cpu_count() or 1
     payload = write_bgzf_threads(path, [bam_header_blob([f"g{i:07d}" for i in range(len(tlen))], tlen), raw], level=1, threads=min(cores, 16))

@@ -73,3 +73,120 @@ def test_two_rank_sharding_matches_whole(tmp_path, oracle, share_type):
     # no QNAME group straddles the cut
     o0, o1 = int(off[cuts[1] - 1]), int(off[cuts[1]])
     assert bytes(raw[o0 + 36:o0 + 36 + int(raw[o0 + 12])]) != bytes(raw[o1 + 36:o1 + 36 + int(raw[o1 + 12])])
+
+
+# ---------------------------------------------------------------- PropSharing across ranks: the reduce-scatter / all-gather algebra
+def _multimapper_lists(raw, off, idx):
+    """(doubled unique counts, multi-mapper feature lists) of one shard's kept stream, restated in Python from
+    msam_profile.c:204-243 (grouping on tid != -1, QNAME vs the last counted record) and :65-200 (distinct features in
+    first-appearance order; one feature -> +2, several -> a list in proportional mode)"""
+    ui, lists = {}, []
+    prev, group = None, []
+
+    def close():
+        if not group:
+            return
+        d = list(dict.fromkeys(group))
+        if len(d) == 1:
+            ui[d[0]] = ui.get(d[0], 0) + 2
+        else:
+            lists.append(d)
+
+    for i in idx:
+        o = int(off[i])
+        tid = int(np.frombuffer(raw[o + 4:o + 8].tobytes(), dtype="<i4")[0])
+        if tid == -1:
+            continue
+        lq = int(raw[o + 12])
+        name = bytes(raw[o + 36:o + 36 + lq])
+        if name != prev:
+            close()
+            group = []
+            prev = name
+        group.append(tid)
+    close()
+    return ui, lists
+
+
+def _rsag_worker(rank, world, port, out_dir):
+    """what em_loop_rsag_kernel does, with gloo standing in for the peer-memory stores: every rank owns a slice of the feature
+    axis; partial increments are added IN RANK ORDER by the owner, which applies a = U + inc, the 1e-20 flush and its share
+    of sum (a_new - a_old)^2 (msam_profile.c:369-380); slices and delta shares are then gathered by everyone"""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from msamtools_b200 import synth, shard
+    from oracle import oracle as orc
+    p = synth.make_params("mixed", n_records=30_000, seed=4321)
+    raw, off, _ = synth.generate(p)
+    F = len(synth.target_lengths(p))
+    cuts = shard.shard_bounds(raw, off, world)
+    sraw, soff = shard.shard_view(raw, off, cuts, rank)
+    idx = orc.filter_stream(sraw, soff, orc.filter_cfg(l=80, p=95, z=80, besthit=True))
+    ui, lists = _multimapper_lists(sraw, soff, idx)
+    S = (F + world - 1) // world                                   # slice length (the kernel rounds it up to whole blocks)
+    lo, hi = rank * S, min(F, (rank + 1) * S)
+
+    def exchange(vec, first, U_slice, a_old_slice):
+        parts = [torch.zeros(F, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(vec))             # "every rank stores its partial slice into the owner's region"
+        tot = np.zeros(hi - lo)
+        for r in range(world):                                     # rank order: the same sum on every owner, every run
+            tot = tot + parts[r].numpy()[lo:hi]
+        if first:
+            new, share = tot / 2, 0.0                              # :286
+        else:
+            new = U_slice + tot
+            new[new < 1e-20] = 0.0                                 # :372-376
+            share = float(np.sum((new - a_old_slice) ** 2))        # :377-379
+        pad = np.zeros(S); pad[:hi - lo] = new
+        slices = [torch.zeros(S, dtype=torch.float64) for _ in range(world)]
+        shares = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(slices, torch.from_numpy(pad))            # all-gather of the new abundances
+        dist.all_gather(shares, torch.tensor([share], dtype=torch.float64))
+        a = np.concatenate([s.numpy() for s in slices])[:F]
+        delta = 0.0
+        for r in range(world):                                     # same order everywhere -> same stop decision everywhere
+            delta += float(shares[r][0])
+        return a, new, delta / F
+
+    counts = np.zeros(F)
+    for f, v in ui.items():
+        counts[f] = v
+    a, U_slice, _ = exchange(counts, True, None, None)
+    iters, conv = 0, 0
+    for k in range(1, 20):                                         # :331
+        inc = np.zeros(F)
+        for d in lists:                                            # :341-365
+            s = 0.0
+            for f in d:
+                s += a[f]
+            if s > 0:
+                for f in d:
+                    inc[f] += a[f] / s
+        a, _, delta = exchange(inc, False, U_slice, a[lo:hi].copy())
+        iters = k
+        if delta < 1e-10:                                          # :383
+            conv = 1
+            break
+    purged = torch.tensor([sum(1 for d in lists if sum(a[f] for f in d) == 0)], dtype=torch.int64)
+    nl = torch.tensor([len(lists)], dtype=torch.int64)
+    dist.all_reduce(purged); dist.all_reduce(nl)
+    np.savez(os.path.join(out_dir, f"e{rank}.npz"), a=a, st=np.array([iters, conv, int(purged[0]), int(nl[0])]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_rsag_propsharing_matches_whole(tmp_path, oracle):
+    port = 29650 + os.getpid() % 200
+    mp.spawn(_rsag_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    from msamtools_b200 import synth
+    p = synth.make_params("mixed", n_records=30_000, seed=4321)
+    raw, off, _ = synth.generate(p)
+    F = len(synth.target_lengths(p))
+    idx = oracle.filter_stream(raw, off, oracle.filter_cfg(l=80, p=95, z=80, besthit=True))
+    ab, st, _, _ = oracle.profile(raw, off, idx, F, 3)
+    r = [np.load(tmp_path / f"e{k}.npz") for k in range(2)]
+    assert np.array_equal(r[0]["a"], r[1]["a"])                    # bit-identical on both ranks
+    assert r[0]["st"].tolist() == r[1]["st"].tolist() == [st["iterations"], st["converged"], st["purged"], st["n_lists"]]
+    assert st["iterations"] >= 3 and st["n_lists"] > 100
+    assert np.all(np.abs(r[0]["a"] - ab) <= 1e-9 * np.maximum(np.abs(ab), np.abs(r[0]["a"])))
