@@ -326,6 +326,15 @@ def ref_sample(cfg, args, plan, cores):
     return raw, off, pipes, per
 
 
+def cuda_library_mapped():
+    """whether THIS process has the product's CUDA library mapped (the reference arm must not need it)"""
+    try:
+        with open("/proc/self/maps") as f:
+            return "libmsamtools_b200" in f.read()
+    except OSError:
+        return None
+
+
 def config_json(cfg, key, plan, records, n_refs):
     """identical in both arms (the driver compares them): only what defines the workload, nothing measured"""
     return {"workload": cfg["workload"], "config_index": key, "preset": cfg["preset"], "records_per_gpu_per_step": int(records),
@@ -366,7 +375,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": config_json(cfg, args.config, plan, records, len(tlen)),
             "cpu_baseline": {"value": v, "unit": "M alignments/s", "cores": used, "kind": kind, "host_cores_available": cores, "sample": sample},
-            "e2e": {"value": v, "unit": "M alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "M alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cuda_library_mapped": cuda_library_mapped()}
     print(json.dumps(line))
 
 
