@@ -29,8 +29,10 @@
 
 #include "../../../include/msamtools_b200.h"
 #include "../host/bamio.h"
+#include "../host/gzpar.h"
 #include "../host/keyorder.h"
 #include "../host/margs.h"
+#include "../host/recwalk.h"
 
 #define PROGRAM "msamtools"
 #define PACKAGE_VERSION "1.1.3-b200"
@@ -54,6 +56,26 @@ static void mDie(const char *fmt, ...)
     va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
     fprintf(stderr, "\n");
     exit(EXIT_FAILURE);
+}
+
+/* MSAMTOOLS_TIMING=1: wall time of each host phase on stderr ("# phase <command> <name>: <seconds>") */
+static void phase(const char *cmd, const char *name)
+{
+    static int on = -1; static struct timespec t0;
+    struct timespec t;
+    if (on < 0) { on = getenv("MSAMTOOLS_TIMING") != NULL; clock_gettime(CLOCK_MONOTONIC, &t0); }
+    if (!on) return;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    if (name) fprintf(stderr, "# phase %s %s: %.3f s\n", cmd, name, (t.tv_sec - t0.tv_sec) + 1e-9 * (t.tv_nsec - t0.tv_nsec));
+    t0 = t;
+}
+
+/* worker threads for inflate / deflate / formatting: MSAMTOOLS_THREADS, default the online cores, at most 16 */
+static int host_threads(void)
+{
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    if (getenv("MSAMTOOLS_THREADS")) n = atol(getenv("MSAMTOOLS_THREADS"));
+    return n > 16 ? 16 : (n < 1 ? 1 : (int)n);
 }
 
 static void print_help(const char *sub, void **argtable)
@@ -118,23 +140,20 @@ static void chunk_fill(chunk_t *c, bio_file *in, const bio_hdr *h, size_t want_r
     c->off[c->n] = c->len;
 }
 
+static double g_walk_sec;
 /* bulk (BAM): inflate straight into the fixed-capacity buffer, then walk the block_size chain over the new bytes */
-static void chunk_fill_bulk(chunk_t *c, bio_file *in, size_t want_records, size_t want_bytes, int *eof)
+static void chunk_fill_bulk(chunk_t *c, bio_file *in, int32_t n_targets, size_t want_records, size_t want_bytes, int *eof)
 {
     if (want_bytes > c->cap) want_bytes = c->cap;
     while (!*eof && c->n < want_records && c->len < want_bytes) {
         int rc = bio_read_raw(in, c->raw, c->cap, &c->len);
         if (rc < 0) input_die(in);
         if (rc == 0) { *eof = 1; break; }
-        size_t o = (size_t)c->off[c->n];
-        while (o + 4 <= c->len) {
-            uint32_t bs = (uint32_t)c->raw[o] | (uint32_t)c->raw[o + 1] << 8 | (uint32_t)c->raw[o + 2] << 16 | (uint32_t)c->raw[o + 3] << 24;
-            if (bs < 32 || bs > 0x7fffffffu) mDie("Cannot read input: corrupt BAM record");
-            if (o + 4 + (size_t)bs > c->len) break;
-            o += 4 + (size_t)bs;
-            chunk_reserve_off(c, c->n + 1);
-            c->off[++c->n] = o;
-        }
+        struct timespec w0, w1; clock_gettime(CLOCK_MONOTONIC, &w0);
+        const int wrc = rw_index(c->raw, (size_t)c->off[c->n], c->len, n_targets, host_threads(), &c->off, &c->n, &c->offcap);
+        if (wrc == -1) mDie("Cannot read input: corrupt BAM record");
+        if (wrc) mDie("Out of memory");
+        clock_gettime(CLOCK_MONOTONIC, &w1); g_walk_sec += (w1.tv_sec - w0.tv_sec) + 1e-9 * (w1.tv_nsec - w0.tv_nsec);
         if (rc == 2) break;                                  /* buffer full */
     }
     if (*eof && (size_t)c->off[c->n] != c->len) mDie("Cannot read input: truncated BAM record");
@@ -284,7 +303,7 @@ static void *reader_main(void *arg)
         size_t want_n = CHUNK_RECORDS, want_b = CHUNK_BYTES;
         size_t k;
         for (;;) {
-            if (g->bulk) chunk_fill_bulk(c, r->in, want_n, want_b, &r->eof);
+            if (g->bulk) chunk_fill_bulk(c, r->in, r->hdr->n_targets, want_n, want_b, &r->eof);
             else chunk_fill(c, r->in, r->hdr, want_n, want_b, &r->eof);
             k = choose_cut(c, r->eof);
             if (k || r->eof) break;
@@ -436,6 +455,7 @@ static msg_ctx *run_stream(run_t *r)
         uint64_t ib = 0; double isec = 0; msg_timing tm;
         bio_ingest_stats(r->in, &ib, &isec);
         msg_get_timing(ctx, &tm, 0);
+        fprintf(stderr, "# timing: index walk %.3f s\n", g_walk_sec);
         fprintf(stderr, "# timing: host ingest %.3f GB in %.3f s (%.2f GB/s, read+inflate); push loop %.3f s (H2D %.3f GB, GPU kernels %.1f ms); %llu records\n",
                 ib / 1e9, isec, isec > 0 ? ib / 1e9 / isec : 0.0, t_push, tm.h2d_bytes / 1e9, tm.total_ms, (unsigned long long)n_pushed);
     }
@@ -447,11 +467,7 @@ static void open_input(run_t *r, const char *infile)
     r->path = infile;
     r->in = bio_open_read(infile);
     if (!r->in) mDie("Cannot open %s for reading", infile);
-    {   /* BGZF blocks are inflated on worker threads (MSAMTOOLS_THREADS, default: online cores, at most 16) */
-        long n = sysconf(_SC_NPROCESSORS_ONLN);
-        if (getenv("MSAMTOOLS_THREADS")) n = atol(getenv("MSAMTOOLS_THREADS"));
-        bio_set_threads(r->in, n > 16 ? 16 : (int)n);
-    }
+    bio_set_threads(r->in, host_threads());      /* BGZF blocks are inflated on worker threads */
     r->hdr = bio_read_header(r->in);
     if (!r->hdr) { if (bio_error(r->in)[0]) mDie("Cannot read header from %s: %s", infile, bio_error(r->in)); mDie("Cannot read header from %s", infile); }
 }
@@ -518,7 +534,9 @@ static int filter_main(int argc, char *argv[])
     if (a_u->count > 0) strcat(outmode, "bu"); else if (a_b->count > 0) strcat(outmode, "b"); else if (a_h->count > 0) strcat(outmode, "h");
 
     run_t r; memset(&r, 0, sizeof r);
+    phase(sub, NULL);
     open_input(&r, a_file->filename[0]);
+    phase(sub, "open + header");
     const int hit = a_uniq->count > 0 ? MSG_HIT_UNIQUE : a_best->count > 0 ? MSG_HIT_BEST : MSG_HIT_NONE;
     qn_result qn = { QN_NOT_REQUIRED, 0, 0, 0 };
     if (hit) {
@@ -537,12 +555,9 @@ static int filter_main(int argc, char *argv[])
     }
     r.out = bio_open_write("-", outmode);
     if (!r.out) mDie("Cannot open - for writing");
-    {
-        long n = sysconf(_SC_NPROCESSORS_ONLN);
-        if (getenv("MSAMTOOLS_THREADS")) n = atol(getenv("MSAMTOOLS_THREADS"));
-        bio_set_threads(r.out, n > 16 ? 16 : (int)n);
-    }
+    bio_set_threads(r.out, host_threads());
     if (bio_write_header(r.out, r.out_hdr) < 0) mDie("Cannot write SAM header");
+    phase(sub, "pre-flight + output header");
 
     /* mFilterFileWrapper, msam_filter.c:79-84 */
     if (!(MIN_LENGTH > 0) && PPT == 0 && !(MAX_CLIP < 100) && !hit)
@@ -554,32 +569,77 @@ static int filter_main(int argc, char *argv[])
     r.cfg.want_records = 1;
     r.cfg.n_targets = r.hdr->n_targets; r.cfg.n_features = r.hdr->n_targets;
     msg_ctx *ctx = run_stream(&r);
+    phase(sub, "stream");
     msg_destroy(ctx);
     bio_close(r.in);
     if (bio_close(r.out)) mDie("Cannot write output");
+    phase(sub, "close");
     return 0;
 }
 
 /* ============================================================ profile */
-static void print_insert_stats(gzFile s, int left, const char *type, int number, int total, const char *post)
+static void print_insert_stats(gzp *s, int left, const char *type, int number, int total, const char *post)
 {   /* mPrintInsertStats, msam_profile.c:434-470 */
     int width = 7;
     if (total > 0) width = 1 + log10(total);
-    gzprintf(s, "# ");
-    if (left) gzprintf(s, "%-20s: ", type); else gzprintf(s, "%20s: ", type);
-    if (strcmp(type, "Total inserts") == 0 && number == -1) gzprintf(s, "%*s (", width, "NA"); else gzprintf(s, "%*d (", width, number);
-    if (total > 0) gzprintf(s, "%6.2f", 100.0 * number / total); else gzprintf(s, "%6s", "NA");
-    gzprintf(s, "%%)");
-    if (post) gzprintf(s, " %s\n", post); else gzprintf(s, "\n");
+    gzp_printf(s, "# ");
+    if (left) gzp_printf(s, "%-20s: ", type); else gzp_printf(s, "%20s: ", type);
+    if (strcmp(type, "Total inserts") == 0 && number == -1) gzp_printf(s, "%*s (", width, "NA"); else gzp_printf(s, "%*d (", width, number);
+    if (total > 0) gzp_printf(s, "%6.2f", 100.0 * number / total); else gzp_printf(s, "%6s", "NA");
+    gzp_printf(s, "%%)");
+    if (post) gzp_printf(s, " %s\n", post); else gzp_printf(s, "\n");
 }
-static void print_insert_stats_double(gzFile s, const char *type, double number, int total, const char *post)
+static void print_insert_stats_double(gzp *s, const char *type, double number, int total, const char *post)
 {   /* mPrintInsertStatsDouble, msam_profile.c:472-499 (always left aligned by its callers) */
-    gzprintf(s, "# ");
-    gzprintf(s, "%-20s: ", type);
-    gzprintf(s, "%10.7g (", number);
-    if (total > 0) gzprintf(s, "%6.2f", 100.0 * number / total); else gzprintf(s, "%6s", "NA");
-    gzprintf(s, "%%)");
-    if (post) gzprintf(s, " %s\n", post); else gzprintf(s, "\n");
+    gzp_printf(s, "# ");
+    gzp_printf(s, "%-20s: ", type);
+    gzp_printf(s, "%10.7g (", number);
+    if (total > 0) gzp_printf(s, "%6.2f", 100.0 * number / total); else gzp_printf(s, "%6s", "NA");
+    gzp_printf(s, "%%)");
+    if (post) gzp_printf(s, " %s\n", post); else gzp_printf(s, "\n");
+}
+
+/* the "<name>\t%.8g\n" rows of mWriteMatrixTransposedGzip (mMatrix.c:359-376): row ranges are formatted on worker threads
+ * (same printf conversion, so the same text), then handed to the gzip writer in order */
+typedef struct { char **name; const double *v; size_t a, b; char *buf; size_t len; int err; } row_job;
+static void *row_worker(void *arg)
+{
+    row_job *j = arg;
+    size_t cap = 1;
+    for (size_t i = j->a; i < j->b; i++) cap += strlen(j->name[i]) + 40;
+    char *d = j->buf = malloc(cap);
+    if (!d) { j->err = 1; return NULL; }
+    for (size_t i = j->a; i < j->b; i++) {
+        const size_t l = strlen(j->name[i]);
+        memcpy(d, j->name[i], l); d += l; *d++ = '\t';
+        const double x = j->v[i];
+        if (x == 0.0 && !signbit(x)) *d++ = '0';             /* what %.8g prints for +0 */
+        else d += snprintf(d, 38, "%.8g", x);
+        *d++ = '\n';
+    }
+    j->len = (size_t)(d - j->buf);
+    return NULL;
+}
+static void write_rows(gzp *out, char **name, const double *v, size_t n, int threads)
+{
+    enum { SLAB = 1 << 16 };                                  /* rows per job: bounds the text held in memory */
+    for (size_t base = 0; base < n;) {
+        int t = threads;
+        if ((size_t)t * SLAB > n - base) t = (int)((n - base + SLAB - 1) / SLAB);
+        pthread_t th[16]; row_job job[16];
+        for (int i = 0; i < t; i++) {
+            size_t a = base + (size_t)i * SLAB, b = a + SLAB > n ? n : a + SLAB;
+            job[i] = (row_job){ name, v, a, b, NULL, 0, 0 };
+            if (i && pthread_create(&th[i], NULL, row_worker, &job[i])) job[i].err = 2;
+        }
+        row_worker(&job[0]);
+        for (int i = 1; i < t; i++) { if (job[i].err == 2) { job[i].err = 0; row_worker(&job[i]); } else pthread_join(th[i], NULL); }
+        for (int i = 0; i < t; i++) {
+            if (job[i].err || gzp_write(out, job[i].buf, job[i].len)) mDie("Cannot write the profile");
+            free(job[i].buf);
+        }
+        base += (size_t)t * SLAB;
+    }
 }
 
 static int profile_main(int argc, char *argv[])
@@ -621,7 +681,9 @@ static int profile_main(int argc, char *argv[])
     if (a_mincount->count > 0 && a_mincount->ival[0] < 0) USAGE_FAIL("--mincount must be a non-negative integer");
 
     run_t r; memset(&r, 0, sizeof r);
+    phase(sub, NULL);
     open_input(&r, a_file->filename[0]);
+    phase(sub, "open + header");
     chunk_fill(&r.chunk, r.in, r.hdr, COORD_ORDER_CHECK_RECORDS, (size_t)-1, &r.eof);
     qn_result qn = qname_preflight(r.hdr, &r.chunk);
 
@@ -682,11 +744,14 @@ static int profile_main(int argc, char *argv[])
 
     r.cfg.do_filter = 0; r.cfg.want_profile = 1; r.cfg.share_type = (uint8_t)share_type;
     r.cfg.n_targets = n_targets; r.cfg.n_features = n_features; r.cfg.fmap = fmap;
+    phase(sub, "pre-flight + feature map");
     msg_ctx *ctx = run_stream(&r);
+    phase(sub, "stream");
     double *ab = calloc((size_t)n_features + 1, sizeof(double));      /* ab[0] = Unknown, ab[1..] features */
     msg_profile_stats st;
     if (msg_finish_profile(ctx, ab + 1, &st)) gpu_die(ctx);
     msg_destroy(ctx);
+    phase(sub, "finish");
     if (share_type == MSG_MULTI_PROPORTIONAL) {                        /* stderr side channel, msam_profile.c:330,381-390,405 */
         fprintf(stderr, "# Start PropSharing:\n");
         for (int k = 1; k <= st.em_iterations; k++) {
@@ -707,15 +772,15 @@ static int profile_main(int argc, char *argv[])
         fprintf(stderr, "# Ignoring 'unknown' fraction, as total inserts (%d) < mapped inserts (%d)!\n", total_inserts, mapped_inserts);
         total_inserts = -1;
     }
-    gzFile out = strcmp(a_out->sval[0], "-") == 0 ? gzdopen(fileno(stdout), "wb") : gzopen(a_out->sval[0], "wb");
+    gzp *out = gzp_open(a_out->sval[0], host_threads());
     if (!out) mDie("Cannot open %s for writing", a_out->sval[0]);
     {   /* mPrintProfileProvenanceGzip */
         char *cl = command_line(argc, argv), qmsg[1024];
         qn_format(&qn, qmsg, sizeof qmsg);
-        gzprintf(out, "# msamtools version: %s\n", PACKAGE_VERSION);
-        gzprintf(out, "# msamtools git commit: %s\n", MSAM_GIT_COMMIT);
-        gzprintf(out, "# Command line: %s\n", cl);
-        gzprintf(out, "# %s\n", qmsg);
+        gzp_printf(out, "# msamtools version: %s\n", PACKAGE_VERSION);
+        gzp_printf(out, "# msamtools git commit: %s\n", MSAM_GIT_COMMIT);
+        gzp_printf(out, "# Command line: %s\n", cl);
+        gzp_printf(out, "# %s\n", qmsg);
         free(cl);
     }
     double purged_inserts = st.purged_insert_count + purged_eq;
@@ -727,7 +792,7 @@ static int profile_main(int argc, char *argv[])
     print_insert_stats(out, 0, "- Uniquely mapped ", (int)st.uniq_mapper_count, total_inserts, NULL);
     print_insert_stats_double(out, "Purged inserts", purged_inserts, total_inserts, "due to ambiguous mapping or low abundance features");
     print_insert_stats_double(out, "Effective inserts", effective, total_inserts, NULL);
-    if (total_inserts <= 0) gzprintf(out, "# Estimated seq. length for 'Unknown': NA\n");
+    if (total_inserts <= 0) gzp_printf(out, "# Estimated seq. length for 'Unknown': NA\n");
     if (total_inserts > 0) {                                           /* msam_profile.c:906-934 */
         ab[0] = total_inserts - mapped_inserts + purged_inserts;
         if (share_type == MSG_MULTI_IGNORE) ab[0] += st.multi_mapper_count;
@@ -735,9 +800,9 @@ static int profile_main(int argc, char *argv[])
             int count = 0; uint64_t sum = 0;
             for (int i = 0; i < n_features; i++) { sum += feature_len[i]; count++; }
             uint32_t unknown_size = (uint32_t)(sum / (uint64_t)count);
-            gzprintf(out, "# Estimated seq. length for 'Unknown': %dbp\n", unknown_size);
+            gzp_printf(out, "# Estimated seq. length for 'Unknown': %dbp\n", unknown_size);
             ab[0] = 1.0 * ab[0] / unknown_size;
-        } else gzprintf(out, "# Estimated seq. length for 'Unknown': NA\n");
+        } else gzp_printf(out, "# Estimated seq. length for 'Unknown': NA\n");
     }
     if (length_normalize) for (int i = 0; i < n_features; i++) ab[i + 1] /= feature_len[i];
     if (unit_type == 2) {                                              /* fpkm */
@@ -749,16 +814,39 @@ static int profile_main(int argc, char *argv[])
         for (int i = 0; i <= n_features; i++) ab[i] /= sum;
         if (unit_type == 3) for (int i = 0; i <= n_features; i++) ab[i] *= 1.0E6;
     }
-    if (a_nopandas->count == 0) gzprintf(out, "ID\t");                 /* mWriteMatrixTransposedGzip, mMatrix.c:359-376 */
-    gzprintf(out, "%s\n", a_label->sval[0]);
-    gzprintf(out, "%s\t%.8g\n", "Unknown", ab[0]);
-    for (int i = 0; i < n_features; i++) gzprintf(out, "%s\t%.8g\n", feature_name[i], ab[i + 1]);
-    gzclose(out);
+    if (a_nopandas->count == 0) gzp_printf(out, "ID\t");                 /* mWriteMatrixTransposedGzip, mMatrix.c:359-376 */
+    gzp_printf(out, "%s\n", a_label->sval[0]);
+    gzp_printf(out, "%s\t%.8g\n", "Unknown", ab[0]);
+    write_rows(out, feature_name, ab + 1, (size_t)n_features, host_threads());
+    if (gzp_close(out)) mDie("Cannot write %s", a_out->sval[0]);
+    phase(sub, "table");
     bio_close(r.in);
     return 0;
 }
 
 /* ============================================================ coverage */
+/* the depth values of one sequence, `wordsize` per line (mWriteCoverageToStream, msam_coverage.c:160-185); depth == NULL: zeros */
+static void write_depths(gzp *out, const int32_t *depth, int64_t tlen, int wordsize)
+{
+    enum { STEP = 8192 };
+    if (tlen <= 0) { gzp_puts(out, "0\n"); return; }           /* the reference's loops print one value even then */
+    for (int64_t base = 0; base < tlen; base += STEP) {
+        const int64_t end = base + STEP < tlen ? base + STEP : tlen;
+        char *d = gzp_reserve(out, (size_t)STEP * 12), *d0 = d;
+        if (!d) mDie("Cannot write coverage");
+        for (int64_t i = base; i < end; i++) {
+            int32_t v = depth ? depth[i] : 0;
+            if (v < 0) { *d++ = '-'; }
+            uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+            char tmp[10]; int k = 0;
+            do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+            while (k) *d++ = tmp[--k];
+            *d++ = (i == tlen - 1 || (i + 1) % wordsize == 0) ? '\n' : ' ';
+        }
+        gzp_commit(out, (size_t)(d - d0));
+    }
+}
+
 static int coverage_main(int argc, char *argv[])
 {
     const char *sub = "coverage";
@@ -788,7 +876,7 @@ static int coverage_main(int argc, char *argv[])
     if (a_w->count > 0) { wordsize = a_w->ival[0]; if (wordsize < 1) USAGE_FAIL("-w must be a non-zero positive integer"); }
     if (a_out->count != 1) USAGE_FAIL("requires -o");
 
-    gzFile out = strcmp(a_out->sval[0], "-") == 0 ? gzdopen(fileno(stdout), "wb") : gzopen(a_out->sval[0], "wb");
+    gzp *out = gzp_open(a_out->sval[0], host_threads());
     if (!out) mDie("Cannot open %s for writing", a_out->sval[0]);
     run_t r; memset(&r, 0, sizeof r);
     open_input(&r, a_file->filename[0]);
@@ -802,8 +890,8 @@ static int coverage_main(int argc, char *argv[])
     if (a_summary->count > 0) {                                        /* mWriteCoverageSummaryToStream, msam_coverage.c:189-219 */
         for (int t = 0; t < T; t++) {
             int64_t tlen = r.hdr->target_len[t];
-            if (!covered[t]) { if (!skip) gzprintf(out, "%s\t%d\t%d\n", r.hdr->target_name[t], 0, 0); continue; }
-            gzprintf(out, "%s\t%.8f\t%.2f\n", r.hdr->target_name[t], 1.0 * touched[t] / tlen, 1.0 * sum[t] / tlen);
+            if (!covered[t]) { if (!skip) gzp_printf(out, "%s\t%d\t%d\n", r.hdr->target_name[t], 0, 0); continue; }
+            gzp_printf(out, "%s\t%.8f\t%.2f\n", r.hdr->target_name[t], 1.0 * touched[t] / tlen, 1.0 * sum[t] / tlen);
         }
     } else {                                                           /* mWriteCoverageToStream, msam_coverage.c:143-187 */
         int32_t *depth = NULL; size_t dcap = 0;
@@ -811,21 +899,19 @@ static int coverage_main(int argc, char *argv[])
             int64_t tlen = r.hdr->target_len[t];
             if (!covered[t]) {
                 if (!skip) {
-                    gzprintf(out, ">%s\n", r.hdr->target_name[t]);
-                    for (int64_t i = 0; i < tlen - 1; i++) gzputs(out, (i + 1) % wordsize == 0 ? "0\n" : "0 ");
-                    gzputs(out, "0\n");
+                    gzp_printf(out, ">%s\n", r.hdr->target_name[t]);
+                    write_depths(out, NULL, tlen, wordsize);
                 }
                 continue;
             }
             if ((size_t)tlen > dcap) { dcap = (size_t)tlen; depth = realloc(depth, dcap * sizeof(int32_t)); }
             if (msg_pull_coverage(ctx, t, depth)) gpu_die(ctx);
-            gzprintf(out, ">%s\n", r.hdr->target_name[t]);
-            for (int64_t i = 0; i < tlen - 1; i++) gzprintf(out, (i + 1) % wordsize == 0 ? "%d\n" : "%d ", depth[i]);
-            gzprintf(out, "%d\n", depth[tlen - 1]);
+            gzp_printf(out, ">%s\n", r.hdr->target_name[t]);
+            write_depths(out, depth, tlen, wordsize);
         }
         free(depth);
     }
-    gzclose(out);
+    if (gzp_close(out)) mDie("Cannot write %s", a_out->sval[0]);
     msg_destroy(ctx);
     bio_close(r.in);
     return 0;
