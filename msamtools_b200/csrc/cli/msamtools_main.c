@@ -42,15 +42,19 @@
 #define COORD_ORDER_CHECK_RECORDS 100000
 #define COORD_ORDER_MIN_RECORDS   10000
 
+static void warm_join(void);
 static void mQuit(const char *fmt, ...)
 {
-    va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
+    va_list ap;
+    warm_join();
+    va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
     fprintf(stderr, "\n");
     exit(EXIT_FAILURE);
 }
 static void mDie(const char *fmt, ...)
 {
     va_list ap;
+    warm_join();                            /* never exit() under a CUDA start-up still running on the warm-up thread */
     fflush(stdout);
     fprintf(stderr, "Fatal Error: ");
     va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
@@ -267,8 +271,8 @@ typedef struct {
 
 /* chunk size: records / bytes per push (MSAMTOOLS_CHUNK_RECORDS / MSAMTOOLS_CHUNK_MB override, for tests and tuning) */
 static size_t env_size(const char *name, size_t dflt, size_t unit) { const char *e = getenv(name); return e && atol(e) > 0 ? (size_t)atol(e) * unit : dflt; }
-#define CHUNK_RECORDS env_size("MSAMTOOLS_CHUNK_RECORDS", (size_t)4 << 20, 1)
-#define CHUNK_BYTES   env_size("MSAMTOOLS_CHUNK_MB", (size_t)1024 << 20, (size_t)1 << 20)
+#define CHUNK_RECORDS env_size("MSAMTOOLS_CHUNK_RECORDS", (size_t)1 << 20, 1)
+#define CHUNK_BYTES   env_size("MSAMTOOLS_CHUNK_MB", (size_t)256 << 20, (size_t)1 << 20)
 #define NBUF 3
 
 static void gpu_die(msg_ctx *ctx) { mDie("%s", msg_last_error(ctx)); }
@@ -282,7 +286,7 @@ typedef struct {
     chunk_t buf[NBUF];
     int state[NBUF];                      /* 0 free, 1 posted */
     int posted_last;                      /* the posted chunk with this index is the final one (-1: not yet known) */
-    int bulk;
+    int bulk, pin;
     pthread_mutex_t mu; pthread_cond_t cv;
 } ring_t;
 
@@ -293,6 +297,8 @@ static size_t choose_cut(chunk_t *c, int eof)
     size_t k = msg_split_point(c->raw, c->off, c->n, c->n - 1);
     return k;
 }
+
+static void ring_buffer_alloc(ring_t *g, int i, int pin);
 
 static void *reader_main(void *arg)
 {
@@ -327,6 +333,7 @@ static void *reader_main(void *arg)
             pthread_mutex_lock(&g->mu);
             while (g->state[nxt]) pthread_cond_wait(&g->cv, &g->mu);
             pthread_mutex_unlock(&g->mu);
+            ring_buffer_alloc(g, nxt, g->pin);
             chunk_t *d = &g->buf[nxt];
             const size_t base = (size_t)c->off[k], tail = c->len - base;
             if (!d->fixed && tail > d->cap) { d->raw = realloc(d->raw, tail + (1 << 20)); d->cap = tail + (1 << 20); if (!d->raw) mDie("Out of memory"); }
@@ -341,22 +348,101 @@ static void *reader_main(void *arg)
     }
 }
 
-static void write_kept_records(run_t *r, msg_ctx *ctx, uint8_t **outbuf, size_t *outcap)
+/* ---- record output (filter): a writer thread packs BGZF blocks / formats SAM and writes while the GPU thread is
+ * already on the next chunk.  Two output buffers; the order of chunks is the order of posts. */
+typedef struct {
+    run_t *r;
+    uint8_t *buf[2]; size_t cap[2], len[2];
+    int state[2];                         /* 0 free, 1 posted */
+    int done, failed;
+    double t_write;
+    pthread_mutex_t mu; pthread_cond_t cv;
+} wring_t;
+
+static int emit_records(run_t *r, const uint8_t *buf, size_t nb)
 {
-    size_t nb = 0, nr = 0;
-    if (msg_pull_records(ctx, NULL, 0, &nb, &nr)) gpu_die(ctx);
-    if (nb > *outcap) { *outcap = nb + nb / 4; *outbuf = realloc(*outbuf, *outcap); if (!*outbuf) mDie("Out of memory"); }
-    if (msg_pull_records(ctx, *outbuf, *outcap, &nb, &nr)) gpu_die(ctx);
-    if (bio_is_bam(r->out)) {                         /* the bytes already are BAM records: blocks are packed on the worker threads */
-        if (bio_write_raw(r->out, *outbuf, nb)) mDie("Cannot write alignment record");
-        return;
-    }
+    if (bio_is_bam(r->out)) return bio_write_raw(r->out, buf, nb);      /* the bytes already are BAM records: blocks are packed on the worker threads */
     for (size_t o = 0; o < nb;) {
-        const uint8_t *p = *outbuf + o;
+        const uint8_t *p = buf + o;
         uint32_t bs = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
-        if (bio_write_record(r->out, r->out_hdr, p, 4 + (size_t)bs)) mDie("Cannot write alignment record");
+        if (bio_write_record(r->out, r->out_hdr, p, 4 + (size_t)bs)) return -1;
         o += 4 + (size_t)bs;
     }
+    return 0;
+}
+
+static void *writer_main(void *arg)
+{
+    wring_t *w = arg;
+    struct timespec ta, tb;
+    for (int cur = 0;; cur ^= 1) {
+        pthread_mutex_lock(&w->mu);
+        while (!w->state[cur] && !w->done) pthread_cond_wait(&w->cv, &w->mu);
+        const int have = w->state[cur];
+        pthread_mutex_unlock(&w->mu);
+        if (!have) return NULL;
+        clock_gettime(CLOCK_MONOTONIC, &ta);
+        const int rc = emit_records(w->r, w->buf[cur], w->len[cur]);
+        clock_gettime(CLOCK_MONOTONIC, &tb);
+        w->t_write += (tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec);
+        pthread_mutex_lock(&w->mu);
+        if (rc) w->failed = 1;
+        w->state[cur] = 0;
+        pthread_cond_broadcast(&w->cv);
+        pthread_mutex_unlock(&w->mu);
+    }
+}
+
+/* kept records of the chunk just pushed -> output buffer `*wcur` (the writer thread takes it from there; w->r == NULL: no
+ * thread, written here) */
+static void pull_kept_records(run_t *r, msg_ctx *ctx, wring_t *w, int *wcur)
+{
+    size_t nb = 0, nr = 0;
+    const int i = *wcur;
+    if (msg_pull_records(ctx, NULL, 0, &nb, &nr)) gpu_die(ctx);
+    pthread_mutex_lock(&w->mu);
+    while (w->state[i]) pthread_cond_wait(&w->cv, &w->mu);
+    const int failed = w->failed;
+    pthread_mutex_unlock(&w->mu);
+    if (failed) mDie("Cannot write alignment record");
+    if (nb > w->cap[i]) { free(w->buf[i]); w->cap[i] = nb + nb / 4 + 4096; w->buf[i] = malloc(w->cap[i]); if (!w->buf[i]) mDie("Out of memory"); }
+    if (msg_pull_records(ctx, w->buf[i], w->cap[i], &nb, &nr)) gpu_die(ctx);
+    w->len[i] = nb;
+    if (!w->r) { if (emit_records(r, w->buf[i], nb)) mDie("Cannot write alignment record"); return; }
+    pthread_mutex_lock(&w->mu);
+    w->state[i] = 1;
+    pthread_cond_broadcast(&w->cv);
+    pthread_mutex_unlock(&w->mu);
+    *wcur ^= 1;
+}
+
+/* ---- CUDA start-up off the critical path: runtime + context creation (hundreds of ms) overlaps reading the header */
+static pthread_t g_warm_thread; static int g_warm_started;
+static void *warm_main(void *arg)
+{
+    void *p = NULL;
+    if (msg_host_alloc((int)(intptr_t)arg, 4096, &p) == MSG_OK) msg_host_free(p);
+    return NULL;
+}
+static void warm_start(void)
+{
+    int dev = getenv("MSAMTOOLS_DEVICE") ? atoi(getenv("MSAMTOOLS_DEVICE")) : 0;
+    if (getenv("MSAMTOOLS_NO_WARMUP")) return;
+    g_warm_started = pthread_create(&g_warm_thread, NULL, warm_main, (void *)(intptr_t)dev) == 0;
+}
+static void warm_join(void) { if (g_warm_started) { g_warm_started = 0; pthread_join(g_warm_thread, NULL); } }
+
+static void ring_buffer_alloc(ring_t *g, int i, int pin)
+{   /* BAM: fixed-capacity buffers the inflate workers write into directly; pinned (so that H2D copies run asynchronously
+       at full PCIe rate) once the input is large enough to pay for page-locking them */
+    chunk_t *c = &g->buf[i];
+    if (!g->bulk || c->raw) return;
+    c->fixed = 1; c->cap = CHUNK_BYTES + ((size_t)64 << 20);
+    void *pmem = NULL;
+    if (pin && msg_host_alloc(g->r->cfg.device, c->cap, &pmem) == MSG_OK) { c->raw = pmem; c->pinned = 1; }
+    else { c->raw = malloc(c->cap); if (!c->raw) mDie("Out of memory"); }
+    chunk_reserve_off(c, 1);
+    c->off[0] = 0;
 }
 
 static msg_ctx *run_stream(run_t *r)
@@ -365,46 +451,37 @@ static msg_ctx *run_stream(run_t *r)
     r->cfg.abi_version = MSG_ABI_VERSION;
     r->cfg.n_ranks = 1;
     if (getenv("MSAMTOOLS_DEVICE")) r->cfg.device = atoi(getenv("MSAMTOOLS_DEVICE"));
+    warm_join();
     if (msg_create(&r->cfg, &ctx)) mDie("%s", msg_last_error(NULL));
-    uint8_t *outbuf = NULL; size_t outcap = 0;
     double t_push = 0; size_t n_pushed = 0;
     struct timespec ta, tb;
+    wring_t w; memset(&w, 0, sizeof w);
+    pthread_mutex_init(&w.mu, NULL); pthread_cond_init(&w.cv, NULL);
+    int wcur = 0;
 
     if (!r->eof) chunk_fill(&r->chunk, r->in, r->hdr, r->chunk.n + 1, (size_t)-1, &r->eof);      /* learn whether there is anything beyond the pre-flight sample */
     if (r->eof) {
-        /* small input: everything is already in the pre-flight chunk, one synchronous push, no reader thread */
+        /* small input: everything is already in the pre-flight chunk, one synchronous push, no threads */
         chunk_t *c = &r->chunk;
         if (c->n) {
             clock_gettime(CLOCK_MONOTONIC, &ta);
             if (msg_push(ctx, c->raw, c->len, c->off, c->n)) gpu_die(ctx);
             clock_gettime(CLOCK_MONOTONIC, &tb);
             t_push += (tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec); n_pushed += c->n;
-            if (r->cfg.want_records) write_kept_records(r, ctx, &outbuf, &outcap);
+            if (r->cfg.want_records) pull_kept_records(r, ctx, &w, &wcur);
         }
     } else {
         ring_t g; memset(&g, 0, sizeof g);
         g.r = r; g.posted_last = -1;
         g.bulk = bio_is_bam(r->in);
         pthread_mutex_init(&g.mu, NULL); pthread_cond_init(&g.cv, NULL);
-        /* BAM: fixed-capacity buffers the inflate workers write into directly; pinned (so that H2D copies run
-           asynchronously at full PCIe rate) once the input is large enough to pay for page-locking them */
-        int pin = 0;
         if (g.bulk) {
             struct stat sb;
             const char *e = getenv("MSAMTOOLS_PINNED");
-            if (e) pin = atoi(e) != 0;
-            else pin = r->path && strcmp(r->path, "-") != 0 && stat(r->path, &sb) == 0 && (size_t)sb.st_size >= ((size_t)192 << 20);
+            if (e) g.pin = atoi(e) != 0;
+            else g.pin = r->path && strcmp(r->path, "-") != 0 && stat(r->path, &sb) == 0 && (size_t)sb.st_size >= ((size_t)192 << 20);
         }
-        for (int i = 0; i < NBUF; i++) {
-            chunk_t *c = &g.buf[i];
-            if (!g.bulk) continue;
-            c->fixed = 1; c->cap = CHUNK_BYTES + ((size_t)64 << 20);
-            void *pmem = NULL;
-            if (pin && msg_host_alloc(r->cfg.device, c->cap, &pmem) == MSG_OK) { c->raw = pmem; c->pinned = 1; }
-            else { c->raw = malloc(c->cap); if (!c->raw) mDie("Out of memory"); }
-            chunk_reserve_off(c, 1);
-            c->off[0] = 0;
-        }
+        ring_buffer_alloc(&g, 0, g.pin);                     /* the others are allocated by the reader thread when it first needs them */
         {   /* the pre-flight records open buffer 0 */
             chunk_t *c = &g.buf[0], *s0 = &r->chunk;
             if (c->fixed) {
@@ -415,8 +492,9 @@ static msg_ctx *run_stream(run_t *r)
             chunk_reserve_off(c, c->n + 1);
             memcpy(c->off, s0->off, (s0->n + 1) * sizeof(uint64_t));
         }
-        pthread_t th;
+        pthread_t th, wth; int have_writer = 0;
         if (pthread_create(&th, NULL, reader_main, &g)) mDie("Cannot start the reader thread");
+        if (r->cfg.want_records) { w.r = r; have_writer = pthread_create(&wth, NULL, writer_main, &w) == 0; if (!have_writer) w.r = NULL; }
         int cur = 0, inflight[2] = { -1, -1 };
         for (;;) {
             pthread_mutex_lock(&g.mu);
@@ -427,9 +505,9 @@ static msg_ctx *run_stream(run_t *r)
             if (c->k) {
                 clock_gettime(CLOCK_MONOTONIC, &ta);
                 if (msg_push_async(ctx, c->raw, (size_t)c->off[c->k], c->off, c->k)) gpu_die(ctx);
+                if (r->cfg.want_records) pull_kept_records(r, ctx, &w, &wcur);      /* completes the chunk */
                 clock_gettime(CLOCK_MONOTONIC, &tb);
                 t_push += (tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec); n_pushed += c->k;
-                if (r->cfg.want_records) write_kept_records(r, ctx, &outbuf, &outcap);      /* completes the chunk */
             }
             /* the buffer pushed two calls ago is no longer referenced by the library */
             if (inflight[0] >= 0) {
@@ -444,18 +522,27 @@ static msg_ctx *run_stream(run_t *r)
         }
         if (msg_wait(ctx)) gpu_die(ctx);
         pthread_join(th, NULL);
+        if (have_writer) {
+            pthread_mutex_lock(&w.mu);
+            w.done = 1;
+            pthread_cond_broadcast(&w.cv);
+            pthread_mutex_unlock(&w.mu);
+            pthread_join(wth, NULL);
+            if (w.failed) mDie("Cannot write alignment record");
+        }
         for (int i = 0; i < NBUF; i++) {
             if (g.buf[i].pinned) msg_host_free(g.buf[i].raw); else free(g.buf[i].raw);
             free(g.buf[i].off);
         }
         pthread_mutex_destroy(&g.mu); pthread_cond_destroy(&g.cv);
     }
-    free(outbuf);
+    free(w.buf[0]); free(w.buf[1]);
+    pthread_mutex_destroy(&w.mu); pthread_cond_destroy(&w.cv);
     if (getenv("MSAMTOOLS_TIMING")) {      /* host-ingest vs GPU time, reported separately (BASELINE.json north_star) */
         uint64_t ib = 0; double isec = 0; msg_timing tm;
         bio_ingest_stats(r->in, &ib, &isec);
         msg_get_timing(ctx, &tm, 0);
-        fprintf(stderr, "# timing: index walk %.3f s\n", g_walk_sec);
+        fprintf(stderr, "# timing: index walk %.3f s; record output %.3f s (writer thread)\n", g_walk_sec, w.t_write);
         fprintf(stderr, "# timing: host ingest %.3f GB in %.3f s (%.2f GB/s, read+inflate); push loop %.3f s (H2D %.3f GB, GPU kernels %.1f ms); %llu records\n",
                 ib / 1e9, isec, isec > 0 ? ib / 1e9 / isec : 0.0, t_push, tm.h2d_bytes / 1e9, tm.total_ms, (unsigned long long)n_pushed);
     }
@@ -535,6 +622,7 @@ static int filter_main(int argc, char *argv[])
 
     run_t r; memset(&r, 0, sizeof r);
     phase(sub, NULL);
+    warm_start();
     open_input(&r, a_file->filename[0]);
     phase(sub, "open + header");
     const int hit = a_uniq->count > 0 ? MSG_HIT_UNIQUE : a_best->count > 0 ? MSG_HIT_BEST : MSG_HIT_NONE;
@@ -682,6 +770,7 @@ static int profile_main(int argc, char *argv[])
 
     run_t r; memset(&r, 0, sizeof r);
     phase(sub, NULL);
+    warm_start();
     open_input(&r, a_file->filename[0]);
     phase(sub, "open + header");
     chunk_fill(&r.chunk, r.in, r.hdr, COORD_ORDER_CHECK_RECORDS, (size_t)-1, &r.eof);
@@ -879,6 +968,7 @@ static int coverage_main(int argc, char *argv[])
     gzp *out = gzp_open(a_out->sval[0], host_threads());
     if (!out) mDie("Cannot open %s for writing", a_out->sval[0]);
     run_t r; memset(&r, 0, sizeof r);
+    warm_start();
     open_input(&r, a_file->filename[0]);
     const int T = r.hdr->n_targets;
     r.cfg.do_filter = 0; r.cfg.want_coverage = 1; r.cfg.coverage_summary = a_summary->count > 0; r.cfg.n_targets = T; r.cfg.n_features = T; r.cfg.target_len = r.hdr->target_len;

@@ -1,8 +1,13 @@
 /* bamio.c -- SAM / BAM / BGZF I/O over zlib.  See bamio.h. */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE            /* F_SETPIPE_SZ */
+#endif
 #include "bamio.h"
 #include "finflate.h"
 #include <ctype.h>
 #include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,7 +29,8 @@ struct bio_file {
     char *line; size_t line_cap;
     /* parallel BGZF inflate */
     int threads, bgzf;
-    uint8_t *cin; size_t cin_len, cin_cap;
+    uint8_t *cin; size_t cin_len;        /* view of the compressed bytes not yet consumed (inside io->mem[io_cur]) */
+    struct io_ring *io; int io_cur;
     uint64_t ingest_bytes; double ingest_sec;
     uint64_t blocks_fast, blocks_zlib;   /* parallel path: blocks inflated by finflate.c / handed to zlib */
     /* name -> tid hash for SAM parsing */
@@ -64,6 +70,101 @@ void bio_set_threads(bio_file *f, int n) { if (f) f->threads = n < 1 ? 1 : (n > 
 void bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds) { if (bytes) *bytes = f->ingest_bytes; if (seconds) *seconds = f->ingest_sec; }
 void bio_inflate_stats(const bio_file *f, uint64_t *fast_blocks, uint64_t *zlib_blocks) { if (fast_blocks) *fast_blocks = f->blocks_fast; if (zlib_blocks) *zlib_blocks = f->blocks_zlib; }
 
+/* ---- compressed input arrives through a read-ahead thread: while the workers inflate one batch, the next one is being read
+ * (from a pipe that is what keeps the upstream process writing).  Two slots; the consumer's view carries the unconsumed tail
+ * of a slot (less than one block) into the room reserved in front of the next one. */
+#ifndef IO_BATCH                            /* (tests build with a slot of little more than one block) */
+#define IO_BATCH   ((size_t)24 << 20)
+#endif
+#define IO_RESERVE ((size_t)1 << 17)
+typedef struct io_ring {
+    FILE *fp;
+    uint8_t *mem[2]; size_t len[2]; int full[2], eof[2];
+    int quit, done, started;
+    pthread_t th; pthread_mutex_t mu; pthread_cond_t cv;
+} io_ring;
+
+static void *io_main(void *arg)
+{
+    io_ring *r = arg;
+    for (int i = 1;; i ^= 1) {
+        pthread_mutex_lock(&r->mu);
+        while (r->full[i] && !r->quit) pthread_cond_wait(&r->cv, &r->mu);
+        const int quit = r->quit;
+        pthread_mutex_unlock(&r->mu);
+        if (quit) break;
+        const size_t got = fread(r->mem[i] + IO_RESERVE, 1, IO_BATCH, r->fp);
+        pthread_mutex_lock(&r->mu);
+        r->len[i] = got; r->eof[i] = got < IO_BATCH; r->full[i] = 1;
+        pthread_cond_broadcast(&r->cv);
+        pthread_mutex_unlock(&r->mu);
+        if (got < IO_BATCH) break;
+    }
+    pthread_mutex_lock(&r->mu);
+    r->done = 1;
+    pthread_mutex_unlock(&r->mu);
+    return NULL;
+}
+
+/* the first bytes of the stream (already read for format detection) open slot 0; the thread starts unless they were all */
+static int io_start(bio_file *f, const uint8_t *first, size_t n, int at_eof)
+{
+    io_ring *r = calloc(1, sizeof *r);
+    if (!r) return -1;
+    r->fp = f->fp;
+    r->mem[0] = malloc(IO_RESERVE + (n > IO_BATCH ? n : IO_BATCH));
+    if (!r->mem[0]) { free(r); return -1; }
+    memcpy(r->mem[0] + IO_RESERVE, first, n);
+    r->len[0] = n; r->full[0] = 1; r->eof[0] = at_eof;
+    pthread_mutex_init(&r->mu, NULL); pthread_cond_init(&r->cv, NULL);
+    f->io = r; f->io_cur = 0; f->cin = r->mem[0] + IO_RESERVE; f->cin_len = n;
+    if (!at_eof) {
+        r->mem[1] = malloc(IO_RESERVE + IO_BATCH);
+        if (!r->mem[1]) return -1;
+        if (pthread_create(&r->th, NULL, io_main, r)) return -1;
+        r->started = 1;
+    }
+    return 0;
+}
+
+/* append the next slot to the view (whose remaining bytes move in front of it); sets in_eof with the last one */
+static void io_fetch(bio_file *f)
+{
+    io_ring *r = f->io;
+    const int cur = f->io_cur, nxt = cur ^ 1;
+    pthread_mutex_lock(&r->mu);
+    while (!r->full[nxt]) pthread_cond_wait(&r->cv, &r->mu);
+    pthread_mutex_unlock(&r->mu);
+    uint8_t *v = r->mem[nxt] + IO_RESERVE - f->cin_len;         /* cin_len < one block <= IO_RESERVE */
+    memcpy(v, f->cin, f->cin_len);
+    f->cin = v; f->cin_len += r->len[nxt];
+    if (r->eof[nxt]) f->in_eof = 1;
+    pthread_mutex_lock(&r->mu);
+    r->full[cur] = 0;
+    pthread_cond_broadcast(&r->cv);
+    pthread_mutex_unlock(&r->mu);
+    f->io_cur = nxt;
+}
+
+static void io_stop(bio_file *f)
+{
+    io_ring *r = f->io;
+    if (!r) return;
+    if (r->started) {
+        pthread_mutex_lock(&r->mu);
+        r->quit = 1;
+        const int done = r->done;
+        pthread_cond_broadcast(&r->cv);
+        pthread_mutex_unlock(&r->mu);
+        /* a reader abandoned before the end of a PIPE may have its thread blocked in read(): leave it behind */
+        if (!done && !f->own_fp && !f->in_eof) { pthread_detach(r->th); f->io = NULL; return; }
+        pthread_join(r->th, NULL);
+    }
+    pthread_mutex_destroy(&r->mu); pthread_cond_destroy(&r->cv);
+    free(r->mem[0]); free(r->mem[1]); free(r);
+    f->io = NULL;
+}
+
 /* ---- BGZF blocks are independent gzip members: inflate a batch of them on worker threads */
 typedef struct { size_t in_off, in_len, out_off; uint32_t isize, crc; } bgzf_blk;
 typedef struct { const uint8_t *in; uint8_t *out; const bgzf_blk *blk; size_t nblk; int id, nthr; int err; uint64_t n_fast, n_zlib; } bgzf_job;
@@ -91,7 +192,6 @@ static void *bgzf_worker(void *arg)
     return NULL;
 }
 
-#define BGZF_BATCH ((size_t)48 << 20)
 
 /* Inflate the next batch of whole blocks.  dst == NULL: into f->dec (grown as needed), which becomes the readable window.
  * dst != NULL: straight into the caller's buffer, as many blocks as fit in dst_cap (*out_len = bytes produced; 0 with
@@ -99,13 +199,7 @@ static void *bgzf_worker(void *arg)
 static int bgzf_batch(bio_file *f, uint8_t *dst, size_t dst_cap, size_t *out_len)
 {
     for (;;) {
-        if (!f->in_eof && f->cin_len < BGZF_BATCH) {
-            if (grow(&f->cin, &f->cin_cap, BGZF_BATCH + (1 << 17))) { set_err(f, "out of memory"); return -1; }
-            size_t got = fread(f->cin + f->cin_len, 1, BGZF_BATCH + (1 << 16) - f->cin_len, f->fp);
-            f->cin_len += got;
-            if (got == 0 || feof(f->fp)) f->in_eof = 1;
-        }
-        /* split into whole blocks */
+        /* split what the view holds into whole blocks */
         size_t p = 0, nblk = 0, out = 0, cap = 0; bgzf_blk *blk = NULL; int full = 0;
         while (p + 18 <= f->cin_len) {
             const uint8_t *h = f->cin + p;
@@ -135,7 +229,7 @@ static int bgzf_batch(bio_file *f, uint8_t *dst, size_t dst_cap, size_t *out_len
         if (nblk == 0) {
             free(blk);
             if (full) { *out_len = 0; return 1; }
-            if (!f->in_eof) continue;
+            if (!f->in_eof) { if (f->cin_len > IO_RESERVE) { set_err(f, "corrupt BGZF block header"); return -1; } io_fetch(f); continue; }
             if (f->cin_len) { set_err(f, "truncated BGZF block"); return -1; }
             return 0;
         }
@@ -156,7 +250,7 @@ static int bgzf_batch(bio_file *f, uint8_t *dst, size_t dst_cap, size_t *out_len
         for (int i = 0; i < nthr; i++) { f->blocks_fast += job[i].n_fast; f->blocks_zlib += job[i].n_zlib; }
         free(blk);
         if (err) { set_err(f, "corrupt BGZF block (inflate/CRC)"); return -1; }
-        memmove(f->cin, f->cin + p, f->cin_len - p); f->cin_len -= p;
+        f->cin += p; f->cin_len -= p;
         if (!dst) { f->dec_pos = 0; f->dec_len = out; }
         *out_len = out;
         if (out) return 1;           /* a batch of empty (EOF-marker) blocks: look at the next one */
@@ -192,8 +286,7 @@ static int rd_fill_inner(bio_file *f)
         f->detected = 1;
         if (f->compressed && f->threads > 1 && f->in_len >= 18 && (f->in[3] & 4) && f->in[12] == 'B' && f->in[13] == 'C') {
             f->bgzf = 1;
-            if (grow(&f->cin, &f->cin_cap, BGZF_BATCH + (1 << 17))) { set_err(f, "out of memory"); return -1; }
-            memcpy(f->cin, f->in, f->in_len); f->cin_len = f->in_len;
+            if (io_start(f, f->in, f->in_len, f->in_eof)) { set_err(f, "out of memory"); return -1; }
             return rd_fill_bgzf(f);
         }
         if (f->compressed) {
@@ -305,11 +398,22 @@ static long rd_line(bio_file *f)
     return (long)l;
 }
 
+/* a pipe between two msamtools processes carries gigabytes: ask for a 1 MB pipe buffer instead of 64 KB (fewer wake-ups per
+ * byte; silently keeps the default where the kernel says no or the descriptor is not a pipe) */
+static void widen_pipe(FILE *fp)
+{
+#ifdef F_SETPIPE_SZ
+    if (fp) (void)fcntl(fileno(fp), F_SETPIPE_SZ, 1 << 20);
+#else
+    (void)fp;
+#endif
+}
+
 bio_file *bio_open_read(const char *path)
 {
     bio_file *f = calloc(1, sizeof *f);
     if (!f) return NULL;
-    if (strcmp(path, "-") == 0) f->fp = stdin; else { f->fp = fopen(path, "rb"); f->own_fp = 1; }
+    if (strcmp(path, "-") == 0) { f->fp = stdin; widen_pipe(stdin); } else { f->fp = fopen(path, "rb"); f->own_fp = 1; }
     if (!f->fp) { free(f); return NULL; }
     f->in = malloc(IN_CHUNK);
     if (!f->in) { if (f->own_fp) fclose(f->fp); free(f); return NULL; }
@@ -808,14 +912,15 @@ static int bgzf_flush_block(bio_file *f, const uint8_t *data, size_t n)
 }
 
 /* ---- bulk output: whole blocks of a large buffer are packed (deflate / stored + CRC) on worker threads, written in order */
-typedef struct { int level; const uint8_t *data; size_t nblk; uint8_t *out; size_t *olen; int id, nthr, err; } bgzf_wjob;
+#define BGZF_STORED_SIZE (BGZF_BLOCK + 31)     /* a full block of "-u" output: 18 header + 5 stored-block header + payload + 8 trailer */
+typedef struct { int level; const uint8_t *data; size_t nblk; uint8_t *out; size_t *olen; int id, nthr, err; size_t stride; } bgzf_wjob;
 static void *bgzf_wworker(void *arg)
 {
     bgzf_wjob *j = arg;
     z_stream zs; int have = 0;
     if (j->level != 0) { memset(&zs, 0, sizeof zs); if (deflateInit2(&zs, j->level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { j->err = 1; return NULL; } have = 1; }
     for (size_t k = (size_t)j->id; k < j->nblk; k += (size_t)j->nthr) {
-        j->olen[k] = bgzf_pack_block(j->level, have ? &zs : NULL, j->data + k * BGZF_BLOCK, BGZF_BLOCK, j->out + k * BGZF_OUT_STRIDE);
+        j->olen[k] = bgzf_pack_block(j->level, have ? &zs : NULL, j->data + k * BGZF_BLOCK, BGZF_BLOCK, j->out + k * j->stride);
         if (!j->olen[k]) { j->err = 1; break; }
     }
     if (have) deflateEnd(&zs);
@@ -847,16 +952,19 @@ int bio_write_raw(bio_file *f, const uint8_t *p, size_t n)
         size_t nblk = n / BGZF_BLOCK; if (nblk > BATCH) nblk = BATCH;
         if (!f->wout) { f->wout = malloc((size_t)BATCH * BGZF_OUT_STRIDE); f->wolen = malloc(sizeof(size_t) * BATCH); if (!f->wout || !f->wolen) return -1; }
         int t = nthr; if ((size_t)t > nblk) t = (int)nblk;
+        /* stored blocks all have the same size: packed back to back, the batch leaves in one write */
+        const size_t stride = f->w_level == 0 ? BGZF_STORED_SIZE : BGZF_OUT_STRIDE;
         pthread_t th[64]; bgzf_wjob job[64];
         for (int i = 0; i < t; i++) {
-            job[i] = (bgzf_wjob){ f->w_level, p, nblk, f->wout, f->wolen, i, t, 0 };
+            job[i] = (bgzf_wjob){ f->w_level, p, nblk, f->wout, f->wolen, i, t, 0, stride };
             if (i && pthread_create(&th[i], NULL, bgzf_wworker, &job[i])) job[i].err = 2;
         }
         bgzf_wworker(&job[0]);
         int err = job[0].err;
         for (int i = 1; i < t; i++) { if (job[i].err == 2) { job[i].err = 0; bgzf_wworker(&job[i]); } else pthread_join(th[i], NULL); err |= job[i].err; }
         if (err) return -1;
-        for (size_t k = 0; k < nblk; k++)
+        if (f->w_level == 0) { if (fwrite(f->wout, 1, nblk * stride, f->fp) != nblk * stride) return -1; }
+        else for (size_t k = 0; k < nblk; k++)
             if (fwrite(f->wout + k * BGZF_OUT_STRIDE, 1, f->wolen[k], f->fp) != f->wolen[k]) return -1;
         p += nblk * BGZF_BLOCK; n -= nblk * BGZF_BLOCK;
     }
@@ -871,7 +979,7 @@ bio_file *bio_open_write(const char *path, const char *mode)
     f->w_bam = strchr(mode, 'b') != NULL;
     f->w_header = f->w_bam || strchr(mode, 'h') != NULL;
     f->w_level = strchr(mode, 'u') ? 0 : Z_DEFAULT_COMPRESSION;
-    if (strcmp(path, "-") == 0) f->fp = stdout; else { f->fp = fopen(path, "wb"); f->own_fp = 1; }
+    if (strcmp(path, "-") == 0) { f->fp = stdout; widen_pipe(stdout); } else { f->fp = fopen(path, "wb"); f->own_fp = 1; }
     if (!f->fp) { free(f); return NULL; }
     if (f->w_bam) f->wbuf = malloc(BGZF_BLOCK);
     return f;
@@ -917,9 +1025,9 @@ int bio_close(bio_file *f)
         }
         if (fflush(f->fp)) rc = -1;
         if (f->wz_init) deflateEnd(&f->wzs);
-    } else if (f->z_init) inflateEnd(&f->zs);
+    } else { if (f->z_init) inflateEnd(&f->zs); io_stop(f); }
     if (f->own_fp && fclose(f->fp)) rc = -1;
-    free(f->in); free(f->dec); free(f->line); free(f->cin); free(f->ht); free(f->wbuf); free(f->wout); free(f->wolen); free(f->fmt); free(f);
+    free(f->in); free(f->dec); free(f->line); free(f->ht); free(f->wbuf); free(f->wout); free(f->wolen); free(f->fmt); free(f);
     return rc;
 }
 

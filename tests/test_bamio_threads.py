@@ -12,16 +12,19 @@ from conftest import ROOT
 HOST = os.path.join(ROOT, "msamtools_b200", "csrc", "host")
 
 
-@pytest.fixture(scope="module")
-def harness(tmp_path_factory):
+@pytest.fixture(scope="module", params=["slots of 24 MB", "slots of 70001 bytes"])
+def harness(tmp_path_factory, request):
+    """built twice: with the product's read-ahead slot size, and with slots of little more than one BGZF block, so that the
+    hand-over between slots (tail of one carried in front of the next) happens thousands of times on a small file"""
     if not shutil.which("gcc"):
         pytest.skip("no gcc")
     d = tmp_path_factory.mktemp("bamio")
     exe = str(d / "reader")
+    small = ["-DIO_BATCH=((size_t)70001)"] if "70001" in request.param else []
     srcs = [os.path.join(ROOT, "tests", "c", "bamio_read_harness.c"), os.path.join(HOST, "bamio.c")]
     if os.path.exists(os.path.join(HOST, "finflate.c")):
         srcs.append(os.path.join(HOST, "finflate.c"))
-    subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", HOST] + srcs +
+    subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", HOST] + small + srcs +
                    ["-lz", "-lpthread", "-o", exe], check=True)
     return exe, d
 
@@ -56,6 +59,29 @@ def test_parallel_inflate_equals_streaming(harness, stream, level):
     assert outs[1] == raw and outs[2] == raw and outs[5] == raw
 
 
+def test_pipe_input_through_the_read_ahead_thread(harness, stream):
+    """stdin instead of a file, fed in dribbles by a slow producer: the read-ahead thread's slots are handed over in order and the
+    tail of one slot is carried into the next (a file much larger than one slot is covered by the bulk-reader test below)"""
+    exe, d = harness
+    raw, names, tlen = stream
+    import numpy as np
+    path = str(d / "pipe.bam")
+    samutil.write_bam(path, samutil.synth_header(names, tlen), names, tlen, np.frombuffer(raw, dtype=np.uint8), level=1)
+    blob = open(path, "rb").read()
+    for thr in (2, 4):
+        p = subprocess.Popen([exe, "-", str(thr)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        import threading
+        out = []
+        t = threading.Thread(target=lambda: out.append(p.stdout.read()))
+        t.start()
+        for o in range(0, len(blob), 300_001):
+            p.stdin.write(blob[o:o + 300_001]); p.stdin.flush()
+        p.stdin.close()
+        t.join()
+        assert p.wait() == 0, p.stderr.read().decode()
+        assert out[0] == raw
+
+
 def test_corrupt_block_is_reported(harness, stream):
     exe, d = harness
     raw, names, tlen = stream
@@ -70,14 +96,15 @@ def test_corrupt_block_is_reported(harness, stream):
         assert r.returncode == 1 and (b"corrupt" in r.stderr or b"inflate" in r.stderr or b"CRC" in r.stderr or b"truncated" in r.stderr), r.stderr
 
 
-@pytest.fixture(scope="module")
-def bulk(tmp_path_factory):
+@pytest.fixture(scope="module", params=["slots of 24 MB", "slots of 70001 bytes"])
+def bulk(tmp_path_factory, request):
     if not shutil.which("gcc"):
         pytest.skip("no gcc")
     d = tmp_path_factory.mktemp("bamio_bulk")
     exe = str(d / "bulk")
+    small = ["-DIO_BATCH=((size_t)70001)"] if "70001" in request.param else []
     srcs = [os.path.join(ROOT, "tests", "c", "bamio_bulk_harness.c"), os.path.join(HOST, "bamio.c"), os.path.join(HOST, "finflate.c")]
-    subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", HOST] + srcs +
+    subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", HOST] + small + srcs +
                    ["-lz", "-lpthread", "-o", exe], check=True)
     return exe, d
 

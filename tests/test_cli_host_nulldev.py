@@ -1,0 +1,129 @@
+"""CPU: the HOST plumbing of the drop-in CLI -- reader thread and buffer ring, read-ahead, multi-threaded record index, QNAME
+cuts, the record-output writer thread, BGZF packing, the parallel gzip tables -- run against a NULL DEVICE
+(tests/hostprof/nulldev.c: keeps the records whose POS is not a multiple of 5, returns fixed patterns for profile and
+coverage).  Nothing here says anything about alignment arithmetic (that is the GPU parity suite); it checks that every byte
+that goes in comes out where it should, for many chunk sizes and thread counts, and that the threads are race-free
+(ThreadSanitizer build)."""
+import gzip
+import os
+import shutil
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import samutil
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "hostprof"))
+CS = os.path.join(ROOT, "msamtools_b200", "csrc")
+HOSTSRC = [os.path.join(CS, "cli", "msamtools_main.c")] + [os.path.join(CS, "host", f) for f in
+                                                          ("bamio.c", "finflate.c", "gzpar.c", "margs.c", "keyorder.c", "recwalk.c")]
+
+
+def build(d, san):
+    lib = os.path.join(d, "libmsamtools_b200.so")
+    flags = ["-O1", "-g", "-std=gnu99"] + ([f"-fsanitize={san}", "-fno-sanitize-recover=all"] if san else [])
+    subprocess.run(["gcc"] + flags + ["-fPIC", "-shared", "-o", lib, os.path.join(ROOT, "tests", "hostprof", "nulldev.c")], check=True)
+    cli = os.path.join(d, "msamtools")
+    subprocess.run(["gcc"] + flags + ["-o", cli] + HOSTSRC + ["-L" + d, "-lmsamtools_b200", "-Wl,-rpath," + d, "-lz", "-lm", "-lpthread"], check=True)
+    return cli
+
+
+@pytest.fixture(scope="module", params=["address,undefined", "thread"])
+def cli(tmp_path_factory, request):
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    d = str(tmp_path_factory.mktemp("nulldev_" + request.param.split(",")[0]))
+    os.environ["ASAN_OPTIONS"] = "detect_leaks=0"            # a command-line tool: what it holds at exit is the OS's to free
+    return build(d, request.param)
+
+
+@pytest.fixture(scope="module")
+def bam(tmp_path_factory):
+    from msamtools_b200 import synth
+    d = tmp_path_factory.mktemp("nulldev_in")
+    p = synth.make_params("mixed", n_records=160_000, seed=11)            # ~ 48 MB of records
+    raw, off, _ = synth.generate(p)
+    n = len(off) - 1
+    raw = raw[:int(off[n])]
+    tlen = synth.target_lengths(p)
+    names = [f"ref{i:04d}" for i in range(len(tlen))]
+    path = str(d / "in.bam")
+    samutil.write_bam(path, samutil.synth_header(names, tlen), names, tlen, raw, level=1)
+    pos = np.array([struct.unpack_from("<I", raw, int(o) + 8)[0] for o in off[:n]])
+    kept = b"".join(bytes(raw[int(off[i]):int(off[i + 1])]) for i in range(n) if pos[i] % 5 != 0)
+    return path, bytes(raw), kept, names, tlen, n
+
+
+ENVS = [dict(MSAMTOOLS_CHUNK_RECORDS="7000", MSAMTOOLS_THREADS="4"),          # many chunks: ring, tails, writer hand-over
+        dict(MSAMTOOLS_CHUNK_RECORDS="50000", MSAMTOOLS_THREADS="1"),        # streaming inflate, record index without threads
+        dict(MSAMTOOLS_THREADS="8")]                                          # default chunk size: one chunk
+
+
+@pytest.mark.parametrize("env", ENVS, ids=lambda e: "-".join(e.values()))
+def test_filter_record_output_and_pipe_into_profile(cli, bam, env, tmp_path):
+    path, raw, kept, names, tlen, n = bam
+    e = dict(os.environ, MSAMTOOLS_TIMING="1", **env)
+    for mode in ("-bu", "-b"):
+        f = subprocess.run([cli, "filter", mode, "-l", "80", "--besthit", path], capture_output=True, env=e)
+        assert f.returncode == 0, f.stderr.decode()[-3000:]
+        out = str(tmp_path / "f.bam")
+        open(out, "wb").write(f.stdout)
+        got = samutil.read_bam(out)
+        assert bytes(got.raw) == kept, mode
+    # the -b stream piped into `profile` on stdin: every kept record arrives (the null device reports the count) and the table is the pattern
+    outp = str(tmp_path / "p.gz")
+    p = subprocess.run([cli, "profile", "--label", "S", "--unit", "ab", "--nolen", "-o", outp, "-"], input=f.stdout, capture_output=True, env=e)
+    assert p.returncode == 0, p.stderr.decode()[-3000:]
+    comments, body = samutil.read_profile_gz(outp)
+    n_kept = sum(1 for _ in _records(kept))
+    assert any(c.startswith("# Mapped inserts") and f" {n_kept} (" in c for c in comments), comments
+    want = [0.0 if i % 11 == 0 else ((i * 2654435761 & 0xffffffff) >> 7) / 1024.0 / (i % 13 + 1) for i in range(len(names))]
+    assert list(body[0]) == ["ID", "S"] and body[1][0] == "Unknown"
+    assert [k for k, _ in body[2:]] == names and [v for _, v in body[2:]] == ["%.8g" % x for x in want]
+
+
+def _records(blob):
+    o = 0
+    while o < len(blob):
+        bs = struct.unpack_from("<I", blob, o)[0]
+        yield o
+        o += 4 + bs
+
+
+def test_coverage_writers(cli, bam, tmp_path):
+    path, raw, kept, names, tlen, n = bam
+    e = dict(os.environ, MSAMTOOLS_THREADS="3", MSAMTOOLS_CHUNK_RECORDS="20000")
+    out = str(tmp_path / "c.gz")
+    r = subprocess.run([cli, "coverage", "--summary", "-o", out, path], capture_output=True, env=e)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]
+    lines = gzip.open(out, "rt").read().splitlines()
+    want = [f"{nm}\t0\t0" if i % 3 == 1 else "%s\t%.8f\t%.2f" % (nm, (10 + i) / l, (20 + 3 * i) / l) for i, (nm, l) in enumerate(zip(names, tlen))]
+    assert lines == want
+    # per-position dump, -w 7, skipping uncovered sequences: the integer formatter, negative values, line breaks, the last value
+    r = subprocess.run([cli, "coverage", "-x", "-w", "7", "-o", out, path], capture_output=True, env=e)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]
+    text = gzip.open(out, "rt").read()
+    exp = []
+    for t, (nm, l) in enumerate(zip(names, tlen)):
+        if t % 3 == 1:
+            continue
+        i = np.arange(int(l), dtype=np.uint64)
+        d = (((i * 2654435761 + t) & 0xffffffff) >> 12).astype(np.int64) % 100003 - np.where(i % 97 == 0, 7, 0)
+        exp.append(">" + nm)
+        for a in range(0, int(l), 7):
+            exp.append(" ".join(str(int(x)) for x in d[a:a + 7]))
+    assert text == "\n".join(exp) + "\n"
+
+
+def test_small_input_and_sam_output(cli, tmp_path):
+    """inputs that fit the pre-flight sample take the thread-less path; SAM text in and out"""
+    sam = "@HD\tVN:1.6\tSO:queryname\n@SQ\tSN:A\tLN:1000\n" + "".join(
+        f"r{i // 2}\t{0 if i % 2 == 0 else 16}\tA\t{10 + i}\t60\t10M\t*\t0\t0\tACGTACGTAC\tIIIIIIIIII\tNM:i:0\tAS:i:5\n" for i in range(40))
+    r = subprocess.run([cli, "filter", "-S", "-l", "5", "-"], input=sam.encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    got = r.stdout.decode().splitlines()
+    assert got == [l for l in sam.splitlines()[2:] if int(l.split("\t")[3]) % 5 != 1]      # POS is 0-based in the record: 1-based % 5 != 1
