@@ -430,13 +430,14 @@ def write_bgzf_threads(path, blobs, level=1, threads=8):
     return len(data)
 
 
-def ingest_entry(cfg, plan, tlen, raw, off):
+def ingest_entry(cfg, plan, tlen, raw, off, cli=None, env_extra=None, thread_counts=(1, 4, 16)):
     """R3 of SURVEY 8d, reported separately from the kernels (north_star): a level-1 BGZF BAM of the workload on tmpfs through the
-    drop-in CLI (`filter ... | profile ...`, file to result) with 1 / 4 / 16 inflate threads -- host read+inflate GB/s from the
-    CLI's own timers, alignments/s by wall clock -- and the reference's object code on the same file."""
+    drop-in CLI (`filter ... | profile ...`, file to result) with 1 / 4 / 16 host threads -- host read+inflate GB/s and the
+    per-phase wall times from the CLI's own timers, alignments/s by wall clock -- and the reference's object code on the same file.
+    (`cli` / `env_extra`: the CPU tests run this leg against a build of the CLI on the null device of tests/hostprof.)"""
     import re
     import tempfile
-    cli = os.path.join(ROOT, "msamtools_b200", "bin", "msamtools")
+    cli = cli or os.path.join(ROOT, "msamtools_b200", "bin", "msamtools")
     if not os.path.exists(cli):
         return {"unavailable": "msamtools_b200/bin/msamtools not built"}
     n = len(off) - 1
@@ -454,24 +455,35 @@ def ingest_entry(cfg, plan, tlen, raw, off):
             p1 = subprocess.run(a, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
             err, rc = p1.stderr, p1.returncode
         else:
-            p1 = subprocess.Popen([binary] + f_args + [path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
-            p2 = subprocess.Popen([binary] + cfg["ref_second"] + ["-o", os.path.join(d, "o.gz"), "-"], stdin=p1.stdout, stdout=subprocess.DEVNULL,
-                                  stderr=subprocess.DEVNULL, env=env)
-            p1.stdout.close()
-            err = p1.stderr.read()
-            rc = p2.wait() | p1.wait()
+            with open(os.path.join(d, "second.err"), "wb") as e2:
+                p1 = subprocess.Popen([binary] + f_args + [path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+                p2 = subprocess.Popen([binary] + cfg["ref_second"] + ["-o", os.path.join(d, "o.gz"), "-"], stdin=p1.stdout, stdout=subprocess.DEVNULL,
+                                      stderr=e2, env=env)
+                p1.stdout.close()
+                err = p1.stderr.read()
+                rc = p2.wait() | p1.wait()
+            with open(os.path.join(d, "second.err"), "rb") as e2:
+                err += e2.read()
         return time.perf_counter() - t0, err.decode(errors="replace"), rc
 
+    def phases(err):
+        """"# phase <command> <name>: <seconds> s" lines of both processes (MSAMTOOLS_TIMING=1)"""
+        out = {}
+        for c, nm, sec in re.findall(r"^# phase (\S+) (.+?): ([0-9.]+) s$", err, flags=re.M):
+            out[f"{c}: {nm}"] = float(sec)
+        return out
+
     try:
-        for thr in (1, 4, 16):
+        for thr in thread_counts:
             if thr > cores and thr != 1:
                 continue
-            env = dict(os.environ, MSAMTOOLS_TIMING="1", MSAMTOOLS_THREADS=str(thr))
+            env = dict(os.environ, MSAMTOOLS_TIMING="1", MSAMTOOLS_THREADS=str(thr), **(env_extra or {}))
             pipe(cli, env)                                  # warm-up (CUDA context creation is part of every CLI run; page cache)
             dt, err, rc = pipe(cli, env)
             m = re.search(r"host ingest ([0-9.]+) GB in ([0-9.]+) s", err)
             out["threads"][str(thr)] = {"file_to_result_M_aln_per_s": n / dt / 1e6, "wall_s": dt, "rc": rc,
-                                        "inflate_gbs": (float(m.group(1)) / float(m.group(2))) if m and float(m.group(2)) > 0 else None}
+                                        "inflate_gbs": (float(m.group(1)) / float(m.group(2))) if m and float(m.group(2)) > 0 else None,
+                                        "phases_s": phases(err)}
         if have_ref_binary():
             dt, _, rc = pipe(REF_BIN, dict(os.environ))
             out["reference_single_pipe"] = {"file_to_result_M_aln_per_s": n / dt / 1e6, "wall_s": dt, "rc": rc,

@@ -70,7 +70,11 @@ static void phase(const char *cmd, const char *name)
     if (on < 0) { on = getenv("MSAMTOOLS_TIMING") != NULL; clock_gettime(CLOCK_MONOTONIC, &t0); }
     if (!on) return;
     clock_gettime(CLOCK_MONOTONIC, &t);
-    if (name) fprintf(stderr, "# phase %s %s: %.3f s\n", cmd, name, (t.tv_sec - t0.tv_sec) + 1e-9 * (t.tv_nsec - t0.tv_nsec));
+    if (name) {
+        struct timespec rt; clock_gettime(CLOCK_REALTIME, &rt);
+        fprintf(stderr, "# phase %s %s: %.3f s (ends at %02d.%03d)\n", cmd, name, (t.tv_sec - t0.tv_sec) + 1e-9 * (t.tv_nsec - t0.tv_nsec),
+                (int)(rt.tv_sec % 60), (int)(rt.tv_nsec / 1000000));
+    }
     t0 = t;
 }
 

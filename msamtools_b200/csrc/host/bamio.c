@@ -7,6 +7,8 @@
 #include <ctype.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <poll.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -30,7 +32,7 @@ struct bio_file {
     /* parallel BGZF inflate */
     int threads, bgzf;
     uint8_t *cin; size_t cin_len;        /* view of the compressed bytes not yet consumed (inside io->mem[io_cur]) */
-    struct io_ring *io; int io_cur;
+    struct io_ring *io; int io_cur, unbuffered;
     uint64_t ingest_bytes; double ingest_sec;
     uint64_t blocks_fast, blocks_zlib;   /* parallel path: blocks inflated by finflate.c / handed to zlib */
     /* name -> tid hash for SAM parsing */
@@ -77,8 +79,9 @@ void bio_inflate_stats(const bio_file *f, uint64_t *fast_blocks, uint64_t *zlib_
 #define IO_BATCH   ((size_t)24 << 20)
 #endif
 #define IO_RESERVE ((size_t)1 << 17)
+#define IO_MIN_POST ((size_t)8 << 20)       /* pipes: a slot holding this much is handed over the moment the writer pauses */
 typedef struct io_ring {
-    FILE *fp;
+    FILE *fp; int pipe_fd;                  /* >= 0: the input is a pipe, read(2) it directly (the stream is unbuffered, bio_open_read) */
     uint8_t *mem[2]; size_t len[2]; int full[2], eof[2];
     int quit, done, started;
     pthread_t th; pthread_mutex_t mu; pthread_cond_t cv;
@@ -93,12 +96,29 @@ static void *io_main(void *arg)
         const int quit = r->quit;
         pthread_mutex_unlock(&r->mu);
         if (quit) break;
-        const size_t got = fread(r->mem[i] + IO_RESERVE, 1, IO_BATCH, r->fp);
+        size_t got = 0; int eof = 0;
+        if (r->pipe_fd >= 0) {
+            /* a pipe delivers what the upstream process has written so far: waiting for a full slot would hold back, e.g., the
+               header until the first records follow it.  Take what is there; stop at a full slot or when the pipe runs dry. */
+            for (;;) {
+                const ssize_t k = read(r->pipe_fd, r->mem[i] + IO_RESERVE + got, IO_BATCH - got);
+                if (k < 0 && errno == EINTR) continue;
+                if (k <= 0) { eof = 1; break; }            /* a read error ends the stream; what is missing is reported as truncation */
+                got += (size_t)k;
+                if (got == IO_BATCH) break;
+                /* dry now: hand a big slot over at once, a small one if nothing follows within 2 ms (many tiny batches cost more) */
+                struct pollfd pf = { r->pipe_fd, POLLIN, 0 };
+                if (poll(&pf, 1, got >= IO_MIN_POST ? 0 : 2) <= 0) break;
+            }
+        } else {
+            got = fread(r->mem[i] + IO_RESERVE, 1, IO_BATCH, r->fp);
+            eof = got < IO_BATCH;
+        }
         pthread_mutex_lock(&r->mu);
-        r->len[i] = got; r->eof[i] = got < IO_BATCH; r->full[i] = 1;
+        r->len[i] = got; r->eof[i] = eof; r->full[i] = 1;
         pthread_cond_broadcast(&r->cv);
         pthread_mutex_unlock(&r->mu);
-        if (got < IO_BATCH) break;
+        if (eof) break;
     }
     pthread_mutex_lock(&r->mu);
     r->done = 1;
@@ -111,7 +131,8 @@ static int io_start(bio_file *f, const uint8_t *first, size_t n, int at_eof)
 {
     io_ring *r = calloc(1, sizeof *r);
     if (!r) return -1;
-    r->fp = f->fp;
+    r->fp = f->fp; r->pipe_fd = -1;
+    if (f->unbuffered) { struct stat sb; if (fstat(fileno(f->fp), &sb) == 0 && S_ISFIFO(sb.st_mode)) r->pipe_fd = fileno(f->fp); }
     r->mem[0] = malloc(IO_RESERVE + (n > IO_BATCH ? n : IO_BATCH));
     if (!r->mem[0]) { free(r); return -1; }
     memcpy(r->mem[0] + IO_RESERVE, first, n);
@@ -413,7 +434,10 @@ bio_file *bio_open_read(const char *path)
 {
     bio_file *f = calloc(1, sizeof *f);
     if (!f) return NULL;
-    if (strcmp(path, "-") == 0) { f->fp = stdin; widen_pipe(stdin); } else { f->fp = fopen(path, "rb"); f->own_fp = 1; }
+    if (strcmp(path, "-") == 0) {
+        f->fp = stdin; widen_pipe(stdin);
+        f->unbuffered = setvbuf(stdin, NULL, _IONBF, 0) == 0;      /* every read asks for >= 64 KB; lets the read-ahead thread use read(2) on a pipe */
+    } else { f->fp = fopen(path, "rb"); f->own_fp = 1; }
     if (!f->fp) { free(f); return NULL; }
     f->in = malloc(IN_CHUNK);
     if (!f->in) { if (f->own_fp) fclose(f->fp); free(f); return NULL; }
@@ -466,14 +490,24 @@ bio_hdr *bio_hdr_dup(const bio_hdr *s)
     h->text = xstrndup(s->text ? s->text : "", s->l_text); h->l_text = s->l_text; h->n_targets = s->n_targets;
     h->target_name = malloc(sizeof(char *) * (size_t)(s->n_targets ? s->n_targets : 1));
     h->target_len = malloc(sizeof(uint32_t) * (size_t)(s->n_targets ? s->n_targets : 1));
-    for (int32_t i = 0; i < s->n_targets; i++) { h->target_name[i] = xstrndup(s->target_name[i], strlen(s->target_name[i])); h->target_len[i] = s->target_len[i]; }
+    size_t total = 1;
+    for (int32_t i = 0; i < s->n_targets; i++) total += strlen(s->target_name[i]) + 1;
+    h->name_arena = malloc(total);
+    if (!h->text || !h->target_name || !h->target_len || !h->name_arena) { h->n_targets = 0; bio_hdr_free(h); return NULL; }
+    char *a = h->name_arena;
+    for (int32_t i = 0; i < s->n_targets; i++) {
+        const size_t l = strlen(s->target_name[i]) + 1;
+        memcpy(a, s->target_name[i], l); h->target_name[i] = a; a += l;
+        h->target_len[i] = s->target_len[i];
+    }
     return h;
 }
 
 void bio_hdr_free(bio_hdr *h)
 {
     if (!h) return;
-    for (int32_t i = 0; i < h->n_targets; i++) free(h->target_name[i]);
+    if (h->name_arena) free(h->name_arena);
+    else for (int32_t i = 0; i < h->n_targets; i++) free(h->target_name[i]);
     free(h->target_name); free(h->target_len); free(h->text); free(h);
 }
 
@@ -601,15 +635,38 @@ bio_hdr *bio_read_header(bio_file *f)
         h->target_name = calloc((size_t)(n_ref ? n_ref : 1), sizeof(char *));
         h->target_len = calloc((size_t)(n_ref ? n_ref : 1), sizeof(uint32_t));
         if (!h->target_name || !h->target_len) { bio_hdr_free(h); set_err(f, "out of memory"); return NULL; }
+        /* names go into one arena (grown geometrically; pointers are fixed up at the end), read straight out of the
+           decompressed window whenever a whole entry is inside it */
+        size_t acap = (size_t)(n_ref < (1 << 20) ? n_ref : (1 << 20)) * 16 + 64, alen = 0;      /* n_ref is only a claim until the entries have been read */
+        char *arena = malloc(acap);
+        size_t *aoff = malloc(sizeof(size_t) * (size_t)(n_ref ? n_ref : 1));
+        if (!arena || !aoff) { free(arena); free(aoff); bio_hdr_free(h); set_err(f, "out of memory"); return NULL; }
         for (int32_t i = 0; i < n_ref; i++) {
-            if (rd_read(f, b, 4) != 1) { bio_hdr_free(h); set_err(f, "truncated BAM header"); return NULL; }
-            uint32_t ln = le32(b);
-            if (ln == 0 || ln > (1u << 20)) { bio_hdr_free(h); set_err(f, "corrupt BAM header (l_name)"); return NULL; }
-            char *nm = malloc((size_t)ln + 1);
-            if (!nm || rd_read(f, (uint8_t *)nm, ln) != 1 || rd_read(f, b, 4) != 1) { free(nm); bio_hdr_free(h); set_err(f, nm ? "truncated BAM header" : "out of memory"); return NULL; }
-            nm[ln] = 0; h->target_name[i] = nm; h->target_len[i] = le32(b);
-            h->n_targets = i + 1;
+            uint32_t ln; const uint8_t *src = NULL;
+            if (f->dec_len - f->dec_pos >= 4 && (ln = le32(f->dec + f->dec_pos)) <= (1u << 20) && f->dec_len - f->dec_pos >= 8 + (size_t)ln) {
+                src = f->dec + f->dec_pos + 4;                              /* whole entry in the window */
+            } else {
+                if (rd_read(f, b, 4) != 1) { free(arena); free(aoff); bio_hdr_free(h); set_err(f, "truncated BAM header"); return NULL; }
+                ln = le32(b);
+            }
+            if (ln == 0 || ln > (1u << 20)) { free(arena); free(aoff); bio_hdr_free(h); set_err(f, "corrupt BAM header (l_name)"); return NULL; }
+            if (alen + ln + 1 > acap) {
+                while (alen + ln + 1 > acap) acap *= 2;
+                char *na = realloc(arena, acap);
+                if (!na) { free(arena); free(aoff); bio_hdr_free(h); set_err(f, "out of memory"); return NULL; }
+                arena = na;
+            }
+            if (src) { memcpy(arena + alen, src, ln); h->target_len[i] = le32(src + ln); f->dec_pos += 8 + (size_t)ln; }
+            else {
+                if (rd_read(f, (uint8_t *)arena + alen, ln) != 1 || rd_read(f, b, 4) != 1) { free(arena); free(aoff); bio_hdr_free(h); set_err(f, "truncated BAM header"); return NULL; }
+                h->target_len[i] = le32(b);
+            }
+            arena[alen + ln] = 0;
+            aoff[i] = alen; alen += (size_t)ln + 1;
         }
+        for (int32_t i = 0; i < n_ref; i++) h->target_name[i] = arena + aoff[i];
+        h->name_arena = arena; h->n_targets = n_ref;
+        free(aoff);
         return h;
     }
     /* SAM text: header lines start with '@'; the first alignment line is kept for the first bio_read_record */
@@ -988,21 +1045,28 @@ bio_file *bio_open_write(const char *path, const char *mode)
 int bio_write_header(bio_file *f, const bio_hdr *h)
 {
     if (!f->w_header) return 0;
-    if (!f->w_bam) return fwrite(h->text, 1, h->l_text, f->fp) == h->l_text ? 0 : -1;
-    uint8_t b[8];
-    memcpy(b, "BAM\1", 4); put32(b + 4, (uint32_t)h->l_text);
-    if (w_bytes(f, b, 8) || w_bytes(f, (const uint8_t *)h->text, h->l_text)) return -1;
-    put32(b, (uint32_t)h->n_targets);
-    if (w_bytes(f, b, 4)) return -1;
+    if (!f->w_bam) return fwrite(h->text, 1, h->l_text, f->fp) == h->l_text && fflush(f->fp) == 0 ? 0 : -1;
+    /* the binary header in one buffer, through the bulk writer (blocks packed on the worker threads: the header of a 1 M-sequence
+       catalogue is 40 MB) -- the same bytes as writing it field by field */
+    size_t total = 12 + h->l_text;
+    for (int32_t i = 0; i < h->n_targets; i++) total += 8 + strlen(h->target_name[i]) + 1;
+    uint8_t *buf = malloc(total), *p = buf;
+    if (!buf) return -1;
+    memcpy(p, "BAM\1", 4); put32(p + 4, (uint32_t)h->l_text); p += 8;
+    memcpy(p, h->text, h->l_text); p += h->l_text;
+    put32(p, (uint32_t)h->n_targets); p += 4;
     for (int32_t i = 0; i < h->n_targets; i++) {
-        size_t ln = strlen(h->target_name[i]) + 1;
-        put32(b, (uint32_t)ln);
-        if (w_bytes(f, b, 4) || w_bytes(f, (const uint8_t *)h->target_name[i], ln)) return -1;
-        put32(b, h->target_len[i]);
-        if (w_bytes(f, b, 4)) return -1;
+        const size_t ln = strlen(h->target_name[i]) + 1;
+        put32(p, (uint32_t)ln); memcpy(p + 4, h->target_name[i], ln); put32(p + 4 + ln, h->target_len[i]);
+        p += 8 + ln;
     }
+    const int wrc = bio_write_raw(f, buf, total);
+    free(buf);
+    if (wrc) return -1;
     if (f->wlen) { if (bgzf_flush_block(f, f->wbuf, f->wlen)) return -1; f->wlen = 0; }   /* header in its own block(s), as htslib */
-    return 0;
+    /* nothing of the header may wait in the stdio buffer for the first records: a downstream process parses the header (and
+       starts up its own device) while this one works on its first chunk */
+    return fflush(f->fp) ? -1 : 0;
 }
 
 int bio_write_record(bio_file *f, const bio_hdr *h, const uint8_t *rec, size_t len)

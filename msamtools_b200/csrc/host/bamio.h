@@ -19,6 +19,8 @@ typedef struct bio_hdr {
     int32_t   n_targets;
     char    **target_name;
     uint32_t *target_len;
+    char     *name_arena;    /* when set, every target_name[i] points into this one block (a 1 M-sequence catalogue is read,
+                                copied and freed as one allocation instead of a million); NULL: names are separate mallocs */
 } bio_hdr;
 
 typedef struct bio_file bio_file;

@@ -56,3 +56,23 @@ def test_reference_arm_runs_on_the_host(tmp_path):
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["config_index"] == 12
     assert line["cuda_library_mapped"] is False                                      # the arm's own process never mapped the CUDA library
+
+
+def test_ingest_leg_against_the_null_device(tmp_path):
+    """bench.py's file-to-result leg (BGZF file -> `filter | profile` through the CLI, per-phase timers of both processes parsed
+    from stderr) run end to end on a build of the CLI over the null device of tests/hostprof (no GPU here): host logic only"""
+    import shutil
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "hostprof"))
+    import run as hostprof
+    cli = hostprof.build()
+    cfg = bench.CONFIGS[12]
+    plan = bench.chunk_plan(cfg, 60_000, 60_000, 1)
+    raw, off = bench.gen_chunk(cfg, 0, 0, plan)
+    tlen = bench.target_lengths(cfg)
+    out = bench.ingest_entry(cfg, plan, tlen, raw[:int(off[-1])], off, cli=cli, thread_counts=(1, 4))
+    assert set(out["threads"]) == {"1", "4"}
+    for t in out["threads"].values():
+        assert t["rc"] == 0 and t["file_to_result_M_aln_per_s"] > 0 and t["inflate_gbs"] > 0
+        assert {"filter: open + header", "filter: stream", "profile: stream", "profile: table"} <= set(t["phases_s"])
