@@ -469,7 +469,7 @@ def ingest_entry(cfg, plan, tlen, raw, off, cli=None, env_extra=None, thread_cou
     def phases(err):
         """"# phase <command> <name>: <seconds> s" lines of both processes (MSAMTOOLS_TIMING=1)"""
         out = {}
-        for c, nm, sec in re.findall(r"^# phase (\S+) (.+?): ([0-9.]+) s$", err, flags=re.M):
+        for c, nm, sec in re.findall(r"^# phase (\S+) (.+?): ([0-9.]+) s\b", err, flags=re.M):
             out[f"{c}: {nm}"] = float(sec)
         return out
 
