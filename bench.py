@@ -430,7 +430,7 @@ def write_bgzf_threads(path, blobs, level=1, threads=8):
     return len(data)
 
 
-def ingest_entry(cfg, plan, tlen, raw, off, cli=None, env_extra=None, thread_counts=(1, 4, 16)):
+def ingest_entry(cfg, plan, tlen, raw, off, cli=None, env_extra=None, thread_counts=(1, 4, 16), with_reference=True):
     """R3 of SURVEY 8d, reported separately from the kernels (north_star): a level-1 BGZF BAM of the workload on tmpfs through the
     drop-in CLI (`filter ... | profile ...`, file to result) with 1 / 4 / 16 host threads -- host read+inflate GB/s and the
     per-phase wall times from the CLI's own timers, alignments/s by wall clock -- and the reference's object code on the same file.
@@ -484,7 +484,7 @@ def ingest_entry(cfg, plan, tlen, raw, off, cli=None, env_extra=None, thread_cou
             out["threads"][str(thr)] = {"file_to_result_M_aln_per_s": n / dt / 1e6, "wall_s": dt, "rc": rc,
                                         "inflate_gbs": (float(m.group(1)) / float(m.group(2))) if m and float(m.group(2)) > 0 else None,
                                         "phases_s": phases(err)}
-        if have_ref_binary():
+        if have_ref_binary() and with_reference:
             dt, _, rc = pipe(REF_BIN, dict(os.environ))
             out["reference_single_pipe"] = {"file_to_result_M_aln_per_s": n / dt / 1e6, "wall_s": dt, "rc": rc,
                                             "note": "the reference's object code on the same file: one process per command, single-threaded inflate (shim I/O)"}

@@ -558,6 +558,7 @@ static void open_input(run_t *r, const char *infile)
     r->path = infile;
     r->in = bio_open_read(infile);
     if (!r->in) mDie("Cannot open %s for reading", infile);
+    warm_start();                                /* the device starts up while the header is read and parsed */
     bio_set_threads(r->in, host_threads());      /* BGZF blocks are inflated on worker threads */
     r->hdr = bio_read_header(r->in);
     if (!r->hdr) { if (bio_error(r->in)[0]) mDie("Cannot read header from %s: %s", infile, bio_error(r->in)); mDie("Cannot read header from %s", infile); }
@@ -626,7 +627,6 @@ static int filter_main(int argc, char *argv[])
 
     run_t r; memset(&r, 0, sizeof r);
     phase(sub, NULL);
-    warm_start();
     open_input(&r, a_file->filename[0]);
     phase(sub, "open + header");
     const int hit = a_uniq->count > 0 ? MSG_HIT_UNIQUE : a_best->count > 0 ? MSG_HIT_BEST : MSG_HIT_NONE;
@@ -774,7 +774,6 @@ static int profile_main(int argc, char *argv[])
 
     run_t r; memset(&r, 0, sizeof r);
     phase(sub, NULL);
-    warm_start();
     open_input(&r, a_file->filename[0]);
     phase(sub, "open + header");
     chunk_fill(&r.chunk, r.in, r.hdr, COORD_ORDER_CHECK_RECORDS, (size_t)-1, &r.eof);
@@ -972,7 +971,6 @@ static int coverage_main(int argc, char *argv[])
     gzp *out = gzp_open(a_out->sval[0], host_threads());
     if (!out) mDie("Cannot open %s for writing", a_out->sval[0]);
     run_t r; memset(&r, 0, sizeof r);
-    warm_start();
     open_input(&r, a_file->filename[0]);
     const int T = r.hdr->n_targets;
     r.cfg.do_filter = 0; r.cfg.want_coverage = 1; r.cfg.coverage_summary = a_summary->count > 0; r.cfg.n_targets = T; r.cfg.n_features = T; r.cfg.target_len = r.hdr->target_len;

@@ -1,7 +1,7 @@
 /*
  * gzpar.h -- gzip writer whose deflate work runs on worker threads (C99, zlib).
  *
- * The reference writes its tables through gzopen/gzprintf (msam_profile.c:936-1012, mMatrix.c:359-376,
+ * The reference writes its tables through gzopen/gzprintf (msam_profile.c:880-1012, mMatrix.c:359-376,
  * msam_coverage.c:143-219): one thread formats and deflates row by row.  For a 1 M-gene catalogue that is seconds per
  * profile; here the text is collected in large blocks, the blocks are deflated concurrently (each primed with the last
  * 32 KB of its predecessor as dictionary and closed with a sync flush, the way pigz does) and written in order as ONE

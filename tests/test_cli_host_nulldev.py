@@ -127,3 +127,16 @@ def test_small_input_and_sam_output(cli, tmp_path):
     assert r.returncode == 0, r.stderr.decode()
     got = r.stdout.decode().splitlines()
     assert got == [l for l in sam.splitlines()[2:] if int(l.split("\t")[3]) % 5 != 1]      # POS is 0-based in the record: 1-based % 5 != 1
+
+
+def test_sam_text_through_the_ring(cli):
+    """more SAM records than the pre-flight sample: the record-wise reader feeds the ring (growable buffers), the writer thread formats SAM"""
+    seq, q = "A" * 60, "I" * 60
+    lines = ["@HD\tVN:1.6", "@SQ\tSN:A\tLN:100000000", "@SQ\tSN:B\tLN:1000"]
+    for i in range(130_000):
+        lines.append(f"q{i // 3:06d}\t0\tA\t{1 + i * 7 % 1000003}\t60\t60M\t*\t0\t0\t{seq}\t{q}\tAS:i:50\tNM:i:0")
+    e = dict(os.environ, MSAMTOOLS_CHUNK_RECORDS="9000", MSAMTOOLS_THREADS="3")
+    r = subprocess.run([cli, "filter", "-S", "-h", "--besthit", "-"], input=("\n".join(lines) + "\n").encode(), capture_output=True, env=e)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]
+    out = [l for l in r.stdout.decode().splitlines() if not l.startswith("@")]
+    assert out == [l for l in lines[3:] if (int(l.split("\t")[3]) - 1) % 5 != 0]
