@@ -290,7 +290,9 @@ typedef struct {
     chunk_t buf[NBUF];
     int state[NBUF];                      /* 0 free, 1 posted */
     int posted_last;                      /* the posted chunk with this index is the final one (-1: not yet known) */
-    int bulk, pin;
+    int bulk, pin;                        /* pin: page-lock the chunk buffers (msg_host_alloc) */
+    int pin_later;                        /* ... only those after the first: an input of unknown size (a pipe) that needs a second
+                                             buffer is at least a chunk long, and page-locking pays from there on */
     pthread_mutex_t mu; pthread_cond_t cv;
 } ring_t;
 
@@ -337,7 +339,7 @@ static void *reader_main(void *arg)
             pthread_mutex_lock(&g->mu);
             while (g->state[nxt]) pthread_cond_wait(&g->cv, &g->mu);
             pthread_mutex_unlock(&g->mu);
-            ring_buffer_alloc(g, nxt, g->pin);
+            ring_buffer_alloc(g, nxt, g->pin || g->pin_later);
             chunk_t *d = &g->buf[nxt];
             const size_t base = (size_t)c->off[k], tail = c->len - base;
             if (!d->fixed && tail > d->cap) { d->raw = realloc(d->raw, tail + (1 << 20)); d->cap = tail + (1 << 20); if (!d->raw) mDie("Out of memory"); }
@@ -357,6 +359,7 @@ static void *reader_main(void *arg)
 typedef struct {
     run_t *r;
     uint8_t *buf[2]; size_t cap[2], len[2];
+    int pinned[2], want_pinned;           /* page-locked output buffers (device -> host copies by DMA) when the input buffers are */
     int state[2];                         /* 0 free, 1 posted */
     int done, failed;
     double t_write;
@@ -409,7 +412,18 @@ static void pull_kept_records(run_t *r, msg_ctx *ctx, wring_t *w, int *wcur)
     const int failed = w->failed;
     pthread_mutex_unlock(&w->mu);
     if (failed) mDie("Cannot write alignment record");
-    if (nb > w->cap[i]) { free(w->buf[i]); w->cap[i] = nb + nb / 4 + 4096; w->buf[i] = malloc(w->cap[i]); if (!w->buf[i]) mDie("Out of memory"); }
+    if (nb > w->cap[i]) {
+        if (w->pinned[i]) msg_host_free(w->buf[i]); else free(w->buf[i]);
+        w->buf[i] = NULL; w->pinned[i] = 0;
+        w->cap[i] = nb + nb / 4 + 4096;
+        if (w->want_pinned) {
+            /* kept records never exceed the chunk (--rescore may add an AS tag per record: then the buffer is simply replaced) */
+            void *pm = NULL;
+            const size_t pcap = w->cap[i] > CHUNK_BYTES + ((size_t)64 << 20) ? w->cap[i] : CHUNK_BYTES + ((size_t)64 << 20);
+            if (msg_host_alloc(r->cfg.device, pcap, &pm) == MSG_OK) { w->buf[i] = pm; w->cap[i] = pcap; w->pinned[i] = 1; }
+        }
+        if (!w->buf[i]) { w->buf[i] = malloc(w->cap[i]); if (!w->buf[i]) mDie("Out of memory"); }
+    }
     if (msg_pull_records(ctx, w->buf[i], w->cap[i], &nb, &nr)) gpu_die(ctx);
     w->len[i] = nb;
     if (!w->r) { if (emit_records(r, w->buf[i], nb)) mDie("Cannot write alignment record"); return; }
@@ -483,9 +497,11 @@ static msg_ctx *run_stream(run_t *r)
             struct stat sb;
             const char *e = getenv("MSAMTOOLS_PINNED");
             if (e) g.pin = atoi(e) != 0;
-            else g.pin = r->path && strcmp(r->path, "-") != 0 && stat(r->path, &sb) == 0 && (size_t)sb.st_size >= ((size_t)192 << 20);
+            else if (r->path && strcmp(r->path, "-") != 0 && stat(r->path, &sb) == 0 && S_ISREG(sb.st_mode)) g.pin = (size_t)sb.st_size >= ((size_t)192 << 20);
+            else g.pin_later = 1;
         }
         ring_buffer_alloc(&g, 0, g.pin);                     /* the others are allocated by the reader thread when it first needs them */
+        w.want_pinned = g.pin;
         {   /* the pre-flight records open buffer 0 */
             chunk_t *c = &g.buf[0], *s0 = &r->chunk;
             if (c->fixed) {
@@ -540,7 +556,7 @@ static msg_ctx *run_stream(run_t *r)
         }
         pthread_mutex_destroy(&g.mu); pthread_cond_destroy(&g.cv);
     }
-    free(w.buf[0]); free(w.buf[1]);
+    for (int i = 0; i < 2; i++) { if (w.pinned[i]) msg_host_free(w.buf[i]); else free(w.buf[i]); }
     pthread_mutex_destroy(&w.mu); pthread_cond_destroy(&w.cv);
     if (getenv("MSAMTOOLS_TIMING")) {      /* host-ingest vs GPU time, reported separately (BASELINE.json north_star) */
         uint64_t ib = 0; double isec = 0; msg_timing tm;

@@ -59,6 +59,7 @@ def bam(tmp_path_factory):
 
 
 ENVS = [dict(MSAMTOOLS_CHUNK_RECORDS="7000", MSAMTOOLS_THREADS="4"),          # many chunks: ring, tails, writer hand-over
+        dict(MSAMTOOLS_CHUNK_RECORDS="9000", MSAMTOOLS_THREADS="3", MSAMTOOLS_PINNED="1"),   # buffers from msg_host_alloc (input ring and output)
         dict(MSAMTOOLS_CHUNK_RECORDS="50000", MSAMTOOLS_THREADS="1"),        # streaming inflate, record index without threads
         dict(MSAMTOOLS_THREADS="8")]                                          # default chunk size: one chunk
 
