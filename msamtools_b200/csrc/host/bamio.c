@@ -1005,6 +1005,7 @@ int bio_write_raw(bio_file *f, const uint8_t *p, size_t n)
     }
     enum { BATCH = 256 };
     int nthr = f->threads > 1 ? f->threads : 1;
+    if (f->w_level == 0 && nthr > 4) nthr = 4;               /* stored blocks are a memcpy + CRC32: four threads outrun any pipe or disk */
     while (n >= BGZF_BLOCK) {
         size_t nblk = n / BGZF_BLOCK; if (nblk > BATCH) nblk = BATCH;
         if (!f->wout) { f->wout = malloc((size_t)BATCH * BGZF_OUT_STRIDE); f->wolen = malloc(sizeof(size_t) * BATCH); if (!f->wout || !f->wolen) return -1; }
