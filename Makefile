@@ -9,7 +9,7 @@ SYNTH   := msamtools_b200/libmsamsynth.so
 HOSTLIB := msamtools_b200/libmsamhost.so
 
 CLI     := msamtools_b200/bin/msamtools
-HOSTSRC := $(CSRC)/host/bamio.c $(CSRC)/host/finflate.c $(CSRC)/host/gzpar.c $(CSRC)/host/margs.c $(CSRC)/host/keyorder.c $(CSRC)/host/recwalk.c
+HOSTSRC := $(CSRC)/host/bamio.c $(CSRC)/host/finflate.c $(CSRC)/host/crc32x.c $(CSRC)/host/gzpar.c $(CSRC)/host/margs.c $(CSRC)/host/keyorder.c $(CSRC)/host/recwalk.c
 
 all: $(LIB) $(SYNTH) $(HOSTLIB) $(CLI) oracle
 

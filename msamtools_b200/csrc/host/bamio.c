@@ -4,6 +4,7 @@
 #endif
 #include "bamio.h"
 #include "finflate.h"
+#include "crc32x.h"
 #include <ctype.h>
 #include <errno.h>
 #include <fcntl.h>
@@ -200,14 +201,14 @@ static void *bgzf_worker(void *arg)
         if (b->isize == 0) continue;
         /* fast one-shot decoder first (finflate.c); anything it declines, or whose CRC does not match, goes through zlib */
         if (fi_inflate(j->in + b->in_off, b->in_len, j->out + b->out_off, b->isize) == 0 &&
-            (uint32_t)crc32(crc32(0L, NULL, 0), j->out + b->out_off, b->isize) == b->crc) { j->n_fast++; continue; }
+            crc32x(0, j->out + b->out_off, b->isize) == b->crc) { j->n_fast++; continue; }
         j->n_zlib++;
         inflateReset(&zs);
         zs.next_in = (Bytef *)(j->in + b->in_off); zs.avail_in = (uInt)b->in_len;
         zs.next_out = j->out + b->out_off; zs.avail_out = b->isize;
         int rc = inflate(&zs, Z_FINISH);
         if (rc != Z_STREAM_END || zs.avail_out != 0) { j->err = 1; break; }
-        if ((uint32_t)crc32(crc32(0L, NULL, 0), j->out + b->out_off, b->isize) != b->crc) { j->err = 1; break; }
+        if (crc32x(0, j->out + b->out_off, b->isize) != b->crc) { j->err = 1; break; }
     }
     inflateEnd(&zs);
     return NULL;
@@ -950,7 +951,7 @@ static size_t bgzf_pack_block(int level, z_stream *zs, const uint8_t *data, size
         if (rc != Z_STREAM_END) return 0;
     }
     put16(out + 16, (uint32_t)(clen + 18 + 8 - 1));
-    put32(out + 18 + clen, (uint32_t)crc32(crc32(0L, NULL, 0), data, (uInt)n));
+    put32(out + 18 + clen, crc32x(0, data, n));
     put32(out + 18 + clen + 4, (uint32_t)n);
     return clen + 26;
 }

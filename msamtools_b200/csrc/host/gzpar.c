@@ -1,5 +1,6 @@
 /* gzpar.c -- gzip writer with concurrent deflate.  See gzpar.h. */
 #include "gzpar.h"
+#include "crc32x.h"
 #include <pthread.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -39,7 +40,7 @@ static void *gzp_worker(void *arg)
         const int rc = deflate(&zs, last ? Z_FINISH : Z_SYNC_FLUSH);
         if ((last ? rc != Z_STREAM_END : rc != Z_OK) || zs.avail_in != 0 || zs.avail_out == 0) { j->err = 1; break; }
         g->olen[k] = GZP_STRIDE - zs.avail_out;
-        g->bcrc[k] = crc32(crc32(0L, Z_NULL, 0), (const Bytef *)g->pend + o, (uInt)n);
+        g->bcrc[k] = crc32x(0, g->pend + o, n);
     }
     deflateEnd(&zs);
     return NULL;

@@ -24,7 +24,7 @@ def build():
     subprocess.check_call(["gcc", "-O2", "-g", "-std=gnu99", "-fPIC", "-shared", "-o", lib, os.path.join(HERE, "nulldev.c")])
     cs = os.path.join(ROOT, "msamtools_b200", "csrc")
     cli = os.path.join(BUILD, "msamtools")
-    src = [os.path.join(cs, "cli", "msamtools_main.c")] + [os.path.join(cs, "host", f) for f in ("bamio.c", "finflate.c", "gzpar.c", "margs.c", "keyorder.c", "recwalk.c")]
+    src = [os.path.join(cs, "cli", "msamtools_main.c")] + [os.path.join(cs, "host", f) for f in ("bamio.c", "finflate.c", "crc32x.c", "gzpar.c", "margs.c", "keyorder.c", "recwalk.c")]
     subprocess.check_call(["gcc", "-O2", "-g", "-std=gnu99", "-Wall", "-Wextra", "-o", cli] + src +
                           ["-L" + BUILD, "-lmsamtools_b200", "-Wl,-rpath," + BUILD, "-lz", "-lm", "-lpthread"])
     return cli

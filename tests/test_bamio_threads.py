@@ -21,7 +21,7 @@ def harness(tmp_path_factory, request):
     d = tmp_path_factory.mktemp("bamio")
     exe = str(d / "reader")
     small = ["-DIO_BATCH=((size_t)70001)"] if "70001" in request.param else []
-    srcs = [os.path.join(ROOT, "tests", "c", "bamio_read_harness.c"), os.path.join(HOST, "bamio.c")]
+    srcs = [os.path.join(ROOT, "tests", "c", "bamio_read_harness.c"), os.path.join(HOST, "bamio.c"), os.path.join(HOST, "crc32x.c")]
     if os.path.exists(os.path.join(HOST, "finflate.c")):
         srcs.append(os.path.join(HOST, "finflate.c"))
     subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", HOST] + small + srcs +
@@ -103,7 +103,7 @@ def bulk(tmp_path_factory, request):
     d = tmp_path_factory.mktemp("bamio_bulk")
     exe = str(d / "bulk")
     small = ["-DIO_BATCH=((size_t)70001)"] if "70001" in request.param else []
-    srcs = [os.path.join(ROOT, "tests", "c", "bamio_bulk_harness.c"), os.path.join(HOST, "bamio.c"), os.path.join(HOST, "finflate.c")]
+    srcs = [os.path.join(ROOT, "tests", "c", "bamio_bulk_harness.c"), os.path.join(HOST, "bamio.c"), os.path.join(HOST, "finflate.c"), os.path.join(HOST, "crc32x.c")]
     subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", HOST] + small + srcs +
                    ["-lz", "-lpthread", "-o", exe], check=True)
     return exe, d

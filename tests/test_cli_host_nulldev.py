@@ -20,7 +20,7 @@ from conftest import ROOT
 sys.path.insert(0, os.path.join(ROOT, "tests", "hostprof"))
 CS = os.path.join(ROOT, "msamtools_b200", "csrc")
 HOSTSRC = [os.path.join(CS, "cli", "msamtools_main.c")] + [os.path.join(CS, "host", f) for f in
-                                                          ("bamio.c", "finflate.c", "gzpar.c", "margs.c", "keyorder.c", "recwalk.c")]
+                                                          ("bamio.c", "finflate.c", "crc32x.c", "gzpar.c", "margs.c", "keyorder.c", "recwalk.c")]
 
 
 def build(d, san):

@@ -21,7 +21,7 @@ def harness(tmp_path_factory):
     d = tmp_path_factory.mktemp("gzpar")
     exe = str(d / "gzp")
     subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", HOST,
-                    os.path.join(ROOT, "tests", "c", "gzpar_harness.c"), os.path.join(HOST, "gzpar.c"), "-lz", "-lpthread", "-o", exe], check=True)
+                    os.path.join(ROOT, "tests", "c", "gzpar_harness.c"), os.path.join(HOST, "gzpar.c"), os.path.join(HOST, "crc32x.c"), "-lz", "-lpthread", "-o", exe], check=True)
     return exe, d
 
 
