@@ -291,8 +291,6 @@ typedef struct {
     int state[NBUF];                      /* 0 free, 1 posted */
     int posted_last;                      /* the posted chunk with this index is the final one (-1: not yet known) */
     int bulk, pin;                        /* pin: page-lock the chunk buffers (msg_host_alloc) */
-    int pin_later;                        /* ... only those after the first: an input of unknown size (a pipe) that needs a second
-                                             buffer is at least a chunk long, and page-locking pays from there on */
     pthread_mutex_t mu; pthread_cond_t cv;
 } ring_t;
 
@@ -339,7 +337,7 @@ static void *reader_main(void *arg)
             pthread_mutex_lock(&g->mu);
             while (g->state[nxt]) pthread_cond_wait(&g->cv, &g->mu);
             pthread_mutex_unlock(&g->mu);
-            ring_buffer_alloc(g, nxt, g->pin || g->pin_later);
+            ring_buffer_alloc(g, nxt, g->pin);
             chunk_t *d = &g->buf[nxt];
             const size_t base = (size_t)c->off[k], tail = c->len - base;
             if (!d->fixed && tail > d->cap) { d->raw = realloc(d->raw, tail + (1 << 20)); d->cap = tail + (1 << 20); if (!d->raw) mDie("Out of memory"); }
@@ -497,8 +495,9 @@ static msg_ctx *run_stream(run_t *r)
             struct stat sb;
             const char *e = getenv("MSAMTOOLS_PINNED");
             if (e) g.pin = atoi(e) != 0;
-            else if (r->path && strcmp(r->path, "-") != 0 && stat(r->path, &sb) == 0 && S_ISREG(sb.st_mode)) g.pin = (size_t)sb.st_size >= ((size_t)192 << 20);
-            else g.pin_later = 1;
+            else g.pin = r->path && strcmp(r->path, "-") != 0 && stat(r->path, &sb) == 0 && S_ISREG(sb.st_mode) && (size_t)sb.st_size >= ((size_t)192 << 20);
+            /* (a pipe stays pageable: page-locking a buffer stalls the reader thread for ~0.1 s, and behind a pipe the staged
+               copies are not what limits the stream) */
         }
         ring_buffer_alloc(&g, 0, g.pin);                     /* the others are allocated by the reader thread when it first needs them */
         w.want_pinned = g.pin;
