@@ -4,10 +4,14 @@
  * BGZF blocks are small (<= 64 KiB), independent and carry their inflated size and CRC32, so a
  * decoder can be one-shot and strict: decode `in_len` bytes into exactly `out_len` bytes or say
  * "no" -- the caller (bamio.c) then hands the block to zlib, and checks the CRC either way.  What
- * makes it faster than a streaming inflate: a 64-bit bit buffer refilled eight bytes at a time,
- * two-level lookup tables (11 / 8 primary bits) whose entries already hold base value and
- * extra-bit count, up to two literals per refill, and 8-byte match copies.  Never writes outside
- * [out, out + out_len): neighbouring blocks are inflated by other threads.
+ * makes it faster than a streaming inflate: a 64-bit bit buffer refilled eight bytes at a time
+ * (one branch-free refill per symbol: >= 56 bits cover a length code with its extra bits AND the
+ * distance code with its extra bits), two-level lookup tables (11 / 8 primary bits) whose entries
+ * hold the base value and the TOTAL number of bits to consume (code + extra bits: one shift per
+ * symbol, the extra bits are cut out of the saved buffer), the table entry of the NEXT symbol
+ * loaded before the current match is copied (so the literal-or-match branch, which is close to a
+ * coin flip on BAM data, resolves as soon as it is reached), and 8-byte match copies.  Never writes
+ * outside [out, out + out_len): neighbouring blocks are inflated by other threads.
  */
 #include "finflate.h"
 #include <string.h>
@@ -17,7 +21,8 @@
 #define LIT_TABSZ 8192   /* 2^11 + at most 286 subtables of <= 16 entries */
 #define DST_TABSZ 4352   /* 2^8  + at most 30 subtables of <= 128 entries */
 
-/* table entry: [0,8) bits to drop | [8,13) extra-bit count or subtable index bits | 13 literal | 14 end of block | 15 link | [16,32) value */
+/* table entry: [0,8) bits to consume at this table level = code bits + extra bits (0: invalid) | [8,12) the code bits among them
+ * (link entries: subtable index bits) | 13 literal | 14 end of block | 15 link | [16,32) value (literal, base, subtable base) */
 #define E_LITERAL (1u << 13)
 #define E_EOB     (1u << 14)
 #define E_LINK    (1u << 15)
@@ -42,14 +47,21 @@ static uint32_t sym_entry(int kind, int sym)
     if (kind == 0) {                                   /* literal / length alphabet */
         if (sym < 256) return E_LITERAL | ((uint32_t)sym << 16);
         if (sym == 256) return E_EOB;
-        if (sym <= 285) return ((uint32_t)LEN_XBITS[sym - 257] << 8) | ((uint32_t)LEN_BASE[sym - 257] << 16);
+        if (sym <= 285) return (uint32_t)LEN_BASE[sym - 257] << 16;
         return 0xffffffffu;                            /* 286, 287: never valid in a stream */
     }
     if (kind == 1) {                                   /* distance alphabet */
-        if (sym < 30) return ((uint32_t)DST_XBITS[sym] << 8) | ((uint32_t)DST_BASE[sym] << 16);
+        if (sym < 30) return (uint32_t)DST_BASE[sym] << 16;
         return 0xffffffffu;
     }
     return (uint32_t)sym << 16;                        /* code-length alphabet: plain symbol */
+}
+
+static uint32_t sym_xbits(int kind, int sym)
+{
+    if (kind == 0) return sym >= 257 && sym <= 285 ? LEN_XBITS[sym - 257] : 0u;
+    if (kind == 1) return sym < 30 ? DST_XBITS[sym] : 0u;
+    return 0u;
 }
 
 /* Canonical Huffman code -> two-level table.  Returns 0, or -1 for anything but a complete code
@@ -87,7 +99,8 @@ static int build_table(const uint8_t *lens, int nsym, int kind, int tbits, uint3
         if (l <= tbits) {
             const uint32_t e = sym_entry(kind, s);
             if (e == 0xffffffffu) continue;            /* unusable symbol: its slots stay invalid */
-            for (uint32_t k = r; k < psize; k += 1u << l) tab[k] = e | (uint32_t)l;
+            const uint32_t ent = e | ((uint32_t)l + sym_xbits(kind, s)) | ((uint32_t)l << 8);
+            for (uint32_t k = r; k < psize; k += 1u << l) tab[k] = ent;
         } else {
             const uint32_t slot = r & (psize - 1);
             if (l - tbits > sublen[slot]) sublen[slot] = (uint8_t)(l - tbits);
@@ -110,8 +123,9 @@ static int build_table(const uint8_t *lens, int nsym, int kind, int tbits, uint3
         const uint32_t e = sym_entry(kind, s);
         if (e == 0xffffffffu) continue;
         const uint32_t r = codes[s], link = tab[r & (psize - 1)];
-        const uint32_t base = link >> 16, sbits = (link >> 8) & 31u, rem = (uint32_t)(l - tbits);
-        for (uint32_t k = r >> tbits; k < (1u << sbits); k += 1u << rem) tab[base + k] = e | rem;
+        const uint32_t base = link >> 16, sbits = (link >> 8) & 15u, rem = (uint32_t)(l - tbits);
+        const uint32_t ent = e | (rem + sym_xbits(kind, s)) | (rem << 8);
+        for (uint32_t k = r >> tbits; k < (1u << sbits); k += 1u << rem) tab[base + k] = ent;
     }
     return 0;
 }
@@ -187,86 +201,78 @@ int fi_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
                 if (build_table(lens + hlit, (int)hdist, 1, DST_TBITS, dst_tab, DST_TABSZ)) return -1;
             }
             /* ---- symbols */
+            /* value of a length / distance symbol: base + the extra bits, which sit in the saved buffer right behind the code bits */
+#define XVAL(e, saved) (((e) >> 16) + ((uint32_t)((saved) >> (((e) >> 8) & 15u)) & ((1u << (((e) & 0xffu) - (((e) >> 8) & 15u))) - 1u)))
             for (;;) {
-                /* fast iterations while both buffers have slack: two full refills (<= 14 bytes) cannot run out of input and
-                 * three literals + one match with its <= 7-byte copy overshoot (<= 268 bytes) cannot run out of output, so
-                 * there are no availability or bounds checks in here.  Bit budget per refill (>= 56): three codes of <= 15
-                 * bits and 5 length extra bits = 50; the distance (<= 15 + 13) gets its own refill. */
-                while (in_end - ip >= 16 && out_end - op >= 320) {
+                /* Fast iterations while both buffers have slack.  Invariant at the top: the buffer was just refilled (>= 56 bits) and
+                 * `e` is the primary-table entry of the symbol that starts at its low end.  One symbol per iteration -- a literal
+                 * (<= 15 bits) or a whole match (length <= 15 + 5, distance <= 15 + 13: 48 bits) -- then ONE refill (8 bytes read,
+                 * <= 7 consumed) and the lookup for the next symbol, issued before the match is copied.  in_end - ip >= 16 covers
+                 * the refill, out_end - op >= 320 a literal or a 258-byte match with its <= 7-byte copy overshoot: no
+                 * availability or bounds checks in here. */
+                if (in_end - ip >= 16 && out_end - op >= 320) {
                     bitbuf |= le64(ip) << bitcnt; ip += (63u - bitcnt) >> 3; bitcnt |= 56u;
                     uint32_t e = lit_tab[BITS(LIT_TBITS)];
-                    if (e & E_LINK) { DROP(LIT_TBITS); e = lit_tab[(e >> 16) + BITS((e >> 8) & 31u)]; }
-                    if (!(e & 0xffu)) return -1;
-                    DROP(e & 0xffu);
-                    if (e & E_LITERAL) {
-                        *op++ = (uint8_t)(e >> 16);
-                        e = lit_tab[BITS(LIT_TBITS)];
-                        if (e & E_LINK) { DROP(LIT_TBITS); e = lit_tab[(e >> 16) + BITS((e >> 8) & 31u)]; }
-                        if (!(e & 0xffu)) return -1;
+                    do {
+                        if (e & E_LINK) { DROP(LIT_TBITS); e = lit_tab[(e >> 16) + BITS((e >> 8) & 15u)]; }
+                        const uint64_t saved = bitbuf;
                         DROP(e & 0xffu);
                         if (e & E_LITERAL) {
-                            *op++ = (uint8_t)(e >> 16);
-                            e = lit_tab[BITS(LIT_TBITS)];
-                            if (e & E_LINK) { DROP(LIT_TBITS); e = lit_tab[(e >> 16) + BITS((e >> 8) & 31u)]; }
-                            if (!(e & 0xffu)) return -1;
-                            DROP(e & 0xffu);
-                            if (e & E_LITERAL) { *op++ = (uint8_t)(e >> 16); continue; }
+                            const uint8_t lit = (uint8_t)(e >> 16);
+                            e = lit_tab[BITS(LIT_TBITS)];                  /* >= 41 bits are left: look up first, refill behind it (a refill */
+                            bitbuf |= le64(ip) << bitcnt; ip += (63u - bitcnt) >> 3; bitcnt |= 56u;   /* only adds bits above the valid ones) */
+                            *op++ = lit;
+                            continue;
                         }
-                    }
-                    if (e & E_EOB) goto block_done;
-                    const uint32_t lx = (e >> 8) & 31u;
-                    const uint32_t len = (e >> 16) + BITS(lx); DROP(lx);
-                    bitbuf |= le64(ip) << bitcnt; ip += (63u - bitcnt) >> 3; bitcnt |= 56u;
-                    uint32_t d = dst_tab[BITS(DST_TBITS)];
-                    if (d & E_LINK) { DROP(DST_TBITS); d = dst_tab[(d >> 16) + BITS((d >> 8) & 31u)]; }
-                    if (!(d & 0xffu)) return -1;
-                    DROP(d & 0xffu);
-                    const uint32_t dx = (d >> 8) & 31u;
-                    const uint32_t dist = (d >> 16) + BITS(dx); DROP(dx);
-                    if (dist > (size_t)(op - out)) return -1;
-                    const uint8_t *src = op - dist;
-                    uint8_t *const stop = op + len;
-                    if (dist >= 8) {
-                        do { memcpy(op, src, 8); op += 8; src += 8; } while (op < stop);
-                    } else if (dist == 1) {
-                        memset(op, *src, len);
-                    } else {
-                        do { *op++ = *src++; } while (op < stop);
-                    }
-                    op = stop;
+                        if (!(e & 0xffu)) return -1;
+                        if (e & E_EOB) goto block_done;
+                        const uint32_t len = XVAL(e, saved);
+                        uint32_t d = dst_tab[BITS(DST_TBITS)];
+                        if (d & E_LINK) { DROP(DST_TBITS); d = dst_tab[(d >> 16) + BITS((d >> 8) & 15u)]; }
+                        if (!(d & 0xffu)) return -1;
+                        const uint32_t dist = XVAL(d, bitbuf);
+                        DROP(d & 0xffu);
+                        bitbuf |= le64(ip) << bitcnt; ip += (63u - bitcnt) >> 3; bitcnt |= 56u;
+                        e = lit_tab[BITS(LIT_TBITS)];                      /* next symbol's entry is on its way while the match is copied */
+                        if (dist > (size_t)(op - out)) return -1;
+                        const uint8_t *src = op - dist;
+                        uint8_t *const stop = op + len;
+                        if (dist >= 8) {
+                            /* two words unconditionally (most matches are shorter than 16 bytes: no data-dependent loop exit to
+                               mispredict); in this order they are right for distances 8..15 too */
+                            memcpy(op, src, 8); memcpy(op + 8, src + 8, 8);
+                            if (len > 16) { op += 16; src += 16; do { memcpy(op, src, 8); op += 8; src += 8; } while (op < stop); }
+                        } else if (dist == 1) {
+                            memset(op, *src, len);
+                        } else {
+                            do { *op++ = *src++; } while (op < stop);
+                        }
+                        op = stop;
+                    } while (in_end - ip >= 16 && out_end - op >= 320);
+                    /* (the entry loaded last is dropped: it consumed nothing, the careful code below looks it up again) */
                 }
                 REFILL();
                 uint32_t e = lit_tab[BITS(LIT_TBITS)];
-                if (e & E_LINK) { NEED(LIT_TBITS); DROP(LIT_TBITS); e = lit_tab[(e >> 16) + BITS((e >> 8) & 31u)]; }
+                if (e & E_LINK) { NEED(LIT_TBITS); DROP(LIT_TBITS); e = lit_tab[(e >> 16) + BITS((e >> 8) & 15u)]; }
                 if (!(e & 0xffu)) return -1;
-                NEED(e & 0xffu); DROP(e & 0xffu);
+                NEED(e & 0xffu);
+                const uint64_t saved = bitbuf;
+                DROP(e & 0xffu);
                 if (e & E_LITERAL) {
                     if (op >= out_end) return -1;
                     *op++ = (uint8_t)(e >> 16);
-                    /* a second literal from the same refill (>= 41 bits left) */
-                    e = lit_tab[BITS(LIT_TBITS)];
-                    if (e & E_LINK) { NEED(LIT_TBITS); DROP(LIT_TBITS); e = lit_tab[(e >> 16) + BITS((e >> 8) & 31u)]; }
-                    if (!(e & 0xffu)) return -1;
-                    NEED(e & 0xffu); DROP(e & 0xffu);
-                    if (e & E_LITERAL) {
-                        if (op >= out_end) return -1;
-                        *op++ = (uint8_t)(e >> 16);
-                        continue;
-                    }
+                    continue;
                 }
                 if (e & E_EOB) goto block_done;
-                /* length (extra bits: at most 5, still inside the same refill), then the distance after a fresh refill */
-                const uint32_t lx = (e >> 8) & 31u;
-                NEED(lx);
-                const uint32_t len = (e >> 16) + BITS(lx); DROP(lx);
+                /* the length came with its extra bits; the distance (<= 15 + 13 bits) after a fresh refill */
+                const uint32_t len = XVAL(e, saved);
                 REFILL();
                 uint32_t d = dst_tab[BITS(DST_TBITS)];
-                if (d & E_LINK) { NEED(DST_TBITS); DROP(DST_TBITS); d = dst_tab[(d >> 16) + BITS((d >> 8) & 31u)]; }
+                if (d & E_LINK) { NEED(DST_TBITS); DROP(DST_TBITS); d = dst_tab[(d >> 16) + BITS((d >> 8) & 15u)]; }
                 if (!(d & 0xffu)) return -1;
-                NEED(d & 0xffu); DROP(d & 0xffu);
-                const uint32_t dx = (d >> 8) & 31u;
-                NEED(dx);
-                const uint32_t dist = (d >> 16) + BITS(dx); DROP(dx);
+                NEED(d & 0xffu);
+                const uint32_t dist = XVAL(d, bitbuf);
+                DROP(d & 0xffu);
                 if (dist > (size_t)(op - out) || len > (size_t)(out_end - op)) return -1;
                 const uint8_t *src = op - dist;
                 if (dist >= 8 && (size_t)(out_end - op) >= (size_t)len + 8) {
@@ -280,6 +286,7 @@ int fi_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
                     op += len;
                 }
             }
+#undef XVAL
         block_done: ;
         }
         if (bfinal) break;

@@ -33,6 +33,9 @@ def corpus():
              bytes(nprng.integers(0, 256, 65536, dtype=np.uint8)), bytes(nprng.integers(0, 4, 65280, dtype=np.uint8)),
              bam[:65280], bam[65280:2 * 65280], bam[100000:100000 + 1500], bam[:17],
              b"".join(bytes([rng.randrange(256)]) * rng.randrange(1, 300) for _ in range(400))[:65280]]
+    # periodic data: long matches whose distance is shorter than the match (overlapping copies), one text per period around the
+    # 8- and 16-byte copy units of the decoder
+    texts += [bytes(rng.randrange(256) for _ in range(per)) * (9000 // per) + b"x" for per in (2, 3, 5, 7, 8, 9, 10, 12, 15, 16, 17, 23, 31, 33)]
     cases = []
     for t in texts:
         for level in (0, 1, 6, 9):
