@@ -5,6 +5,7 @@
 #include "bamio.h"
 #include "finflate.h"
 #include "crc32x.h"
+#include "hostthr.h"
 #include <ctype.h>
 #include <errno.h>
 #include <fcntl.h>
@@ -191,6 +192,8 @@ static void io_stop(bio_file *f)
 typedef struct { size_t in_off, in_len, out_off; uint32_t isize, crc; } bgzf_blk;
 typedef struct { const uint8_t *in; uint8_t *out; const bgzf_blk *blk; size_t nblk; int id, nthr; int err; uint64_t n_fast, n_zlib; } bgzf_job;
 
+static void *bgzf_worker(void *arg);
+static void *bgzf_worker_spawned(void *arg) { worker_step_back(); return bgzf_worker(arg); }
 static void *bgzf_worker(void *arg)
 {
     bgzf_job *j = arg;
@@ -264,7 +267,7 @@ static int bgzf_batch(bio_file *f, uint8_t *dst, size_t dst_cap, size_t *out_len
         pthread_t th[64]; bgzf_job job[64];
         for (int i = 0; i < nthr; i++) {
             job[i] = (bgzf_job){ f->cin, target, blk, nblk, i, nthr, 0, 0, 0 };
-            if (i && pthread_create(&th[i], NULL, bgzf_worker, &job[i])) { job[i].err = 2; }
+            if (i && pthread_create(&th[i], NULL, bgzf_worker_spawned, &job[i])) { job[i].err = 2; }
         }
         bgzf_worker(&job[0]);
         int err = job[0].err;
@@ -972,6 +975,8 @@ static int bgzf_flush_block(bio_file *f, const uint8_t *data, size_t n)
 /* ---- bulk output: whole blocks of a large buffer are packed (deflate / stored + CRC) on worker threads, written in order */
 #define BGZF_STORED_SIZE (BGZF_BLOCK + 31)     /* a full block of "-u" output: 18 header + 5 stored-block header + payload + 8 trailer */
 typedef struct { int level; const uint8_t *data; size_t nblk; uint8_t *out; size_t *olen; int id, nthr, err; size_t stride; } bgzf_wjob;
+static void *bgzf_wworker(void *arg);
+static void *bgzf_wworker_spawned(void *arg) { worker_step_back(); return bgzf_wworker(arg); }
 static void *bgzf_wworker(void *arg)
 {
     bgzf_wjob *j = arg;
@@ -1007,25 +1012,33 @@ int bio_write_raw(bio_file *f, const uint8_t *p, size_t n)
     enum { BATCH = 256 };
     int nthr = f->threads > 1 ? f->threads : 1;
     if (f->w_level == 0 && nthr > 4) nthr = 4;               /* stored blocks are a memcpy + CRC32: four threads outrun any pipe or disk */
-    while (n >= BGZF_BLOCK) {
+    /* stored blocks all have the same size: packed back to back, a batch leaves in one write */
+    const size_t stride = f->w_level == 0 ? BGZF_STORED_SIZE : BGZF_OUT_STRIDE;
+    if (n >= BGZF_BLOCK && !f->wout) {
+        f->wout = malloc((size_t)2 * BATCH * BGZF_OUT_STRIDE); f->wolen = malloc(sizeof(size_t) * 2 * BATCH);
+        if (!f->wout || !f->wolen) return -1;
+    }
+    /* two batch buffers: while this thread writes batch k (to a pipe that is the slow part), the workers pack batch k + 1 */
+    uint8_t *prev_out = NULL; size_t *prev_len = NULL; size_t prev_blk = 0; int which = 0, rc = 0;
+    while (n >= BGZF_BLOCK || prev_out) {
         size_t nblk = n / BGZF_BLOCK; if (nblk > BATCH) nblk = BATCH;
-        if (!f->wout) { f->wout = malloc((size_t)BATCH * BGZF_OUT_STRIDE); f->wolen = malloc(sizeof(size_t) * BATCH); if (!f->wout || !f->wolen) return -1; }
+        uint8_t *out = f->wout + (size_t)which * BATCH * BGZF_OUT_STRIDE; size_t *olen = f->wolen + (size_t)which * BATCH;
         int t = nthr; if ((size_t)t > nblk) t = (int)nblk;
-        /* stored blocks all have the same size: packed back to back, the batch leaves in one write */
-        const size_t stride = f->w_level == 0 ? BGZF_STORED_SIZE : BGZF_OUT_STRIDE;
-        pthread_t th[64]; bgzf_wjob job[64];
+        pthread_t th[64]; bgzf_wjob job[64]; int spawned[64];
+        const int overlap = prev_out != NULL && nblk > 0;       /* something to write meanwhile: every packing job goes to a spawned thread */
         for (int i = 0; i < t; i++) {
-            job[i] = (bgzf_wjob){ f->w_level, p, nblk, f->wout, f->wolen, i, t, 0, stride };
-            if (i && pthread_create(&th[i], NULL, bgzf_wworker, &job[i])) job[i].err = 2;
+            job[i] = (bgzf_wjob){ f->w_level, p, nblk, out, olen, i, t, 0, stride };
+            spawned[i] = (i || overlap) && pthread_create(&th[i], NULL, bgzf_wworker_spawned, &job[i]) == 0;
         }
-        bgzf_wworker(&job[0]);
-        int err = job[0].err;
-        for (int i = 1; i < t; i++) { if (job[i].err == 2) { job[i].err = 0; bgzf_wworker(&job[i]); } else pthread_join(th[i], NULL); err |= job[i].err; }
-        if (err) return -1;
-        if (f->w_level == 0) { if (fwrite(f->wout, 1, nblk * stride, f->fp) != nblk * stride) return -1; }
-        else for (size_t k = 0; k < nblk; k++)
-            if (fwrite(f->wout + k * BGZF_OUT_STRIDE, 1, f->wolen[k], f->fp) != f->wolen[k]) return -1;
+        if (prev_out && !rc) {
+            if (f->w_level == 0) { if (fwrite(prev_out, 1, prev_blk * stride, f->fp) != prev_blk * stride) rc = -1; }
+            else for (size_t k = 0; k < prev_blk && !rc; k++)
+                if (fwrite(prev_out + k * BGZF_OUT_STRIDE, 1, prev_len[k], f->fp) != prev_len[k]) rc = -1;
+        }
+        for (int i = 0; i < t; i++) { if (spawned[i]) pthread_join(th[i], NULL); else bgzf_wworker(&job[i]); if (job[i].err) rc = -1; }
+        prev_out = nblk ? out : NULL; prev_len = olen; prev_blk = nblk; which ^= 1;
         p += nblk * BGZF_BLOCK; n -= nblk * BGZF_BLOCK;
+        if (rc) return -1;
     }
     return n ? w_bytes(f, p, n) : 0;
 }

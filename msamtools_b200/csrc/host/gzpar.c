@@ -1,6 +1,7 @@
 /* gzpar.c -- gzip writer with concurrent deflate.  See gzpar.h. */
 #include "gzpar.h"
 #include "crc32x.h"
+#include "hostthr.h"
 #include <pthread.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -46,6 +47,8 @@ static void *gzp_worker(void *arg)
     return NULL;
 }
 
+static void *gzp_worker_spawned(void *arg) { worker_step_back(); return gzp_worker(arg); }
+
 /* deflate everything pending (final: close the deflate stream, even when nothing is pending) and write it */
 static int gzp_flush(gzp *g, int final)
 {
@@ -63,7 +66,7 @@ static int gzp_flush(gzp *g, int final)
     pthread_t th[64]; gzp_job job[64];
     for (int i = 0; i < t; i++) {
         job[i] = (gzp_job){ g, nblk, final, i, t, 0 };
-        if (i && pthread_create(&th[i], NULL, gzp_worker, &job[i])) job[i].err = 2;
+        if (i && pthread_create(&th[i], NULL, gzp_worker_spawned, &job[i])) job[i].err = 2;
     }
     gzp_worker(&job[0]);
     int err = job[0].err;

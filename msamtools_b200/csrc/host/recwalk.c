@@ -1,5 +1,6 @@
 /* recwalk.c -- verified multi-threaded record index.  See recwalk.h. */
 #include "recwalk.h"
+#include "hostthr.h"
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -83,6 +84,9 @@ static void *walk_main(void *arg)
     return NULL;
 }
 
+static void *guess_spawned(void *arg) { worker_step_back(); return guess_main(arg); }
+static void *walk_spawned(void *arg) { worker_step_back(); return walk_main(arg); }
+
 static int reserve(uint64_t **off, size_t *cap, size_t need)
 {
     if (need <= *cap) return 0;
@@ -132,7 +136,8 @@ int rw_index(const uint8_t *raw, size_t from, size_t len, int32_t n_targets, int
                 seg[t].stop_at = u < T ? seg[u].start : len;
             }
         void *(*fn)(void *) = phase ? walk_main : guess_main;
-        for (size_t t = 1; t < T; t++) started[t] = pthread_create(&th[t], NULL, fn, &seg[t]) == 0;
+        void *(*fn_spawned)(void *) = phase ? walk_spawned : guess_spawned;
+        for (size_t t = 1; t < T; t++) started[t] = pthread_create(&th[t], NULL, fn_spawned, &seg[t]) == 0;
         fn(&seg[0]);
         for (size_t t = 1; t < T; t++) { if (started[t]) pthread_join(th[t], NULL); else fn(&seg[t]); }
     }
