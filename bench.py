@@ -789,14 +789,17 @@ def run_ours(args):
         alg_step = tim["alg_bytes"] / args.steps
         if has_rec:       # A_out(rec) = 8 + B_rec + keep * B_rec: the records are read once and the survivors written once
             alg_step = raw_bytes + 8 * n_local + raw_bytes * kept_last / max(n_local, 1)
-        traffic = None
+        traffic = traffic_stale = None
         tpath = os.path.join(ROOT, "profiles", "decode_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 tj = json.load(fh)
-            if tj.get("source_stamp") == source_stamp(["msamtools_b200/csrc/decode.cuh", "msamtools_b200/csrc/common.cuh"]) \
-                    and tj.get("config_index") == key and abs(tj.get("records_per_launch", 0) - n_local / nchunks) < 1000:
-                traffic = tj.get("dram_bytes_per_launch")
+            if tj.get("config_index") == key and abs(tj.get("records_per_launch", 0) - n_local / nchunks) < 1000:
+                if tj.get("source_stamp") == source_stamp(["msamtools_b200/csrc/decode.cuh", "msamtools_b200/csrc/common.cuh"]):
+                    traffic = tj.get("dram_bytes_per_launch")
+                else:       # the kernel source changed after the ncu capture: `traffic` stays null, the last capture is shown as what it is
+                    traffic_stale = {"dram_bytes_per_launch": tj.get("dram_bytes_per_launch"), "measured_on_source_stamp": tj.get("source_stamp"),
+                                     "note": "ncu capture of an EARLIER build of this kernel (decode.cuh changed since); not this run's traffic"}
         line = {
             "metric": METRIC, "value": value, "unit": "M alignments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -809,7 +812,7 @@ def run_ours(args):
             "parity_checked": bool(parity_ok) if parity_ok is not None else False, "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "decode_kernel (record decode + fused filter statistics)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": traffic, "alg_bytes_per_launch": alg_per_launch, "launch_ms": dec_ms, "launches_per_step": launches / args.steps,
+                         "traffic": traffic, "traffic_last_capture": traffic_stale, "alg_bytes_per_launch": alg_per_launch, "launch_ms": dec_ms, "launches_per_step": launches / args.steps,
                          "full_scan_gbs": (raw_bytes + 8 * n_local) / nchunks / (dec_ms * 1e-3) / 1e9, "kernel_share_of_step": dec_ms * launches / args.steps / step_ms,
                          "step": {"alg_bytes": alg_step, "achieved": alg_step / (step_ms * 1e-3) / 1e9, "frac": alg_step / (step_ms * 1e-3) / 1e9 / peak}},
             "e2e": e2e,
