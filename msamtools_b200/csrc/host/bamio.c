@@ -35,6 +35,8 @@ struct bio_file {
     int threads, bgzf;
     uint8_t *cin; size_t cin_len;        /* view of the compressed bytes not yet consumed (inside io->mem[io_cur]) */
     struct io_ring *io; int io_cur, unbuffered;
+    int block_mode;                      /* bio_set_threads was called: BGZF input is read block-wise (read-ahead thread, finflate, CRC per
+                                            block) on `threads` inflate threads, 1 included; never called: zlib's streaming inflate */
     uint64_t ingest_bytes; double ingest_sec;
     uint64_t blocks_fast, blocks_zlib;   /* parallel path: blocks inflated by finflate.c / handed to zlib */
     /* name -> tid hash for SAM parsing */
@@ -70,7 +72,7 @@ static int grow(uint8_t **buf, size_t *cap, size_t need)
 /* ============================================================ decompressed byte stream */
 static double now_sec(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
-void bio_set_threads(bio_file *f, int n) { if (f) f->threads = n < 1 ? 1 : (n > 64 ? 64 : n); }
+void bio_set_threads(bio_file *f, int n) { if (f) { f->threads = n < 1 ? 1 : (n > 64 ? 64 : n); f->block_mode = 1; } }
 void bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds) { if (bytes) *bytes = f->ingest_bytes; if (seconds) *seconds = f->ingest_sec; }
 void bio_inflate_stats(const bio_file *f, uint64_t *fast_blocks, uint64_t *zlib_blocks) { if (fast_blocks) *fast_blocks = f->blocks_fast; if (zlib_blocks) *zlib_blocks = f->blocks_zlib; }
 
@@ -309,7 +311,7 @@ static int rd_fill_inner(bio_file *f)
         if (f->in_len < IN_CHUNK) f->in_eof = 1;
         f->compressed = f->in_len >= 2 && f->in[0] == 0x1f && f->in[1] == 0x8b;
         f->detected = 1;
-        if (f->compressed && f->threads > 1 && f->in_len >= 18 && (f->in[3] & 4) && f->in[12] == 'B' && f->in[13] == 'C') {
+        if (f->compressed && f->block_mode && f->in_len >= 18 && (f->in[3] & 4) && f->in[12] == 'B' && f->in[13] == 'C') {
             f->bgzf = 1;
             if (io_start(f, f->in, f->in_len, f->in_eof)) { set_err(f, "out of memory"); return -1; }
             return rd_fill_bgzf(f);

@@ -31,13 +31,15 @@ bio_hdr  *bio_read_header(bio_file *f);                       /* NULL on error *
 /* next record as a raw BAM record appended at (*buf)+(*len); grows *buf. 1 = record, 0 = EOF, <0 = error */
 int       bio_read_record(bio_file *f, const bio_hdr *h, uint8_t **buf, size_t *cap, size_t *len);
 /* BAM input, bulk: append bytes of the decompressed record stream at buf + *len, never beyond cap.  With worker threads
- * (bio_set_threads > 1) whole BGZF blocks are inflated straight into buf -- no intermediate copy; a record may end up
+ * (bio_set_threads) whole BGZF blocks are inflated straight into buf -- no intermediate copy; a record may end up
  * split across two calls, the caller walks the block_size chain itself.  1 = appended, 0 = EOF, -1 = error,
  * 2 = the next block does not fit in cap - *len.  May be mixed with bio_read_record only in the order records-then-raw. */
 int       bio_read_raw(bio_file *f, uint8_t *buf, size_t cap, size_t *len);
 const char *bio_error(const bio_file *f);
-/* BGZF input: inflate blocks on `n` worker threads (blocks are independent gzip members); default 1 (streaming inflate on the
- * caller's thread); call before bio_read_header.  BAM output: threads that pack blocks in bio_write_raw.                    */
+/* BGZF input: read block-wise -- a read-ahead thread, blocks (independent gzip members) inflated by the one-shot decoder of
+ * finflate.c on `n` threads (n = 1: the caller's) with zlib as fallback and the CRC checked either way; call before
+ * bio_read_header.  Never called: zlib's streaming inflate on the caller's thread (also what plain gzip input always gets).
+ * BAM output: threads that pack blocks in bio_write_raw.                                                                    */
 void      bio_set_threads(bio_file *f, int n);
 /* bytes of decompressed input produced so far / seconds spent producing them (read + inflate)  */
 void      bio_ingest_stats(const bio_file *f, uint64_t *bytes, double *seconds);

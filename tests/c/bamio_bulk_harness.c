@@ -13,7 +13,7 @@ int main(int argc, char **argv)
     if (argc < 5) return 2;
     bio_file *f = bio_open_read(argv[2]);
     if (!f) { fprintf(stderr, "open failed\n"); return 1; }
-    bio_set_threads(f, atoi(argv[3]));
+    if (atoi(argv[3]) > 0) bio_set_threads(f, atoi(argv[3]));     /* 0: never called = streaming zlib path */
     bio_hdr *h = bio_read_header(f);
     if (!h) { fprintf(stderr, "header: %s\n", bio_error(f)); return 1; }
     if (!strcmp(argv[1], "read")) {

@@ -10,7 +10,7 @@ int main(int argc, char **argv)
     if (argc < 3) return 2;
     bio_file *f = bio_open_read(argv[1]);
     if (!f) { fprintf(stderr, "open failed\n"); return 1; }
-    bio_set_threads(f, atoi(argv[2]));
+    if (atoi(argv[2]) > 0) bio_set_threads(f, atoi(argv[2]));     /* 0: never called = streaming zlib path */
     bio_hdr *h = bio_read_header(f);
     if (!h) { fprintf(stderr, "header: %s\n", bio_error(f)); return 1; }
     uint8_t *buf = NULL; size_t cap = 0, len = 0; int rc;

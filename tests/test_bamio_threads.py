@@ -47,16 +47,16 @@ def test_parallel_inflate_equals_streaming(harness, stream, level):
     import numpy as np
     samutil.write_bam(path, samutil.synth_header(names, tlen), names, tlen, np.frombuffer(raw, dtype=np.uint8), level=level)
     outs = {}
-    for thr in (1, 2, 5):
+    for thr in (0, 1, 2, 5):
         r = subprocess.run([exe, path, str(thr)], capture_output=True)
         assert r.returncode == 0, r.stderr.decode()
         outs[thr] = r.stdout
         fast, zl = (int(x) for x in r.stderr.decode().split()[1::2])
-        if thr == 1:
-            assert (fast, zl) == (0, 0)                 # streaming zlib path
+        if thr == 0:
+            assert (fast, zl) == (0, 0)                 # bio_set_threads never called: streaming zlib path
         else:
-            assert fast > 0 and zl == 0                 # every block of a zlib-written file is taken by the fast decoder
-    assert outs[1] == raw and outs[2] == raw and outs[5] == raw
+            assert fast > 0 and zl == 0                 # block-wise (one thread included): every block of a zlib-written file is taken by the fast decoder
+    assert outs[0] == raw and outs[1] == raw and outs[2] == raw and outs[5] == raw
 
 
 def test_pipe_input_through_the_read_ahead_thread(harness, stream):
@@ -91,7 +91,7 @@ def test_corrupt_block_is_reported(harness, stream):
     blob = bytearray(open(path, "rb").read())
     blob[len(blob) // 2] ^= 0x10                       # somewhere inside a block's deflate payload
     open(path, "wb").write(bytes(blob))
-    for thr in (1, 4):
+    for thr in (0, 1, 4):
         r = subprocess.run([exe, path, str(thr)], capture_output=True)
         assert r.returncode == 1 and (b"corrupt" in r.stderr or b"inflate" in r.stderr or b"CRC" in r.stderr or b"truncated" in r.stderr), r.stderr
 
@@ -118,7 +118,7 @@ def test_bulk_reader_into_fixed_buffer(bulk, stream, level):
     import numpy as np
     path = str(d / f"r{level}.bam")
     samutil.write_bam(path, samutil.synth_header(names, tlen), names, tlen, np.frombuffer(raw, dtype=np.uint8), level=level)
-    for thr in (1, 3):
+    for thr in (0, 1, 3):
         for cap in (70_000, 200_001, 64 << 20):
             r = subprocess.run([exe, "read", path, str(thr), str(cap)], capture_output=True)
             assert r.returncode == 0, r.stderr.decode()
