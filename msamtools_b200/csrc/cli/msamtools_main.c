@@ -733,14 +733,13 @@ static void write_rows(gzp *out, char **name, const double *v, size_t n, int thr
     for (size_t base = 0; base < n;) {
         int t = threads;
         if ((size_t)t * SLAB > n - base) t = (int)((n - base + SLAB - 1) / SLAB);
-        pthread_t th[16]; row_job job[16];
+        pthread_t th[16]; row_job job[16]; int spawned[16];
         for (int i = 0; i < t; i++) {
             size_t a = base + (size_t)i * SLAB, b = a + SLAB > n ? n : a + SLAB;
             job[i] = (row_job){ name, v, a, b, NULL, 0, 0 };
-            if (i && pthread_create(&th[i], NULL, row_worker, &job[i])) job[i].err = 2;
+            spawned[i] = i && pthread_create(&th[i], NULL, row_worker, &job[i]) == 0;
         }
-        row_worker(&job[0]);
-        for (int i = 1; i < t; i++) { if (job[i].err == 2) { job[i].err = 0; row_worker(&job[i]); } else pthread_join(th[i], NULL); }
+        for (int i = 0; i < t; i++) { if (spawned[i]) pthread_join(th[i], NULL); else row_worker(&job[i]); }
         for (int i = 0; i < t; i++) {
             if (job[i].err || gzp_write(out, job[i].buf, job[i].len)) mDie("Cannot write the profile");
             free(job[i].buf);

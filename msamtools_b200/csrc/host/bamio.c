@@ -266,14 +266,13 @@ static int bgzf_batch(bio_file *f, uint8_t *dst, size_t dst_cap, size_t *out_len
             target = f->dec;
         }
         int nthr = f->threads; if ((size_t)nthr > nblk) nthr = (int)nblk;
-        pthread_t th[64]; bgzf_job job[64];
+        pthread_t th[64]; bgzf_job job[64]; int spawned[64];
         for (int i = 0; i < nthr; i++) {
             job[i] = (bgzf_job){ f->cin, target, blk, nblk, i, nthr, 0, 0, 0 };
-            if (i && pthread_create(&th[i], NULL, bgzf_worker_spawned, &job[i])) { job[i].err = 2; }
+            spawned[i] = i && pthread_create(&th[i], NULL, bgzf_worker_spawned, &job[i]) == 0;
         }
-        bgzf_worker(&job[0]);
-        int err = job[0].err;
-        for (int i = 1; i < nthr; i++) { if (job[i].err == 2) { job[i].err = 0; bgzf_worker(&job[i]); } else pthread_join(th[i], NULL); err |= job[i].err; }
+        int err = 0;
+        for (int i = 0; i < nthr; i++) { if (spawned[i]) pthread_join(th[i], NULL); else bgzf_worker(&job[i]); err |= job[i].err; }
         for (int i = 0; i < nthr; i++) { f->blocks_fast += job[i].n_fast; f->blocks_zlib += job[i].n_zlib; }
         free(blk);
         if (err) { set_err(f, "corrupt BGZF block (inflate/CRC)"); return -1; }

@@ -63,14 +63,13 @@ static int gzp_flush(gzp *g, int final)
         if (!g->out || !g->olen || !g->bcrc) { g->out_blocks = 0; g->err = 1; return -1; }
     }
     int t = g->threads; if ((size_t)t > nblk) t = (int)nblk;
-    pthread_t th[64]; gzp_job job[64];
+    pthread_t th[64]; gzp_job job[64]; int spawned[64];
     for (int i = 0; i < t; i++) {
         job[i] = (gzp_job){ g, nblk, final, i, t, 0 };
-        if (i && pthread_create(&th[i], NULL, gzp_worker_spawned, &job[i])) job[i].err = 2;
+        spawned[i] = i && pthread_create(&th[i], NULL, gzp_worker_spawned, &job[i]) == 0;
     }
-    gzp_worker(&job[0]);
-    int err = job[0].err;
-    for (int i = 1; i < t; i++) { if (job[i].err == 2) { job[i].err = 0; gzp_worker(&job[i]); } else pthread_join(th[i], NULL); err |= job[i].err; }
+    int err = 0;
+    for (int i = 0; i < t; i++) { if (spawned[i]) pthread_join(th[i], NULL); else gzp_worker(&job[i]); err |= job[i].err; }
     if (err) { g->err = 1; return -1; }
     for (size_t k = 0; k < nblk; k++) {
         const size_t o = k * GZP_BLOCK, n = g->len - o < GZP_BLOCK ? g->len - o : GZP_BLOCK;

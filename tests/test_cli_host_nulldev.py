@@ -38,6 +38,7 @@ def cli(tmp_path_factory, request):
         pytest.skip("no gcc")
     d = str(tmp_path_factory.mktemp("nulldev_" + request.param.split(",")[0]))
     os.environ["ASAN_OPTIONS"] = "detect_leaks=0"            # a command-line tool: what it holds at exit is the OS's to free
+    os.environ["TSAN_OPTIONS"] = "report_thread_leaks=0"     # ... including the threads still running when a fatal error exits
     return build(d, request.param)
 
 
@@ -141,3 +142,25 @@ def test_sam_text_through_the_ring(cli):
     assert r.returncode == 0, r.stderr.decode()[-3000:]
     out = [l for l in r.stdout.decode().splitlines() if not l.startswith("@")]
     assert out == [l for l in lines[3:] if (int(l.split("\t")[3]) - 1) % 5 != 0]
+
+
+def test_error_paths_do_not_hang_or_leave_results(cli, bam, tmp_path):
+    """mid-stream corruption and truncation are fatal from the reader thread while the GPU and writer threads are busy (exit 1, message,
+    no profile file); a downstream process that closes the pipe early ends `filter` by SIGPIPE instead of leaving it blocked"""
+    path, raw, kept, names, tlen, n = bam
+    blob = open(path, "rb").read()
+    e = dict(os.environ, MSAMTOOLS_CHUNK_RECORDS="5000", MSAMTOOLS_THREADS="3")
+    bad = bytearray(blob)
+    bad[len(bad) * 2 // 3] ^= 0x5a
+    p1, p2, outp = str(tmp_path / "bad.bam"), str(tmp_path / "trunc.bam"), str(tmp_path / "p.gz")
+    open(p1, "wb").write(bad)
+    open(p2, "wb").write(blob[:len(blob) * 2 // 3])
+    r = subprocess.run([cli, "filter", "-b", "-u", "-l", "80", "--besthit", p1], capture_output=True, env=e, timeout=120)
+    assert r.returncode == 1 and b"Fatal Error: Cannot read input" in r.stderr, r.stderr[-500:]
+    r = subprocess.run([cli, "profile", "--label", "x", "-o", outp, p2], capture_output=True, env=e, timeout=120)
+    assert r.returncode == 1 and b"Fatal Error: Cannot read input" in r.stderr and not os.path.exists(outp), r.stderr[-500:]
+    p = subprocess.Popen([cli, "filter", "-b", "-u", "-l", "80", "--besthit", path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+    p.stdout.read(3_000_000)
+    p.stdout.close()
+    assert p.wait(timeout=120) == -13                       # SIGPIPE
+    p.stderr.close()
