@@ -46,7 +46,7 @@ def cli(tmp_path_factory, request):
 def bam(tmp_path_factory):
     from msamtools_b200 import synth
     d = tmp_path_factory.mktemp("nulldev_in")
-    p = synth.make_params("mixed", n_records=160_000, seed=11)            # ~ 48 MB of records
+    p = synth.make_params("mixed", n_records=115_000, seed=11)            # ~ 34 MB of records
     raw, off, _ = synth.generate(p)
     n = len(off) - 1
     raw = raw[:int(off[n])]
