@@ -36,7 +36,10 @@ def test_reference_suite_passes_on_ref_binary(ref_bin, suite, tmp_path):
 STREAMS = {"mixed": ("mixed", 40_000, 424242, {}),
            # second stream: few references, heavy clipping / indels, unmapped pairs, up to 12 occurrences per insert
            "clippy": ("community", 30_000, 7, dict(n_refs=12, ref_len_min=3_000, ref_len_max=9_000, clip_fraction=0.35, indel_fraction=0.25,
-                                                  unmapped_fraction=0.06, shared_fraction=0.45, single_fraction=0.15, max_occ=12))}
+                                                  unmapped_fraction=0.06, shared_fraction=0.45, single_fraction=0.15, max_occ=12)),
+           # third stream: a gene catalogue (10 000 short references, log-normal abundances, 30 % multi-mappers): the PropSharing loop
+           # of the restatement against the reference's own over thousands of features and lists
+           "catalog": ("catalog10k", 60_000, 2026, {})}
 
 
 @pytest.fixture(scope="module", params=list(STREAMS))
