@@ -266,6 +266,10 @@ static int bgzf_batch(bio_file *f, uint8_t *dst, size_t dst_cap, size_t *out_len
             target = f->dec;
         }
         int nthr = f->threads; if ((size_t)nthr > nblk) nthr = (int)nblk;
+        /* a level-0 stream (what `filter -u` pipes into `profile`) is a memcpy + CRC32 per block: four threads keep up with any pipe,
+           more only compete with the threads that feed it (first and last block of the batch are looked at: BTYPE 00 = stored) */
+        if (nthr > 4 && blk[0].in_len && blk[nblk - 1].in_len &&
+            ((f->cin[blk[0].in_off] >> 1) & 3u) == 0 && ((f->cin[blk[nblk - 1].in_off] >> 1) & 3u) == 0) nthr = 4;
         pthread_t th[64]; bgzf_job job[64]; int spawned[64];
         for (int i = 0; i < nthr; i++) {
             job[i] = (bgzf_job){ f->cin, target, blk, nblk, i, nthr, 0, 0, 0 };
