@@ -2,7 +2,7 @@
  * nulldev.c -- a NULL DEVICE behind include/msamtools_b200.h, for profiling the HOST side of the drop-in CLI
  * (reader thread, BGZF inflate, record index, QNAME split, record output, header and table writers) on a machine
  * without a GPU, and for testing that plumbing (tests/test_cli_host_nulldev.py, also under ThreadSanitizer).  TEST
- * INFRASTRUCTURE ONLY: it computes nothing -- `filter` "keeps" the records whose POS is not a multiple of 5 (one memcpy,
+ * INFRASTRUCTURE ONLY: it computes nothing -- `filter` "keeps" the records whose 0-based POS is not a multiple of 5 (or is absent) (one memcpy,
  * standing in for gather + D2H), `profile` returns a fixed pattern and the record count, `coverage` a fixed pattern -- so
  * its outputs say nothing about alignments and nothing in the product, the parity tests or bench.py's measured legs may
  * load it.  Built by tests/hostprof/run.py into
@@ -39,7 +39,7 @@ static int kept(const msg_ctx *c, size_t i)
 {
     const uint8_t *r = c->raw + c->off[i];
     const uint32_t pos = (uint32_t)r[8] | (uint32_t)r[9] << 8 | (uint32_t)r[10] << 16 | (uint32_t)r[11] << 24;
-    return pos % 5u != 0;
+    return pos == 0xffffffffu || pos % 5u != 0;           /* (POS 0 = no position is kept, so that unplaced records are exercised) */
 }
 int msg_kept_count(msg_ctx *c, size_t *n) { size_t k = 0; for (size_t i = 0; i < c->nrec; i++) k += (size_t)kept(c, i); *n = k; return MSG_OK; }
 int msg_pull_records(msg_ctx *c, uint8_t *out, size_t cap, size_t *nbytes, size_t *nrec)
