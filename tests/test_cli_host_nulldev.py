@@ -215,6 +215,8 @@ def _random_sam(n, seed):
                         for _ in range(rng.randrange(0, 6))]
                 aux.append(f"{t}:B:{sub}" + "".join("," + v for v in vals))
         flag = rng.choice([0, 16, 4, 77, 141, 99, 147, 256, 2048, 1024 + 83])
+        if rname == "*":                                      # an unplaced read: unmapped flag, no CIGAR (what aligners write)
+            flag, cigar = flag | 4, "*"
         pos = 0 if rname == "*" else 5 * rng.randrange(0, 100_000) + 2            # (the null device keeps POS % 5 != 0, 0-based)
         fields = [f"r{i // 2:05d}", str(flag), rname, str(pos), str(rng.randrange(0, 255)), cigar,
                   rng.choice(["=", "*", "A", "B"]) if rname != "*" else "*", str(rng.randrange(0, 10 ** 6)), str(rng.randrange(-10 ** 5, 10 ** 5)), seq, qual] + aux
@@ -254,3 +256,21 @@ def test_sam_text_round_trip_is_a_fixed_point(cli):
                 assert y[3] == "f" and abs(float(x[5:]) - float(y[5:])) <= 1e-6 * max(1.0, abs(float(x[5:]))), (x, y)
             else:
                 assert x[:6] == y[:6] and [float(v) for v in x[7:].split(",") if v] == [float(v) for v in y[7:].split(",") if v], (x, y)
+
+
+def test_sam_to_bam_encoding_matches_the_python_encoder(cli, tmp_path):
+    """the C host's SAM -> BAM record encoding (bin, smallest integer aux type, 4-bit sequence, '*' quality, B arrays) against
+    tests/samutil.py's independent encoder (the one the golden fixtures were built with), byte for byte, on the random lines"""
+    hdr = "@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:A\tLN:1000000\n@SQ\tSN:B\tLN:2000000\n"
+    lines = _random_sam(2000, 99)
+    r = subprocess.run([cli, "filter", "-S", "-b", "-l", "1", "-"], input=(hdr + "\n".join(lines) + "\n").encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    out = str(tmp_path / "o.bam")
+    open(out, "wb").write(r.stdout)
+    got = bytes(samutil.read_bam(out).raw)
+    want = [samutil.encode_record(l.split("\t"), {"A": 0, "B": 1}) for l in lines]
+    o = 0
+    for l, w in zip(lines, want):
+        assert got[o:o + len(w)] == w, l
+        o += len(w)
+    assert o == len(got)
