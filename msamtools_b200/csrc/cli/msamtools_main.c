@@ -275,8 +275,9 @@ typedef struct {
 
 /* chunk size: records / bytes per push (MSAMTOOLS_CHUNK_RECORDS / MSAMTOOLS_CHUNK_MB override, for tests and tuning) */
 static size_t env_size(const char *name, size_t dflt, size_t unit) { const char *e = getenv(name); return e && atol(e) > 0 ? (size_t)atol(e) * unit : dflt; }
-#define CHUNK_RECORDS env_size("MSAMTOOLS_CHUNK_RECORDS", (size_t)1 << 20, 1)
-#define CHUNK_BYTES   env_size("MSAMTOOLS_CHUNK_MB", (size_t)256 << 20, (size_t)1 << 20)
+#define CHUNK_RECORDS env_size("MSAMTOOLS_CHUNK_RECORDS", (size_t)1 << 19, 1)
+#define CHUNK_BYTES   env_size("MSAMTOOLS_CHUNK_MB", (size_t)128 << 20, (size_t)1 << 20)
+#define CHUNK_SLACK   ((size_t)32 << 20)     /* a buffer holds a chunk plus this: the last batch of blocks is cut to fit */
 #define NBUF 3
 
 static void gpu_die(msg_ctx *ctx) { mDie("%s", msg_last_error(ctx)); }
@@ -417,7 +418,7 @@ static void pull_kept_records(run_t *r, msg_ctx *ctx, wring_t *w, int *wcur)
         if (w->want_pinned) {
             /* kept records never exceed the chunk (--rescore may add an AS tag per record: then the buffer is simply replaced) */
             void *pm = NULL;
-            const size_t pcap = w->cap[i] > CHUNK_BYTES + ((size_t)64 << 20) ? w->cap[i] : CHUNK_BYTES + ((size_t)64 << 20);
+            const size_t pcap = w->cap[i] > CHUNK_BYTES + CHUNK_SLACK ? w->cap[i] : CHUNK_BYTES + CHUNK_SLACK;
             if (msg_host_alloc(r->cfg.device, pcap, &pm) == MSG_OK) { w->buf[i] = pm; w->cap[i] = pcap; w->pinned[i] = 1; }
         }
         if (!w->buf[i]) { w->buf[i] = malloc(w->cap[i]); if (!w->buf[i]) mDie("Out of memory"); }
@@ -453,7 +454,7 @@ static void ring_buffer_alloc(ring_t *g, int i, int pin)
        at full PCIe rate) once the input is large enough to pay for page-locking them */
     chunk_t *c = &g->buf[i];
     if (!g->bulk || c->raw) return;
-    c->fixed = 1; c->cap = CHUNK_BYTES + ((size_t)64 << 20);
+    c->fixed = 1; c->cap = CHUNK_BYTES + CHUNK_SLACK;
     void *pmem = NULL;
     if (pin && msg_host_alloc(g->r->cfg.device, c->cap, &pmem) == MSG_OK) { c->raw = pmem; c->pinned = 1; }
     else { c->raw = malloc(c->cap); if (!c->raw) mDie("Out of memory"); }
