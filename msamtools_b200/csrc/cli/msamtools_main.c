@@ -277,7 +277,8 @@ typedef struct {
 static size_t env_size(const char *name, size_t dflt, size_t unit) { const char *e = getenv(name); return e && atol(e) > 0 ? (size_t)atol(e) * unit : dflt; }
 #define CHUNK_RECORDS env_size("MSAMTOOLS_CHUNK_RECORDS", (size_t)1 << 19, 1)
 #define CHUNK_BYTES   env_size("MSAMTOOLS_CHUNK_MB", (size_t)128 << 20, (size_t)1 << 20)
-#define CHUNK_SLACK   ((size_t)32 << 20)     /* a buffer holds a chunk plus this: the last batch of blocks is cut to fit */
+#define CHUNK_SLACK   env_size("MSAMTOOLS_CHUNK_SLACK_KB", (size_t)32 << 20, (size_t)1 << 10)   /* a buffer holds a chunk plus this: the last batch of
+                                                                                             blocks is cut to fit (the override is for tests) */
 #define NBUF 3
 
 static void gpu_die(msg_ctx *ctx) { mDie("%s", msg_last_error(ctx)); }
@@ -292,6 +293,7 @@ typedef struct {
     int state[NBUF];                      /* 0 free, 1 posted */
     int posted_last;                      /* the posted chunk with this index is the final one (-1: not yet known) */
     int bulk, pin;                        /* pin: page-lock the chunk buffers (msg_host_alloc) */
+    size_t cap;                           /* capacity of every fixed buffer */
     pthread_mutex_t mu; pthread_cond_t cv;
 } ring_t;
 
@@ -454,7 +456,7 @@ static void ring_buffer_alloc(ring_t *g, int i, int pin)
        at full PCIe rate) once the input is large enough to pay for page-locking them */
     chunk_t *c = &g->buf[i];
     if (!g->bulk || c->raw) return;
-    c->fixed = 1; c->cap = CHUNK_BYTES + CHUNK_SLACK;
+    c->fixed = 1; c->cap = g->cap;
     void *pmem = NULL;
     if (pin && msg_host_alloc(g->r->cfg.device, c->cap, &pmem) == MSG_OK) { c->raw = pmem; c->pinned = 1; }
     else { c->raw = malloc(c->cap); if (!c->raw) mDie("Out of memory"); }
@@ -500,6 +502,10 @@ static msg_ctx *run_stream(run_t *r)
             /* (a pipe stays pageable: page-locking a buffer stalls the reader thread for ~0.1 s, and behind a pipe the staged
                copies are not what limits the stream) */
         }
+        /* a chunk plus slack -- and never less than what the QNAME pre-flight already read (100 000 records: more than a chunk
+           when records are long) */
+        g.cap = CHUNK_BYTES + CHUNK_SLACK;
+        if (r->chunk.len + CHUNK_SLACK > g.cap) g.cap = r->chunk.len + CHUNK_SLACK;
         ring_buffer_alloc(&g, 0, g.pin);                     /* the others are allocated by the reader thread when it first needs them */
         w.want_pinned = g.pin;
         {   /* the pre-flight records open buffer 0 */

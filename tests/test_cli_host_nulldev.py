@@ -61,6 +61,8 @@ def bam(tmp_path_factory):
 
 ENVS = [dict(MSAMTOOLS_CHUNK_RECORDS="7000", MSAMTOOLS_THREADS="4"),          # many chunks: ring, tails, writer hand-over
         dict(MSAMTOOLS_CHUNK_RECORDS="9000", MSAMTOOLS_THREADS="3", MSAMTOOLS_PINNED="1"),   # buffers from msg_host_alloc (input ring and output)
+        dict(MSAMTOOLS_CHUNK_MB="1", MSAMTOOLS_CHUNK_SLACK_KB="192", MSAMTOOLS_THREADS="4"),  # 1.2 MB buffers: ~30 bulk chunks, batches cut to fit,
+                                                                                              # tails carried from buffer to buffer
         dict(MSAMTOOLS_CHUNK_RECORDS="50000", MSAMTOOLS_THREADS="1"),        # streaming inflate, record index without threads
         dict(MSAMTOOLS_THREADS="8")]                                          # default chunk size: one chunk
 
@@ -69,8 +71,10 @@ ENVS = [dict(MSAMTOOLS_CHUNK_RECORDS="7000", MSAMTOOLS_THREADS="4"),          # 
 def test_filter_record_output_and_pipe_into_profile(cli, bam, env, tmp_path):
     path, raw, kept, names, tlen, n = bam
     e = dict(os.environ, MSAMTOOLS_TIMING="1", **env)
+    # (without --besthit `filter` reads no pre-flight sample, so the tiny-buffer case really runs on 1.2 MB buffers)
+    hit = [] if "MSAMTOOLS_CHUNK_SLACK_KB" in env else ["--besthit"]
     for mode in ("-bu", "-b"):
-        f = subprocess.run([cli, "filter", mode, "-l", "80", "--besthit", path], capture_output=True, env=e)
+        f = subprocess.run([cli, "filter", mode, "-l", "80"] + hit + [path], capture_output=True, env=e)
         assert f.returncode == 0, f.stderr.decode()[-3000:]
         out = str(tmp_path / "f.bam")
         open(out, "wb").write(f.stdout)
