@@ -140,9 +140,10 @@ def read_sam(path):
 
 
 def read_bam(path):
-    """BGZF = concatenated gzip members; python's gzip handles multi-member streams."""
-    with open(path, "rb") as fh:
-        data = gzip.decompress(fh.read())
+    """BGZF = concatenated gzip members; python's gzip handles multi-member streams (through the file object: gzip.decompress
+    re-slices the remaining input once per member, which is quadratic on files of thousands of blocks)."""
+    with gzip.open(path, "rb") as fh:
+        data = fh.read()
     assert data[:4] == b"BAM\1"
     l_text, = struct.unpack_from("<i", data, 4)
     text = data[8:8 + l_text].split(b"\0")[0].decode()

@@ -278,3 +278,32 @@ def test_sam_to_bam_encoding_matches_the_python_encoder(cli, tmp_path):
         assert got[o:o + len(w)] == w, l
         o += len(w)
     assert o == len(got)
+
+
+def test_long_records_through_small_buffers(cli, tmp_path):
+    """records of 150 b to 60 kb (long reads): more than a chunk in the pre-flight sample, few records per buffer, records
+    spanning many BGZF blocks -- the record stream comes out byte for byte through both filter paths and reaches `profile`"""
+    import random
+    rng = random.Random(5)
+    names, tlen = ["A", "B"], [5_000_000, 5_000_000]
+    recs = []
+    for i in range(900):
+        L = rng.choice([20000, 35000, 150, 60000])
+        seq = ("".join(rng.choice("ACGT") for _ in range(64)) * (L // 64 + 1))[:L]
+        f = [f"long{i // 2:05d}", "0", rng.choice(names), str(5 * rng.randrange(0, 900000) + 2), "60", f"{L}M", "*", "0", "0", seq, "*", "NM:i:3", "AS:i:100"]
+        recs.append(samutil.encode_record(f, {"A": 0, "B": 1}))
+    raw = b"".join(recs)
+    path = str(tmp_path / "long.bam")
+    samutil.write_bam(path, samutil.synth_header(names, tlen), names, tlen, np.frombuffer(raw, dtype=np.uint8), level=1)
+    for env in (dict(MSAMTOOLS_CHUNK_MB="1", MSAMTOOLS_CHUNK_SLACK_KB="192"), {}):
+        e = dict(os.environ, MSAMTOOLS_THREADS="4", **env)
+        for hit in ([], ["--besthit"]):
+            r = subprocess.run([cli, "filter", "-bu", "-l", "80"] + hit + [path], capture_output=True, env=e, timeout=300)
+            assert r.returncode == 0, r.stderr.decode()[-2000:]
+            out = str(tmp_path / "o.bam")
+            open(out, "wb").write(r.stdout)
+            assert bytes(samutil.read_bam(out).raw) == raw, (env, hit)
+        outp = str(tmp_path / "p.gz")
+        p = subprocess.run([cli, "profile", "--label", "x", "-o", outp, path], capture_output=True, env=e, timeout=300)
+        assert p.returncode == 0, p.stderr.decode()[-2000:]
+        assert any(c.startswith("# Mapped inserts") and " 900 (" in c for c in samutil.read_profile_gz(outp)[0])
